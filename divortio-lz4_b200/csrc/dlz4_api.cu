@@ -1,0 +1,875 @@
+// dlz4_api.cu -- C ABI (include/dlz4_b200.h) over the sm_100a kernels in dlz4_kernels.cuh.
+// Host code here only moves bytes, launches kernels and writes the frame header/footer; every block is
+// compressed, decoded and hashed on the GPU.  There is no CPU path.
+#include "../../include/dlz4_b200.h"
+#include "dlz4_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace dlz4;
+
+namespace {
+
+constexpr int kWarpsFresh16 = 7;     // 7 x 32 KiB tables = 224 KiB of the 227 KiB a CTA may own
+constexpr int kWarpsGeneric32 = 3;   // 3 x 64 KiB
+constexpr int kWarpsDecode = 8;
+
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct dlz4_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr, side = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_side = nullptr, ev_fork = nullptr;
+    uint32_t *d_counter = nullptr;      // work-queue heads (one per launch slot)
+    uint32_t *d_hash = nullptr;         // small result slots
+    uint64_t *d_total = nullptr;
+    int32_t *d_table = nullptr;         // int32[16384] scratch table
+    Buf work, comp, seg, out, meta, aux, pin;
+    std::string last_error;
+    uint64_t launches = 0;
+    float last_ms = 0.f;
+};
+
+namespace {
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            char m_[512];                                                                             \
+            snprintf(m_, sizeof m_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            ctx->last_error = m_;                                                                     \
+            return DLZ4_E_CUDA;                                                                       \
+        }                                                                                             \
+    } while (0)
+
+#define CKS(expr)                       \
+    do {                                \
+        int s_ = (expr);                \
+        if (s_ != DLZ4_OK) return s_;   \
+    } while (0)
+
+int reserve(dlz4_ctx *ctx, Buf &b, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes + 256 <= b.cap) return DLZ4_OK;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + 256;            // slack so aligned word reads at the very end stay inside
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return DLZ4_OK;
+}
+
+int reserve_pinned(dlz4_ctx *ctx, Buf &b, size_t bytes) {
+    if (bytes <= b.cap) return DLZ4_OK;
+    if (b.p) CK(cudaFreeHost(b.p));
+    b.p = nullptr; b.cap = 0;
+    CK(cudaMallocHost(&b.p, bytes));
+    b.cap = bytes;
+    return DLZ4_OK;
+}
+
+inline cudaStream_t pick(dlz4_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+// host xxh32 for the <= 14 header bytes only (FLG..dictID -> HC byte, bufferCompress.js:177-178)
+uint32_t header_xxh32(const uint8_t *p, size_t len) {
+    auto rd = [](const uint8_t *q) { return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24); };
+    auto rl = [](uint32_t x, int r) { return (x << r) | (x >> (32 - r)); };
+    const uint8_t *end = p + len;
+    uint32_t h = 374761393u + (uint32_t)len;        // len < 16 always
+    while (p + 4 <= end) { h = rl(h + rd(p) * 3266489917u, 17) * 668265263u; p += 4; }
+    while (p < end) { h = rl(h + (*p) * 374761393u, 11) * 2654435761u; ++p; }
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    return h;
+}
+
+inline void wr32(uint8_t *b, uint32_t v) { b[0] = (uint8_t)v; b[1] = (uint8_t)(v >> 8); b[2] = (uint8_t)(v >> 16); b[3] = (uint8_t)(v >> 24); }
+inline uint32_t rd32(const uint8_t *b) { return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24); }
+
+int block_id_for(uint64_t bytes) {          // bufferCompress.js:77-82
+    if (bytes == 0 || bytes <= 65536) return 4;
+    if (bytes <= 262144) return 5;
+    if (bytes <= 1048576) return 6;
+    return 7;
+}
+const uint32_t kBlockMax[8] = {0, 0, 0, 0, 65536, 262144, 1048576, 4194304};
+
+// ---- launch helpers ----------------------------------------------------------------------------------
+int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len, uint32_t n,
+                    uint32_t max_len, const uint8_t *prefix, uint32_t prefix_len, const int32_t *init_table, uint8_t *dst,
+                    const uint64_t *dst_off, uint32_t *comp_len, cudaStream_t st) {
+    if (n == 0) return DLZ4_OK;
+    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(uint32_t), st));
+    if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr) {
+        const int grid = (int)std::min<uint64_t>((n + kWarpsFresh16 - 1) / kWarpsFresh16, (uint64_t)ctx->sm_count);
+        k_compress_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * kHashEntries * 2, st>>>(
+            src, src_off, src_len, n, dst, dst_off, comp_len, ctx->d_counter);
+    } else {
+        const int grid = (int)std::min<uint64_t>((n + kWarpsGeneric32 - 1) / kWarpsGeneric32, (uint64_t)ctx->sm_count);
+        k_compress_generic32<kWarpsGeneric32><<<grid, kWarpsGeneric32 * 32, kWarpsGeneric32 * kHashEntries * 4, st>>>(
+            src, src_off, src_len, n, prefix, prefix_len, init_table, dst, dst_off, comp_len, ctx->d_counter);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DLZ4_OK;
+}
+
+int launch_decompress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len, uint32_t n,
+                      uint8_t *dst, const uint64_t *dst_off, const uint32_t *dst_cap, const uint8_t *dict, uint32_t dict_len,
+                      int hist_frame, const uint8_t *stored, uint32_t *out_len, uint8_t *status, cudaStream_t st) {
+    if (n == 0) return DLZ4_OK;
+    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(uint32_t), st));
+    const int grid = (int)std::min<uint64_t>((n + kWarpsDecode - 1) / kWarpsDecode, (uint64_t)ctx->sm_count * 8);
+    k_decompress_blocks<kWarpsDecode><<<grid, kWarpsDecode * 32, 0, st>>>(src, src_off, src_len, n, dst, dst_off, dst_cap, dict,
+                                                                           dict_len, hist_frame, stored, out_len, status, ctx->d_counter);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DLZ4_OK;
+}
+
+int launch_xxh32_batch(dlz4_ctx *ctx, const uint8_t *base, const uint64_t *off, const uint32_t *len, uint32_t n, uint32_t seed,
+                       uint32_t *out, uint8_t *append_base, cudaStream_t st) {
+    if (n == 0) return DLZ4_OK;
+    const uint64_t threads = (uint64_t)n * 4;
+    k_xxh32_batch<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(base, off, len, n, seed, out, append_base);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DLZ4_OK;
+}
+
+int launch_xxh32_stream(dlz4_ctx *ctx, const uint8_t *data, uint64_t len, uint32_t seed, uint32_t *out, cudaStream_t st) {
+    k_xxh32_stream<<<1, 32, 0, st>>>(data, len, seed, out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DLZ4_OK;
+}
+
+int launch_chain(dlz4_ctx *ctx, const uint8_t *work, int32_t start, int32_t total, int32_t block, uint32_t nblocks,
+                 int32_t *table_io, uint8_t *dst, uint64_t stride, uint32_t *comp_len, cudaStream_t st) {
+    k_compress_chain<<<1, 32, kHashEntries * 4, st>>>(work, start, total, block, nblocks, table_io, dst, stride, comp_len);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DLZ4_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int dlz4_init(int device, dlz4_ctx **out) {
+    if (!out) return DLZ4_E_INVALID_ARG;
+    *out = nullptr;
+    dlz4_ctx *ctx = new dlz4_ctx();
+    ctx->device = device;
+    *out = ctx;                       // returned even on failure so the caller can read last_error
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) { ctx->last_error = "no such CUDA device"; return DLZ4_E_CUDA; }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ctx->ev0));
+    CK(cudaEventCreate(&ctx->ev1));
+    CK(cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(cudaMalloc(&ctx->d_counter, 64));
+    CK(cudaMalloc(&ctx->d_hash, 64));
+    CK(cudaMalloc(&ctx->d_total, 64));
+    CK(cudaMalloc(&ctx->d_table, kHashEntries * sizeof(int32_t)));
+    CK(cudaFuncSetAttribute(k_compress_fresh16<kWarpsFresh16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            kWarpsFresh16 * kHashEntries * 2));
+    CK(cudaFuncSetAttribute(k_compress_generic32<kWarpsGeneric32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            kWarpsGeneric32 * kHashEntries * 4));
+    CK(cudaFuncSetAttribute(k_compress_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kHashEntries * 4));
+    return DLZ4_OK;
+}
+
+void dlz4_shutdown(dlz4_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->side) cudaStreamSynchronize(ctx->side);
+    for (Buf *b : {&ctx->work, &ctx->comp, &ctx->seg, &ctx->out, &ctx->meta, &ctx->aux})
+        if (b->p) cudaFree(b->p);
+    if (ctx->pin.p) cudaFreeHost(ctx->pin.p);
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->d_hash) cudaFree(ctx->d_hash);
+    if (ctx->d_total) cudaFree(ctx->d_total);
+    if (ctx->d_table) cudaFree(ctx->d_table);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
+    delete ctx;
+}
+
+const char *dlz4_strerror(int status) {
+    switch (status) {
+        case DLZ4_OK: return "ok";
+        case DLZ4_E_OUTPUT_TOO_SMALL: return "LZ4: Output Buffer Too Small";
+        case DLZ4_E_MALFORMED: return "LZ4: Malformed Input";
+        case DLZ4_E_OFFSET_ZERO: return "LZ4: Invalid Offset 0";
+        case DLZ4_E_DICT_OOB: return "LZ4: Dictionary Offset Out of Bounds";
+        case DLZ4_E_BAD_MAGIC: return "LZ4: Invalid Magic Number";
+        case DLZ4_E_BAD_VERSION: return "LZ4: Unsupported Version";
+        case DLZ4_E_CONTENT_CHECKSUM: return "LZ4: Content Checksum Error";
+        case DLZ4_E_BLOCK_CHECKSUM: return "LZ4: Block Checksum Error";
+        case DLZ4_E_HEADER_CHECKSUM: return "LZ4: Header Checksum Error";
+        case DLZ4_E_INVALID_ARG: return "dlz4: invalid argument";
+        case DLZ4_E_TOO_LARGE: return "dlz4: input of 2 GiB or more in one call";
+        case DLZ4_E_CUDA: return "dlz4: CUDA error";
+        default: return "dlz4: unknown status";
+    }
+}
+
+const char *dlz4_last_error(const dlz4_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+uint64_t dlz4_launch_count(const dlz4_ctx *ctx) { return ctx ? ctx->launches : 0; }
+float dlz4_last_kernel_ms(const dlz4_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
+
+uint64_t dlz4_compress_bound(uint64_t n) { return n + n / 255 + 16; }
+uint64_t dlz4_frame_bound(uint64_t n) { return 19 + n + (n / 65536 + 1) * 8 + 8 + 64; }
+
+void dlz4_shard_range(uint64_t nblocks, uint32_t world, uint32_t rank, uint64_t *first, uint64_t *count) {
+    if (world == 0) world = 1;
+    // block i belongs to rank floor(i * world / nblocks): rank r owns [ceil(r*n/w), ceil((r+1)*n/w))
+    const uint64_t lo = ((uint64_t)rank * nblocks + world - 1) / world;
+    const uint64_t hi = ((uint64_t)(rank + 1) * nblocks + world - 1) / world;
+    if (first) *first = lo;
+    if (count) *count = hi - lo;
+}
+
+// ---- pinned host memory for callers that want the full PCIe rate (N-API external ArrayBuffers) ---------
+void *dlz4_pinned_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void dlz4_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- batched raw blocks ---------------------------------------------------------------------------------
+int dlz4_compress_blocks_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len,
+                                uint32_t nblocks, uint32_t max_block_len, const uint8_t *prefix, uint32_t prefix_len, int warm,
+                                const int32_t *init_table, uint8_t *dst, const uint64_t *dst_off, uint32_t *comp_len,
+                                void *stream) {
+    if (!ctx) return DLZ4_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    const int32_t *table = nullptr;
+    if (warm == DLZ4_WARM_TABLE) {
+        if (!init_table) return DLZ4_E_INVALID_ARG;
+        table = init_table;
+    } else if (warm == DLZ4_WARM_JENKINS && prefix_len >= 4) {
+        CK(cudaMemsetAsync(ctx->d_table, 0, kHashEntries * sizeof(int32_t), st));
+        const int n = (int)prefix_len - 3;
+        k_warm_jenkins<<<(n + 255) / 256, 256, 0, st>>>(prefix, (int32_t)prefix_len, ctx->d_table);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        table = ctx->d_table;
+    } else if (warm != DLZ4_WARM_NONE && warm != DLZ4_WARM_JENKINS) {
+        return DLZ4_E_INVALID_ARG;
+    }
+    return launch_compress(ctx, src, src_off, src_len, nblocks, max_block_len, prefix, prefix_len, table, dst, dst_off, comp_len, st);
+}
+
+int dlz4_compress_blocks(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_bytes, const uint64_t *src_off, const uint32_t *src_len,
+                         uint32_t nblocks, const uint8_t *prefix, uint32_t prefix_len, int warm, const int32_t *init_table,
+                         uint8_t *dst, uint64_t dst_bytes, const uint64_t *dst_off, uint32_t *comp_len) {
+    if (!ctx || (nblocks && (!src_off || !src_len || !dst_off || !comp_len || !dst))) return DLZ4_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    uint32_t max_len = 0;
+    for (uint32_t i = 0; i < nblocks; ++i) {
+        if (src_off[i] + src_len[i] > src_bytes) return DLZ4_E_INVALID_ARG;
+        if (dst_off[i] + dlz4_compress_bound(src_len[i]) > dst_bytes) return DLZ4_E_OUTPUT_TOO_SMALL;
+        if (src_len[i] > max_len) max_len = src_len[i];
+        if (src_len[i] > 0x7FFFFFF0u - prefix_len) return DLZ4_E_TOO_LARGE;
+    }
+    const size_t meta_bytes = (size_t)nblocks * (8 + 4 + 8 + 4) + 64;
+    const uint64_t src_pad = (src_bytes + 15) & ~(uint64_t)15;
+    CKS(reserve(ctx, ctx->work, src_pad + prefix_len + 16));
+    CKS(reserve(ctx, ctx->comp, dst_bytes));
+    CKS(reserve(ctx, ctx->meta, meta_bytes));
+    uint8_t *d_src = (uint8_t *)ctx->work.p;
+    uint8_t *d_prefix = d_src + src_pad;
+    uint8_t *d_dst = (uint8_t *)ctx->comp.p;
+    uint64_t *d_soff = (uint64_t *)ctx->meta.p;
+    uint64_t *d_doff = d_soff + nblocks;
+    uint32_t *d_slen = (uint32_t *)(d_doff + nblocks);
+    uint32_t *d_clen = d_slen + nblocks;
+    CK(cudaMemcpyAsync(d_src, src, src_bytes, cudaMemcpyHostToDevice, st));
+    if (prefix_len) CK(cudaMemcpyAsync(d_prefix, prefix, prefix_len, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_soff, src_off, (size_t)nblocks * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_doff, dst_off, (size_t)nblocks * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_slen, src_len, (size_t)nblocks * 4, cudaMemcpyHostToDevice, st));
+    const int32_t *d_init = nullptr;
+    if (warm == DLZ4_WARM_TABLE) {
+        if (!init_table) return DLZ4_E_INVALID_ARG;
+        CKS(reserve(ctx, ctx->aux, kHashEntries * 4));
+        CK(cudaMemcpyAsync(ctx->aux.p, init_table, kHashEntries * 4, cudaMemcpyHostToDevice, st));
+        d_init = (const int32_t *)ctx->aux.p;
+    }
+    CK(cudaEventRecord(ctx->ev0, st));
+    CKS(dlz4_compress_blocks_dev(ctx, d_src, d_soff, d_slen, nblocks, max_len, prefix_len ? d_prefix : nullptr, prefix_len, warm,
+                                    d_init, d_dst, d_doff, d_clen, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaMemcpyAsync(comp_len, d_clen, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // bring back only the bytes each block produced
+    uint64_t lo = ~0ull, hi = 0;
+    for (uint32_t i = 0; i < nblocks; ++i) {
+        if (comp_len[i] == 0xFFFFFFFFu) return DLZ4_E_INVALID_ARG;
+        lo = std::min<uint64_t>(lo, dst_off[i]);
+        hi = std::max<uint64_t>(hi, dst_off[i] + comp_len[i]);
+    }
+    if (nblocks && hi > lo) CK(cudaMemcpyAsync(dst + lo, d_dst + lo, hi - lo, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return DLZ4_OK;
+}
+
+int dlz4_decompress_blocks_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len, uint32_t nblocks,
+                               uint8_t *dst, const uint64_t *dst_off, const uint32_t *dst_cap, const uint8_t *dict, uint32_t dict_len,
+                               int hist_mode, uint32_t *out_len, uint8_t *status, void *stream) {
+    if (!ctx) return DLZ4_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return launch_decompress(ctx, src, src_off, src_len, nblocks, dst, dst_off, dst_cap, dict_len ? dict : nullptr, dict_len,
+                             hist_mode == DLZ4_HIST_FRAME, nullptr, out_len, status, pick(ctx, stream));
+}
+
+int dlz4_decompress_blocks(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_bytes, const uint64_t *src_off, const uint32_t *src_len,
+                           uint32_t nblocks, uint8_t *dst, uint64_t dst_bytes, const uint64_t *dst_off, const uint32_t *dst_cap,
+                           const uint8_t *dict, uint32_t dict_len, int hist_mode, uint32_t *out_len, uint8_t *status) {
+    if (!ctx || (nblocks && (!src_off || !src_len || !dst_off || !dst_cap || !out_len || !status))) return DLZ4_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    for (uint32_t i = 0; i < nblocks; ++i) {
+        if (src_off[i] + src_len[i] > src_bytes) return DLZ4_E_INVALID_ARG;
+        if (dst_off[i] + dst_cap[i] > dst_bytes) return DLZ4_E_INVALID_ARG;
+    }
+    const uint64_t src_pad = (src_bytes + 15) & ~(uint64_t)15;
+    CKS(reserve(ctx, ctx->work, src_pad + dict_len + 16));
+    CKS(reserve(ctx, ctx->out, dst_bytes));
+    CKS(reserve(ctx, ctx->meta, (size_t)nblocks * (8 + 8 + 4 + 4 + 4 + 1) + 64));
+    uint8_t *d_src = (uint8_t *)ctx->work.p, *d_dict = d_src + src_pad, *d_dst = (uint8_t *)ctx->out.p;
+    uint64_t *d_soff = (uint64_t *)ctx->meta.p, *d_doff = d_soff + nblocks;
+    uint32_t *d_slen = (uint32_t *)(d_doff + nblocks), *d_cap = d_slen + nblocks, *d_olen = d_cap + nblocks;
+    uint8_t *d_status = (uint8_t *)(d_olen + nblocks);
+    CK(cudaMemcpyAsync(d_src, src, src_bytes, cudaMemcpyHostToDevice, st));
+    if (dict_len) CK(cudaMemcpyAsync(d_dict, dict, dict_len, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_soff, src_off, (size_t)nblocks * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_doff, dst_off, (size_t)nblocks * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_slen, src_len, (size_t)nblocks * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_cap, dst_cap, (size_t)nblocks * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev0, st));
+    CKS(launch_decompress(ctx, d_src, d_soff, d_slen, nblocks, d_dst, d_doff, d_cap, dict_len ? d_dict : nullptr, dict_len,
+                          hist_mode == DLZ4_HIST_FRAME, nullptr, d_olen, d_status, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaMemcpyAsync(out_len, d_olen, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, d_status, nblocks, cudaMemcpyDeviceToHost, st));
+    if (dst_bytes) CK(cudaMemcpyAsync(dst, d_dst, dst_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    for (uint32_t i = 0; i < nblocks; ++i)
+        if (status[i]) return status[i];
+    return DLZ4_OK;
+}
+
+// ---- single raw block (LZ4.compressRaw / LZ4.decompressRaw) ----------------------------------------------------
+int dlz4_compress_block(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_total, int32_t src_start, int32_t src_len, int32_t *table,
+                        uint8_t *output, uint64_t output_total, int32_t output_offset, int32_t *written) {
+    if (!ctx || !table || !written || src_start < 0 || src_len < 0 || output_offset < 0) return DLZ4_E_INVALID_ARG;
+    if ((uint64_t)src_start + (uint64_t)src_len > src_total) return DLZ4_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t need = (uint64_t)src_start + src_len;
+    const uint64_t bound = dlz4_compress_bound((uint64_t)src_len);
+    CKS(reserve(ctx, ctx->work, need + 16));
+    CKS(reserve(ctx, ctx->comp, bound));
+    CKS(reserve(ctx, ctx->aux, kHashEntries * 4 + 64));
+    int32_t *d_table = (int32_t *)ctx->aux.p;
+    uint32_t *d_clen = (uint32_t *)((uint8_t *)ctx->aux.p + kHashEntries * 4);
+    if (need) CK(cudaMemcpyAsync(ctx->work.p, src, need, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_table, table, kHashEntries * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev0, st));
+    CKS(launch_chain(ctx, (const uint8_t *)ctx->work.p, src_start, src_len, src_len > 0 ? src_len : 1, 1, d_table,
+                     (uint8_t *)ctx->comp.p, 0, d_clen, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    uint32_t clen = 0;
+    CK(cudaMemcpyAsync(&clen, d_clen, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(table, d_table, kHashEntries * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // the JS drops stores beyond output.length silently and still returns the full count (blockCompress.js has no checks)
+    uint64_t room = (uint64_t)output_offset < output_total ? output_total - output_offset : 0;
+    uint64_t ncopy = std::min<uint64_t>(clen, room);
+    if (ncopy) CK(cudaMemcpy(output + output_offset, ctx->comp.p, ncopy, cudaMemcpyDeviceToHost));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    *written = (int32_t)clen;
+    return DLZ4_OK;
+}
+
+int dlz4_decompress_block(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_total, int64_t input_offset, int64_t input_size,
+                          uint8_t *output, uint64_t output_total, int64_t output_offset, const uint8_t *dictionary, uint64_t dict_len,
+                          int64_t *written) {
+    if (!ctx || !written || input_offset < 0 || input_size < 0 || output_offset < 0) return DLZ4_E_INVALID_ARG;
+    if ((uint64_t)input_offset + (uint64_t)input_size > input_total || input_size > 0x7FFFFFFF) return DLZ4_E_INVALID_ARG;
+    if ((uint64_t)output_offset > output_total) return DLZ4_E_OUTPUT_TOO_SMALL;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (!dictionary) dict_len = 0;
+    // Matches reach at most 65535 bytes back: upload that much of output[0..outputOffset) as history and
+    // the tail of the dictionary (it is indexed from its end, blockDecompress.js:147).
+    const uint64_t hist = std::min<uint64_t>((uint64_t)output_offset, 65536);
+    const uint64_t dwin = std::min<uint64_t>(dict_len, 65536);
+    const uint64_t room = output_total - (uint64_t)output_offset;
+    const uint64_t cap = std::min<uint64_t>(room, (uint64_t)input_size * 255 + 64);   // a block cannot expand more than 255x
+    const uint64_t in_pad = ((uint64_t)input_size + 15) & ~15ull;
+    CKS(reserve(ctx, ctx->work, in_pad + dwin + 32));
+    CKS(reserve(ctx, ctx->out, hist + cap + 16));
+    CKS(reserve(ctx, ctx->meta, 256));
+    uint8_t *d_in = (uint8_t *)ctx->work.p, *d_dict = d_in + in_pad, *d_out = (uint8_t *)ctx->out.p;
+    if (input_size) CK(cudaMemcpyAsync(d_in, input + input_offset, (size_t)input_size, cudaMemcpyHostToDevice, st));
+    if (dwin) CK(cudaMemcpyAsync(d_dict, dictionary + (dict_len - dwin), dwin, cudaMemcpyHostToDevice, st));
+    if (hist) CK(cudaMemcpyAsync(d_out, output + (output_offset - hist), hist, cudaMemcpyHostToDevice, st));
+    // one block in frame-history mode: the device array's index 0 is `hist` bytes before the block
+    struct { uint64_t soff, doff; uint32_t slen, cap, olen; uint8_t status; } h = {0, hist, (uint32_t)input_size, (uint32_t)std::min<uint64_t>(cap, 0xFFFFFFFFu), 0, 0};
+    uint8_t *m = (uint8_t *)ctx->meta.p;
+    CK(cudaMemcpyAsync(m + 0, &h.soff, 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m + 8, &h.doff, 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m + 16, &h.slen, 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m + 20, &h.cap, 4, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev0, st));
+    // history shorter than the real one is only possible when output_offset > 65536, where no offset can reach index 0,
+    // so the dictionary branch (copySrc < 0) is taken exactly when the reference takes it.
+    const bool truncated = (uint64_t)output_offset > hist;
+    CKS(launch_decompress(ctx, d_in, (uint64_t *)(m + 0), (uint32_t *)(m + 16), 1, d_out, (uint64_t *)(m + 8), (uint32_t *)(m + 20),
+                          (dwin && !truncated) ? d_dict : nullptr, truncated ? 0 : (uint32_t)dwin, 1, nullptr, (uint32_t *)(m + 24), m + 28, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaMemcpyAsync(&h.olen, m + 24, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h.status, m + 28, 1, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    if (h.status) {
+        // a dictionary window shorter than the caller's dictionary can only turn an in-range reference into DICT_OOB when
+        // the reference reaches more than 64 KiB back, which the 16-bit offset cannot express
+        return h.status;
+    }
+    if (h.olen) CK(cudaMemcpy(output + output_offset, d_out + hist, h.olen, cudaMemcpyDeviceToHost));
+    *written = h.olen;
+    return DLZ4_OK;
+}
+
+// ---- xxHash32 ---------------------------------------------------------------------------------------------------
+int dlz4_xxh32_batch_dev(dlz4_ctx *ctx, const uint8_t *base, const uint64_t *off, const uint32_t *len, uint32_t n, uint32_t seed,
+                         uint32_t *out, void *stream) {
+    if (!ctx) return DLZ4_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return launch_xxh32_batch(ctx, base, off, len, n, seed, out, nullptr, pick(ctx, stream));
+}
+
+int dlz4_xxh32_stream_dev(dlz4_ctx *ctx, const uint8_t *data, uint64_t len, uint32_t seed, uint32_t *out, void *stream) {
+    if (!ctx) return DLZ4_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return launch_xxh32_stream(ctx, data, len, seed, out, pick(ctx, stream));
+}
+
+int dlz4_xxh32(dlz4_ctx *ctx, const uint8_t *data, uint64_t len, uint32_t seed, uint32_t *out) {
+    if (!ctx || !out) return DLZ4_E_INVALID_ARG;
+    if (len >= 0x80000000ull) return DLZ4_E_TOO_LARGE;       // xxhash32.js:23 len|0
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CKS(reserve(ctx, ctx->work, len + 16));
+    if (len) CK(cudaMemcpyAsync(ctx->work.p, data, len, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev0, st));
+    CKS(launch_xxh32_stream(ctx, (const uint8_t *)ctx->work.p, len, seed, ctx->d_hash, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaMemcpyAsync(out, ctx->d_hash, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return DLZ4_OK;
+}
+
+int dlz4_xxh32_batch(dlz4_ctx *ctx, const uint8_t *base, uint64_t base_bytes, const uint64_t *off, const uint32_t *len, uint32_t n,
+                     uint32_t seed, uint32_t *out) {
+    if (!ctx || (n && (!off || !len || !out))) return DLZ4_E_INVALID_ARG;
+    for (uint32_t i = 0; i < n; ++i)
+        if (off[i] + len[i] > base_bytes) return DLZ4_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CKS(reserve(ctx, ctx->work, base_bytes + 16));
+    CKS(reserve(ctx, ctx->meta, (size_t)n * 16 + 64));
+    uint64_t *d_off = (uint64_t *)ctx->meta.p;
+    uint32_t *d_len = (uint32_t *)(d_off + n), *d_out = d_len + n;
+    if (base_bytes) CK(cudaMemcpyAsync(ctx->work.p, base, base_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_off, off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_len, len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev0, st));
+    CKS(launch_xxh32_batch(ctx, (const uint8_t *)ctx->work.p, d_off, d_len, n, seed, d_out, nullptr, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return DLZ4_OK;
+}
+
+// ---- frame packing on the device -----------------------------------------------------------------------------------
+int dlz4_frame_pack_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len, const uint8_t *comp,
+                        const uint64_t *comp_off, const uint32_t *comp_len, uint32_t nblocks, int block_checksum, uint8_t *segment,
+                        uint64_t *block_pos, void *stream) {
+    if (!ctx) return DLZ4_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    CKS(reserve(ctx, ctx->aux, (size_t)nblocks * 12 + kHashEntries * 4 + 256));
+    uint64_t *d_doff = (uint64_t *)((uint8_t *)ctx->aux.p + kHashEntries * 4 + 64);
+    uint32_t *d_dlen = (uint32_t *)(d_doff + nblocks);
+    k_frame_layout<<<1, 1024, 0, st>>>(src_len, comp_len, nblocks, block_checksum, block_pos, d_doff, d_dlen);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (nblocks) {
+        const int grid = (int)std::min<uint64_t>(nblocks, (uint64_t)ctx->sm_count * 8);
+        k_frame_gather<<<grid, 256, 0, st>>>(src, src_off, src_len, comp, comp_off, comp_len, nblocks, block_pos, segment);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        if (block_checksum) CKS(launch_xxh32_batch(ctx, segment, d_doff, d_dlen, nblocks, 0, nullptr, segment, st));
+    }
+    return DLZ4_OK;
+}
+
+// ---- frame compress (compressBuffer) ---------------------------------------------------------------------------------
+int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len, const uint8_t *dictionary, uint64_t dict_len,
+                        const dlz4_frame_opts *opts, uint8_t *output, uint64_t output_cap, uint64_t *output_len) {
+    if (!ctx || !opts || !output_len || (input_len && !input)) return DLZ4_E_INVALID_ARG;
+    if (input_len >= 0x7FFF0000ull) return DLZ4_E_TOO_LARGE;            // bufferCompress.js:127 len|0
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const bool have_dict = dictionary && dict_len > 0;                  // :109
+    const uint64_t dwin = have_dict ? std::min<uint64_t>(dict_len, 65536) : 0;   // :115
+    const int bd = block_id_for(opts->max_block_size);                  // :128
+    const uint32_t B = kBlockMax[bd];
+    const uint32_t n = (uint32_t)((input_len + B - 1) / B);
+    const uint64_t stride = (dlz4_compress_bound(B) + 15) & ~15ull;
+
+    // device staging: work = dictionary window ++ input (the reference's workingBuffer, :121-124)
+    const uint64_t dpad = (dwin + 15) & ~15ull;                          // keep the input 16-byte aligned
+    CKS(reserve(ctx, ctx->work, dict_len + dpad + input_len + 64));
+    uint8_t *d_work = (uint8_t *)ctx->work.p + (dpad - dwin);            // dictionary window directly before the input
+    uint8_t *d_in = d_work + dwin;
+    uint8_t *d_fulldict = (uint8_t *)ctx->work.p + dpad + ((input_len + 15) & ~15ull);
+    CKS(reserve(ctx, ctx->comp, (uint64_t)n * stride + 64));
+    CKS(reserve(ctx, ctx->seg, input_len + (uint64_t)n * 8 + 64));
+    CKS(reserve(ctx, ctx->meta, (size_t)n * (8 + 8 + 4 + 4) + 8 * ((size_t)n + 1) + 64));
+    uint64_t *d_soff = (uint64_t *)ctx->meta.p, *d_coff = d_soff + n, *d_pos = d_coff + n;
+    uint32_t *d_slen = (uint32_t *)(d_pos + n + 1), *d_clen = d_slen + n;
+
+    if (input_len) CK(cudaMemcpyAsync(d_in, input, input_len, cudaMemcpyHostToDevice, st));
+    if (dwin) CK(cudaMemcpyAsync(d_work, dictionary + (dict_len - dwin), dwin, cudaMemcpyHostToDevice, st));
+
+    // header (host, bufferCompress.js:147-178)
+    uint8_t hdr[32];
+    size_t hp = 0;
+    wr32(hdr, 0x184D2204u); hp = 4;
+    uint8_t flg = 1 << 6;
+    if (opts->block_independence) flg |= 0x20;
+    if (opts->content_checksum) flg |= 0x04;
+    if (have_dict) flg |= 0x01;
+    if (opts->add_content_size) flg |= 0x08;
+    if (opts->block_checksum) flg |= 0x10;
+    hdr[hp++] = flg;
+    hdr[hp++] = (uint8_t)((bd & 7) << 4);
+    if (opts->add_content_size) { wr32(hdr + hp, (uint32_t)input_len); wr32(hdr + hp + 4, 0); hp += 8; }
+    uint32_t dict_id = 0;
+    if (have_dict) {                                                    // :112 dictId = xxHash32(dict) on the GPU
+        if (dict_len > dwin) {
+            CK(cudaMemcpyAsync(d_fulldict, dictionary, dict_len, cudaMemcpyHostToDevice, ctx->side));
+            CKS(launch_xxh32_stream(ctx, d_fulldict, dict_len, 0, ctx->d_hash + 1, ctx->side));
+        } else {
+            CK(cudaEventRecord(ctx->ev_fork, st));
+            CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+            CKS(launch_xxh32_stream(ctx, d_work, dwin, 0, ctx->d_hash + 1, ctx->side));
+        }
+        CK(cudaMemcpyAsync(&dict_id, ctx->d_hash + 1, 4, cudaMemcpyDeviceToHost, ctx->side));
+        CK(cudaStreamSynchronize(ctx->side));
+        wr32(hdr + hp, dict_id); hp += 4;
+    }
+    hdr[hp] = (uint8_t)((header_xxh32(hdr + 4, hp - 4) >> 8) & 0xFF); hp++;
+
+    // content checksum: serial xxh32 over the whole input on the side stream, overlapped with the block kernels (:248-252)
+    if (opts->content_checksum) {
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        CKS(launch_xxh32_stream(ctx, d_in, input_len, 0, ctx->d_hash, ctx->side));
+        CK(cudaEventRecord(ctx->ev_side, ctx->side));
+    }
+
+    CK(cudaEventRecord(ctx->ev0, st));
+    uint64_t seg_len = 0;
+    if (n) {
+        k_uniform_blocks<<<(n + 255) / 256, 256, 0, st>>>((uint64_t)(d_in - d_work), input_len, B, n, d_soff, d_slen, d_coff, stride);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        uint8_t *d_comp = (uint8_t *)ctx->comp.p;
+        if (!opts->block_independence) {
+            // linked blocks: one serial chain, table and history carried across blocks (:182,:219,:234)
+            CK(cudaMemsetAsync(ctx->d_table, 0, kHashEntries * 4, st));
+            if (dwin >= 4) { k_warm_jenkins<<<((int)dwin - 3 + 255) / 256, 256, 0, st>>>(d_work, (int32_t)dwin, ctx->d_table); ctx->launches++; }
+            CKS(launch_chain(ctx, d_work, (int32_t)dwin, (int32_t)input_len, (int32_t)B, n, ctx->d_table, d_comp, stride, d_clen, st));
+        } else {
+            uint32_t first = 0;
+            if (dwin) {
+                // block 0 alone sees the dictionary prefix and the Jenkins-warmed table (:186-204); the table is
+                // cleared after it (:234-236), so every later block is a fresh independent block
+                CK(cudaMemsetAsync(ctx->d_table, 0, kHashEntries * 4, st));
+                if (dwin >= 4) { k_warm_jenkins<<<((int)dwin - 3 + 255) / 256, 256, 0, st>>>(d_work, (int32_t)dwin, ctx->d_table); ctx->launches++; }
+                const int32_t l0 = (int32_t)std::min<uint64_t>(B, input_len);
+                CKS(launch_chain(ctx, d_work, (int32_t)dwin, l0, l0, 1, ctx->d_table, d_comp, stride, d_clen, st));
+                first = 1;
+            }
+            CKS(launch_compress(ctx, d_work, d_soff + first, d_slen + first, n - first, B, nullptr, 0, nullptr, d_comp, d_coff + first,
+                                d_clen + first, st));
+        }
+        CKS(dlz4_frame_pack_dev(ctx, d_work, d_soff, d_slen, d_comp, d_coff, d_clen, n, opts->block_checksum, (uint8_t *)ctx->seg.p,
+                                d_pos, st));
+        CK(cudaMemcpyAsync(&seg_len, d_pos + n, 8, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+
+    const uint64_t total = hp + seg_len + 4 + (opts->content_checksum ? 4 : 0);
+    *output_len = total;
+    // an undersized outputBuffer truncates silently in the reference (typed-array stores are dropped); same here
+    std::vector<uint8_t> tail;
+    uint64_t pos = 0;
+    auto put = [&](const uint8_t *p, uint64_t len) {
+        if (pos < output_cap) memcpy(output + pos, p, (size_t)std::min<uint64_t>(len, output_cap - pos));
+        pos += len;
+    };
+    put(hdr, hp);
+    if (seg_len) {
+        if (pos < output_cap)
+            CK(cudaMemcpyAsync(output + pos, ctx->seg.p, (size_t)std::min<uint64_t>(seg_len, output_cap - pos), cudaMemcpyDeviceToHost, st));
+        pos += seg_len;
+    }
+    uint8_t foot[8] = {0, 0, 0, 0, 0, 0, 0, 0};                           // EndMark (:244)
+    if (opts->content_checksum) {
+        uint32_t hsh = 0;
+        CK(cudaMemcpyAsync(&hsh, ctx->d_hash, 4, cudaMemcpyDeviceToHost, ctx->side));
+        CK(cudaStreamSynchronize(ctx->side));
+        wr32(foot + 4, hsh);
+    }
+    put(foot, opts->content_checksum ? 8 : 4);
+    CK(cudaStreamSynchronize(st));
+    return DLZ4_OK;
+}
+
+// ---- frame decompress (decompressBuffer) -------------------------------------------------------------------------------
+static int parse_header(const uint8_t *f, uint64_t len, dlz4_frame_info_t *info, uint64_t *body_pos) {
+    memset(info, 0, sizeof *info);
+    if (len < 4 || rd32(f) != 0x184D2204u) return DLZ4_E_BAD_MAGIC;      // bufferDecompress.js:59-61
+    if (len < 5) { info->version = 0; return DLZ4_E_BAD_VERSION; }
+    uint64_t pos = 4;
+    const uint8_t flg = f[pos++];
+    info->flg = flg;
+    info->version = (flg & 0xC0) >> 6;
+    if (info->version != 1) return DLZ4_E_BAD_VERSION;                  // :67
+    info->has_block_checksum = (flg & 0x10) != 0;
+    info->has_content_size = (flg & 0x08) != 0;
+    info->has_content_checksum = (flg & 0x04) != 0;
+    info->has_dict_id = (flg & 0x01) != 0;
+    info->block_independence = (flg & 0x20) != 0;
+    if (pos >= len) return DLZ4_E_MALFORMED;
+    info->bd = f[pos++];                                                // :75 (the JS skips it; we use it to size buffers)
+    const int bid = (info->bd >> 4) & 7;
+    info->block_max_size = bid >= 4 ? kBlockMax[bid] : 4194304u;
+    if (info->has_content_size) {
+        if (pos + 8 > len) return DLZ4_E_MALFORMED;
+        info->content_size = (uint64_t)rd32(f + pos) | ((uint64_t)rd32(f + pos + 4) << 32);   // :81-85
+        pos += 8;
+    }
+    if (info->has_dict_id) {
+        if (pos + 4 > len) return DLZ4_E_MALFORMED;
+        info->dict_id = rd32(f + pos);
+        pos += 4;
+    }
+    pos += 1;                                                           // :92 header checksum
+    if (pos > len) return DLZ4_E_MALFORMED;
+    *body_pos = pos;
+    return DLZ4_OK;
+}
+
+struct BlockRef { uint64_t off; uint32_t len; uint8_t stored; };
+
+static int walk_blocks(const uint8_t *f, uint64_t len, const dlz4_frame_info_t *info, uint64_t pos, std::vector<BlockRef> *blocks,
+                       uint64_t *end_pos) {
+    while (pos < len) {                                                  // :133
+        if (pos + 4 > len) return DLZ4_E_MALFORMED;
+        const uint32_t bs = rd32(f + pos);
+        pos += 4;
+        if (bs == 0) break;                                              // :139 EndMark
+        const uint32_t actual = bs & 0x7FFFFFFFu;
+        if (pos + actual > len) return DLZ4_E_MALFORMED;
+        if (blocks) blocks->push_back({pos, actual, (uint8_t)((bs >> 31) & 1)});
+        pos += actual;
+        if (info->has_block_checksum) pos += 4;                          // :191
+    }
+    *end_pos = pos;
+    return DLZ4_OK;
+}
+
+int dlz4_frame_info(const uint8_t *frame, uint64_t frame_len, dlz4_frame_info_t *info) {
+    if (!frame || !info) return DLZ4_E_INVALID_ARG;
+    uint64_t pos = 0, end = 0;
+    int s = parse_header(frame, frame_len, info, &pos);
+    if (s) return s;
+    std::vector<BlockRef> blocks;
+    s = walk_blocks(frame, frame_len, info, pos, &blocks, &end);
+    if (s) return s;
+    info->nblocks = (uint32_t)blocks.size();
+    uint64_t bound = 0;
+    for (const BlockRef &b : blocks) bound += b.stored ? b.len : std::min<uint64_t>((uint64_t)b.len * 255, info->block_max_size);
+    info->max_decoded = info->content_size ? info->content_size : bound;
+    return DLZ4_OK;
+}
+
+int dlz4_frame_decompress(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_len, const uint8_t *dictionary, uint64_t dict_len,
+                          uint32_t flags, uint8_t *output, uint64_t output_cap, uint64_t *output_len) {
+    if (!ctx || !frame || !output_len) return DLZ4_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    dlz4_frame_info_t info;
+    uint64_t pos = 0, end = 0;
+    CKS(parse_header(frame, frame_len, &info, &pos));
+    if ((flags & 4u)) {
+        const uint64_t hc_pos = pos - 1;
+        if ((uint8_t)((header_xxh32(frame + 4, (size_t)(hc_pos - 4)) >> 8) & 0xFF) != frame[hc_pos]) return DLZ4_E_HEADER_CHECKSUM;
+    }
+    std::vector<BlockRef> blocks;
+    CKS(walk_blocks(frame, frame_len, &info, pos, &blocks, &end));
+    const uint32_t n = (uint32_t)blocks.size();
+    if (!dictionary) dict_len = 0;
+    const uint64_t dwin = std::min<uint64_t>(dict_len, 65536);
+    const uint32_t B = info.block_max_size;
+
+    // capacity the decode may use: the reference allocates contentSize when present (:107), otherwise grows as needed
+    uint64_t cap_total = info.content_size ? info.content_size : 0;
+    if (!info.content_size) {
+        for (const BlockRef &b : blocks) cap_total += b.stored ? b.len : std::min<uint64_t>((uint64_t)b.len * 255, B);
+    }
+    if (cap_total > output_cap) cap_total = output_cap;
+
+    const uint64_t fpad = (frame_len + 15) & ~15ull;
+    CKS(reserve(ctx, ctx->work, fpad + dwin + 32));
+    CKS(reserve(ctx, ctx->out, cap_total + 64));
+    CKS(reserve(ctx, ctx->meta, (size_t)n * (8 + 8 + 4 + 4 + 4 + 1 + 1 + 4) + 256));
+    uint8_t *d_frame = (uint8_t *)ctx->work.p, *d_dict = d_frame + fpad, *d_out = (uint8_t *)ctx->out.p;
+    uint64_t *d_soff = (uint64_t *)ctx->meta.p, *d_doff = d_soff + n;
+    uint32_t *d_slen = (uint32_t *)(d_doff + n), *d_cap = d_slen + n, *d_olen = d_cap + n, *d_bhash = d_olen + n;
+    uint8_t *d_status = (uint8_t *)(d_bhash + n), *d_stored = d_status + n;
+
+    CK(cudaMemcpyAsync(d_frame, frame, frame_len, cudaMemcpyHostToDevice, st));
+    if (dwin) CK(cudaMemcpyAsync(d_dict, dictionary + (dict_len - dwin), dwin, cudaMemcpyHostToDevice, st));
+
+    std::vector<uint64_t> soff(n), doff(n);
+    std::vector<uint32_t> slen(n), cap(n), olen(n), bhash(n);
+    std::vector<uint8_t> status(n), stored(n);
+    for (uint32_t i = 0; i < n; ++i) { soff[i] = blocks[i].off; slen[i] = blocks[i].len; stored[i] = blocks[i].stored; }
+    CK(cudaMemcpyAsync(d_soff, soff.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_slen, slen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_stored, stored.data(), n, cudaMemcpyHostToDevice, st));
+
+    if ((flags & 2u) && info.has_block_checksum && n) {                  // addition: verify block checksums on the GPU
+        CKS(launch_xxh32_batch(ctx, d_frame, d_soff, d_slen, n, 0, d_bhash, nullptr, st));
+        CK(cudaMemcpyAsync(bhash.data(), d_bhash, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    }
+
+    CK(cudaEventRecord(ctx->ev0, st));
+    uint64_t total = 0;
+    int first_status = 0;
+    if (n) {
+        if (!info.block_independence) {
+            // linked blocks: each block may read the previous blocks' output -> serial chain (one warp)
+            k_decompress_chain<<<1, 32, 0, st>>>(d_frame, d_soff, d_slen, d_stored, n, d_out, cap_total, dwin ? d_dict : nullptr,
+                                                (uint32_t)dwin, d_olen, d_status, ctx->d_total);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&total, ctx->d_total, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(status.data(), d_status, n, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (uint32_t i = 0; i < n && !first_status; ++i) first_status = status[i];
+        } else {
+            // independent blocks: every block is decoded by its own warp at i * blockMaxSize (every writer this library
+            // meets -- the reference, liblz4, the lz4 CLI -- emits full blocks except the last); a short block is detected
+            // afterwards and the output is closed up on the device.
+            for (uint32_t i = 0; i < n; ++i) {
+                doff[i] = (uint64_t)i * B;
+                const uint64_t room = doff[i] < cap_total ? cap_total - doff[i] : 0;
+                cap[i] = (uint32_t)std::min<uint64_t>(room, B);
+            }
+            CK(cudaMemcpyAsync(d_doff, doff.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(d_cap, cap.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+            // history of an independent block is the dictionary only (LZ4 frame spec; for frames the reference writes,
+            // blocks > 0 never reach before their own start, so this equals bufferDecompress.js:153 on them)
+            CKS(launch_decompress(ctx, d_frame, d_soff, d_slen, n, d_out, d_doff, d_cap, dwin ? d_dict : nullptr, (uint32_t)dwin, 0,
+                                  d_stored, d_olen, d_status, st));
+            CK(cudaMemcpyAsync(olen.data(), d_olen, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(status.data(), d_status, n, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            bool contiguous = true;
+            for (uint32_t i = 0; i < n; ++i) {
+                if (status[i] && !first_status) first_status = status[i];
+                if (i + 1 < n && olen[i] != B) contiguous = false;
+            }
+            if (!first_status && !contiguous) {
+                // close the gaps front to back (forward moves never overlap later data)
+                uint64_t w = 0;
+                for (uint32_t i = 0; i < n; ++i) {
+                    const uint64_t gap = doff[i] - w;                 // pieces of <= gap bytes never overlap their source
+                    for (uint64_t done = 0; gap && done < olen[i]; done += gap)
+                        CK(cudaMemcpyAsync(d_out + w + done, d_out + doff[i] + done, (size_t)std::min<uint64_t>(gap, olen[i] - done),
+                                           cudaMemcpyDeviceToDevice, st));
+                    w += olen[i];
+                }
+            }
+            for (uint32_t i = 0; i < n; ++i) total += olen[i];
+        }
+    }
+    CK(cudaEventRecord(ctx->ev1, st));
+    if (first_status) { CK(cudaStreamSynchronize(st)); return first_status; }
+
+    if ((flags & 2u) && info.has_block_checksum) {
+        CK(cudaStreamSynchronize(st));
+        for (uint32_t i = 0; i < n; ++i)
+            if (rd32(frame + blocks[i].off + blocks[i].len) != bhash[i]) return DLZ4_E_BLOCK_CHECKSUM;
+    }
+    if (info.has_content_checksum && (flags & 1u)) {                     // :213-217
+        if (end + 4 > frame_len) return DLZ4_E_CONTENT_CHECKSUM;
+        uint32_t h = 0;
+        CKS(launch_xxh32_stream(ctx, d_out, total, 0, ctx->d_hash, st));
+        CK(cudaMemcpyAsync(&h, ctx->d_hash, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h != rd32(frame + end)) return DLZ4_E_CONTENT_CHECKSUM;
+    }
+    *output_len = total;
+    if (total > output_cap) return DLZ4_E_OUTPUT_TOO_SMALL;
+    if (total) CK(cudaMemcpyAsync(output, d_out, total, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return DLZ4_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,660 @@
+// dlz4_kernels.cuh -- sm_100a device code of the B200-native LZ4 block codec.
+//
+// One warp owns one LZ4 block.  The compressor reproduces the reference's greedy single-probe
+// match finder (src/block/blockCompress.js:31-233) bit for bit; the parallelism inside a block is
+// the *miss run*: the next 32 probe positions are a pure function of (sIndex, searchMatchCount),
+// so the 32 lanes probe them at once, resolve intra-batch hash collisions with match.any, a ballot
+// picks the first hit, and only lanes up to the hit commit their table inserts -- exactly the state
+// the serial loop would have left behind.  Match extension is a 128-byte-per-round ballot.
+//
+// No tensor cores: the work is byte-serial integer work bounded by latency and HBM, not FLOPs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dlz4 {
+
+constexpr uint32_t FULL = 0xffffffffu;
+constexpr int kHashEntries = 16384;
+
+// per-block status, same numbering as DLZ4_E_* in include/dlz4_b200.h
+enum : uint8_t { ST_OK = 0, ST_OUTPUT_TOO_SMALL = 1, ST_MALFORMED = 2, ST_OFFSET_ZERO = 3, ST_DICT_OOB = 4 };
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// Unaligned little-endian u32 built from aligned word loads.  Touches only words that contain one of
+// the four requested bytes, so it can never leave an allocation that holds those bytes.
+__device__ __forceinline__ uint32_t ld32u(const uint8_t *p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~static_cast<uintptr_t>(3));
+    const uint32_t sh = static_cast<uint32_t>(a & 3u) * 8u;
+    const uint32_t lo = w[0];
+    if (sh == 0) return lo;
+    return __funnelshift_r(lo, w[1], sh);
+}
+
+__device__ __forceinline__ void st32u(uint8_t *p, uint32_t v) {
+    if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0) { *reinterpret_cast<uint32_t *>(p) = v; return; }
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+}
+
+// Warp-cooperative copy of n bytes, arbitrary alignment on both sides, non-overlapping.
+// (No __restrict__: the decoder copies from bytes this kernel wrote; they must not become ld.global.nc.)
+__device__ __forceinline__ void warp_copy(uint8_t *d, const uint8_t *s, uint32_t n, uint32_t lane) {
+    if (n <= 64) {
+        if (lane < n) d[lane] = s[lane];
+        if (lane + 32 < n) d[lane + 32] = s[lane + 32];
+        return;
+    }
+    const uint32_t head = static_cast<uint32_t>(-reinterpret_cast<intptr_t>(d)) & 3u;
+    if (lane < head) d[lane] = s[lane];
+    d += head; s += head; n -= head;
+    const uint32_t nw = n >> 2;
+    uint32_t *dw = reinterpret_cast<uint32_t *>(d);
+    if ((reinterpret_cast<uintptr_t>(s) & 3u) == 0) {
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(s);
+        for (uint32_t i = lane; i < nw; i += 32) dw[i] = sw[i];
+    } else {
+        for (uint32_t i = lane; i < nw; i += 32) dw[i] = ld32u(s + 4 * i);
+    }
+    const uint32_t done = nw << 2;
+    if (lane < n - done) d[done + lane] = s[done + lane];
+}
+
+// Sum_{u<x} (u >> 6): distance covered by x probes of the skip schedule sIndex += (count++ >> 6)
+// (blockCompress.js:66-67), counted from count = 0.
+__device__ __forceinline__ uint32_t skip_sum(uint32_t x) {
+    const uint32_t q = x >> 6, r = x & 63u;
+    return 32u * q * (q - 1u) + q * r;
+}
+
+// ------------------------------------------------------------------ source address spaces
+// Virtual index v of the reference's `src` array -> byte.
+struct SrcFlat {                          // src is one contiguous buffer
+    const uint8_t *base;
+    __device__ __forceinline__ uint32_t ld32(int32_t v) const { return ld32u(base + v); }
+    __device__ __forceinline__ const uint8_t *lit_ptr(int32_t v) const { return base + v; }
+};
+struct SrcSplit {                         // src = prefix ++ block, stored apart (shared dictionary, config 4)
+    const uint8_t *prefix; int32_t plen; const uint8_t *blk;
+    __device__ __forceinline__ uint32_t byte(int32_t v) const { return v < plen ? prefix[v] : blk[v - plen]; }
+    __device__ __forceinline__ uint32_t ld32(int32_t v) const {
+        if (v >= plen) return ld32u(blk + (v - plen));
+        if (v + 4 <= plen) return ld32u(prefix + v);
+        return byte(v) | (byte(v + 1) << 8) | (byte(v + 2) << 16) | (byte(v + 3) << 24);
+    }
+    __device__ __forceinline__ const uint8_t *lit_ptr(int32_t v) const { return blk + (v - plen); }   // literals are never in the prefix
+};
+
+// ------------------------------------------------------------------ hash tables (shared memory)
+// 16-bit table for a block of <= 65536 bytes that starts from an EMPTY table and has no history:
+// stores (position - start); the value 0 doubles as "empty".  That is exact: position `start` is
+// always the first probe, so the only slot where "candidate = start" could pass the 4-byte check is
+// hash(seq@start), which really holds an entry from then on; in every other slot the check fails
+// just as an empty slot would, and for the probe AT start the candidate equals the position and is
+// rejected as in blockCompress.js:62.
+struct Tab16 {
+    uint16_t *t; int32_t start;
+    __device__ __forceinline__ int32_t get(uint32_t h) const { return start + (int32_t)t[h]; }
+    __device__ __forceinline__ void put(uint32_t h, int32_t p) { t[h] = (uint16_t)(p - start); }
+};
+// The reference's own representation: Int32, value = position + 1, <= 0 empty (blockCompress.js:54-55).
+struct Tab32 {
+    int32_t *t;
+    __device__ __forceinline__ int32_t get(uint32_t h) const { return t[h] - 1; }
+    __device__ __forceinline__ void put(uint32_t h, int32_t p) { t[h] = p + 1; }
+};
+
+// token + literal-length run + literals (blockCompress.js:75-140 / :179-230); returns new write pointer
+template <class Src>
+__device__ __forceinline__ uint8_t *emit_literals(uint8_t *d, const Src &S, int32_t anchor, uint32_t lit,
+                                                   uint32_t token_low, uint32_t lane) {
+    const uint32_t tok = ((lit < 15u ? lit : 15u) << 4) | token_low;
+    if (lane == 0) d[0] = (uint8_t)tok;
+    d += 1;
+    if (lit >= 15u) {
+        const uint32_t rest = lit - 15u, n255 = rest / 255u;
+        for (uint32_t i = lane; i < n255; i += 32) d[i] = 255;
+        if (lane == 0) d[n255] = (uint8_t)(rest - n255 * 255u);
+        d += n255 + 1;
+    }
+    if (lit) warp_copy(d, S.lit_ptr(anchor), lit, lane);
+    return d + lit;
+}
+
+// One LZ4 block by one warp.  All 32 lanes call this with identical arguments; returns bytes written.
+template <class Tab, class Src>
+__device__ uint32_t compress_block_warp(const Src &S, const int32_t start, const int32_t len, Tab &T, uint8_t *const out) {
+    const uint32_t lane = lane_id();
+    const uint32_t lt = (1u << lane) - 1u;
+    const int32_t sEnd = start + len;
+    const int32_t mflimit = sEnd - 12;          // blockCompress.js:34
+    const int32_t matchLimit = sEnd - 5;        // :35
+    int32_t sIndex = start, anchor = start;
+    uint32_t smc = 67;                          // :40 searchMatchCount
+    uint8_t *d = out;
+
+    while (sIndex < mflimit) {                  // :48
+        // lane k probes the k-th upcoming position of the skip schedule (:66-67)
+        const uint32_t base_sum = skip_sum(smc);
+        const int32_t p = sIndex + (int32_t)(skip_sum(smc + lane) - base_sum);
+        const bool valid = p < mflimit;
+        uint32_t seq = 0, h = 0x10000u + lane;  // invalid lanes get a unique pseudo-hash
+        int32_t cand = -1;
+        if (valid) {
+            seq = S.ld32(p);                                    // :50
+            h = (seq * 2654435761u) >> 18;                      // :53 (14 bits)
+            cand = T.get(h);                                    // :54
+        }
+        // the serial loop would have seen the insert of an earlier probe of this batch in the same slot
+        const uint32_t same = __match_any_sync(FULL, h);
+        const uint32_t prev = same & lt;
+        const int j = prev ? 31 - __clz(prev) : (int)lane;
+        const int32_t pj = __shfl_sync(FULL, p, j);
+        const uint32_t sj = __shfl_sync(FULL, seq, j);
+        uint32_t cseq = sj;
+        if (prev) cand = pj;
+        const bool ok = valid && cand >= 0 && cand != p && (((uint32_t)(p - cand)) >> 16) == 0;   // :62
+        if (ok && !prev) cseq = S.ld32(cand);                   // :63
+        const bool hit = ok && cseq == seq;
+        const uint32_t hits = __ballot_sync(FULL, hit);
+        const uint32_t vmask = __ballot_sync(FULL, valid);
+        const int hl = __ffs(hits) - 1;                          // first hit lane, -1 if none
+        const uint32_t commit = hits ? ((2u << hl) - 1u) : vmask;  // probes the serial loop really executed
+        // :55 table[hash] = sIndex+1 -- per slot the LAST executed probe wins
+        if (((commit >> lane) & 1u) && ((same & commit) >> lane) == 1u) T.put(h, p);
+        __syncwarp();
+        if (!hits) {
+            if (vmask != FULL) break;                            // ran into mflimit: loop ends
+            sIndex += (int32_t)(skip_sum(smc + 32u) - base_sum);
+            smc += 32u;
+            continue;
+        }
+        const int32_t s0 = __shfl_sync(FULL, p, hl);
+        const int32_t m0 = __shfl_sync(FULL, cand, hl);
+        smc = 67;                                                // :71
+
+        // :143-150 forward extension, 4 bytes per lane, 128 per round
+        int32_t ml;
+        for (int32_t base = 4;; base += 128) {
+            const int32_t q = s0 + base + 4 * (int32_t)lane;
+            int32_t nv = matchLimit - q;
+            nv = nv > 4 ? 4 : nv;
+            int32_t eq = 0;
+            if (nv > 0) {
+                const uint32_t x = S.ld32(q) ^ S.ld32(m0 + base + 4 * (int32_t)lane);
+                eq = x ? ((__ffs(x) - 1) >> 3) : 4;
+                eq = eq < nv ? eq : nv;
+            }
+            const uint32_t stop = __ballot_sync(FULL, eq < 4);
+            if (stop) {
+                const int l = __ffs(stop) - 1;
+                ml = base + 4 * l + __shfl_sync(FULL, eq, l);
+                break;
+            }
+        }
+
+        const uint32_t code = (uint32_t)(ml - 4);               // :160
+        d = emit_literals(d, S, anchor, (uint32_t)(s0 - anchor), code < 15u ? code : 15u, lane);
+        const uint32_t offset = (uint32_t)(s0 - m0);             // :153
+        if (lane == 0) { d[0] = (uint8_t)offset; d[1] = (uint8_t)(offset >> 8); }   // :156-157
+        d += 2;
+        if (code >= 15u) {                                       // :161-168
+            const uint32_t rest = code - 15u, n255 = rest / 255u;
+            for (uint32_t i = lane; i < n255; i += 32) d[i] = 255;
+            if (lane == 0) d[n255] = (uint8_t)(rest - n255 * 255u);
+            d += n255 + 1;
+        }
+        sIndex = anchor = s0 + ml;                               // :173-174
+    }
+    d = emit_literals(d, S, anchor, (uint32_t)(sEnd - anchor), 0u, lane);   // :179-230
+    return (uint32_t)(d - out);
+}
+
+// ------------------------------------------------------------------ compress kernels
+__device__ __forceinline__ uint32_t next_block(uint32_t *counter, uint32_t lane) {
+    uint32_t b = 0;
+    if (lane == 0) b = atomicAdd(counter, 1u);
+    return __shfl_sync(FULL, b, 0);
+}
+
+// Independent blocks <= 64 KiB, fresh table, no history: 16-bit table, 32 KiB of shared memory per warp.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_compress_fresh16(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
+                   const uint32_t *__restrict__ src_len, uint32_t nblocks, uint8_t *__restrict__ dst,
+                   const uint64_t *__restrict__ dst_off, uint32_t *__restrict__ comp_len, uint32_t *counter) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    uint16_t *tab = reinterpret_cast<uint16_t *>(smem) + warp * kHashEntries;
+    for (;;) {
+        const uint32_t b = next_block(counter, lane);
+        if (b >= nblocks) break;
+        const uint32_t len = src_len[b];
+        if (len > 65536u) { if (lane == 0) comp_len[b] = 0xFFFFFFFFu; continue; }
+        uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+        for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        SrcFlat S{src + src_off[b]};
+        Tab16 T{tab, 0};
+        const uint32_t c = compress_block_warp(S, 0, (int32_t)len, T, dst + dst_off[b]);
+        if (lane == 0) comp_len[b] = c;
+        __syncwarp();
+    }
+}
+
+// Independent blocks of any size, optional shared prefix and initial table: the reference's Int32 table,
+// 64 KiB of shared memory per warp.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_compress_generic32(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
+                     const uint32_t *__restrict__ src_len, uint32_t nblocks, const uint8_t *__restrict__ prefix,
+                     uint32_t prefix_len, const int32_t *__restrict__ init_table, uint8_t *__restrict__ dst,
+                     const uint64_t *__restrict__ dst_off, uint32_t *__restrict__ comp_len, uint32_t *counter) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    int32_t *tab = reinterpret_cast<int32_t *>(smem) + warp * kHashEntries;
+    for (;;) {
+        const uint32_t b = next_block(counter, lane);
+        if (b >= nblocks) break;
+        uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+        if (init_table) {
+            const uint4 *i4 = reinterpret_cast<const uint4 *>(init_table);
+            for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) t4[i] = i4[i];
+        } else {
+            for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+        Tab32 T{tab};
+        uint32_t c;
+        if (prefix_len) {
+            SrcSplit S{prefix, (int32_t)prefix_len, src + src_off[b]};
+            c = compress_block_warp(S, (int32_t)prefix_len, (int32_t)src_len[b], T, dst + dst_off[b]);
+        } else {
+            SrcFlat S{src + src_off[b]};
+            c = compress_block_warp(S, 0, (int32_t)src_len[b], T, dst + dst_off[b]);
+        }
+        if (lane == 0) comp_len[b] = c;
+        __syncwarp();
+    }
+}
+
+// Serial chain: ONE warp walks consecutive blocks of one contiguous working buffer, carrying the table
+// (linked blocks, bufferCompress.js:182,219,234; and the single-block compressRaw entry).  `work` is the
+// reference's workingBuffer (dictionary ++ input); block k covers [start + k*block_size, ...).
+// With nblocks == 1 it is also block 0 of an independent-mode frame that has a dictionary (the only block that
+// sees the warmed table, bufferCompress.js:186-204,234-236).
+__global__ void __launch_bounds__(32, 1)
+k_compress_chain(const uint8_t *__restrict__ work, int32_t start, int32_t total_len, int32_t block_size, uint32_t nblocks,
+                 int32_t *table_io /* global int32[16384], read at entry, written at exit */,
+                 uint8_t *__restrict__ dst, uint64_t dst_stride, uint32_t *__restrict__ comp_len) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = lane_id();
+    int32_t *tab = reinterpret_cast<int32_t *>(smem);
+    uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+    uint4 *g4 = reinterpret_cast<uint4 *>(table_io);
+    for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) t4[i] = g4[i];
+    __syncwarp();
+    Tab32 T{tab};
+    SrcFlat S{work};
+    const int32_t end = start + total_len;
+    for (uint32_t k = 0; k < nblocks; ++k) {
+        const int32_t pos = start + (int32_t)k * block_size;
+        const int32_t blen = (end - pos) < block_size ? (end - pos) : block_size;
+        const uint32_t c = compress_block_warp(S, pos, blen, T, dst + (uint64_t)k * dst_stride);
+        if (lane == 0) comp_len[k] = c;
+        __syncwarp();
+    }
+    for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) g4[i] = t4[i];
+}
+
+// Jenkins warm-up of the table from the dictionary prefix (bufferCompress.js:186-204): table[slot(seq_i)] = i+1
+// for ascending i, i.e. the largest i per slot -> atomicMax on a zeroed table.
+__global__ void k_warm_jenkins(const uint8_t *__restrict__ work, int32_t dict_len, int32_t *table) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > dict_len - 4) return;
+    uint32_t h = ld32u(work + i);
+    h = h + 2127912214u + (h << 12);
+    h = h ^ 3345072700u ^ (h >> 19);
+    h = h + 374761393u + (h << 5);
+    h = (h + 3550635116u) ^ (h << 9);
+    h = h + 4251993797u + (h << 3);
+    h = h ^ 3042594569u ^ (h >> 16);
+    atomicMax(&table[(h >> 18) & 16383u], i + 1);
+}
+
+// ------------------------------------------------------------------ decompress
+// Forward byte-order copy of n bytes from d - offset to d (LZ4 match copy, any overlap).
+__device__ __forceinline__ void warp_match_copy(uint8_t *d, uint32_t offset, uint32_t n, uint32_t lane) {
+    if (offset >= 32u) {
+        const uint8_t *s = d - offset;
+        if (offset >= n) { warp_copy(d, s, n, lane); return; }
+        for (uint32_t base = 0; base < n; base += 32) {          // each round reads only bytes of earlier rounds
+            const uint32_t k = base + lane;
+            if (k < n) d[k] = s[k];
+            __syncwarp();
+        }
+    } else {
+        // period < 32: every output byte equals one of the `offset` bytes before d.  With a stride that is a
+        // multiple of the period each lane keeps writing the same byte.
+        const uint32_t step = 32u - (32u % offset);
+        if (lane < step) {
+            const uint8_t v = d[(int32_t)(lane % offset) - (int32_t)offset];
+            for (uint32_t k = lane; k < n; k += step) d[k] = v;
+        }
+    }
+}
+
+// decompressBlock (blockDecompress.js:30-275) with LZ4-spec copy semantics, one warp per block.
+// out0 = the output ARRAY's index 0 (the dictionary boundary, :142-147), out_pos = outputOffset,
+// out_total = output.length.  Everything is bounds-checked (the JS checks literals only).
+__device__ uint32_t decompress_block_warp(const uint8_t *__restrict__ in, const uint32_t n, uint8_t *const out0,
+                                          const int64_t out_pos, const int64_t out_total,
+                                          const uint8_t *__restrict__ dict, const int64_t dict_len, uint32_t *status) {
+    const uint32_t lane = lane_id();
+    uint32_t ip = 0;
+    int64_t op = out_pos;
+    uint32_t st = ST_OK;
+    while (ip < n) {                                             // :55
+        const uint32_t token = in[ip++];                         // :58
+        uint32_t lit = token >> 4;                               // :61
+        if (lit == 15u) {                                        // :62-68
+            uint32_t b;
+            do {
+                if (ip >= n) { st = ST_MALFORMED; break; }
+                b = in[ip++]; lit += b;
+            } while (b == 255u);
+            if (st) break;
+        }
+        if (op + lit > out_total) { st = ST_OUTPUT_TOO_SMALL; break; }   // :74
+        if ((uint64_t)ip + lit > n) { st = ST_MALFORMED; break; }        // :75
+        if (lit) warp_copy(out0 + op, in + ip, lit, lane);       // :79-121
+        op += lit; ip += lit;
+        if (ip >= n) break;                                      // :123
+        if (ip + 2 > n) { st = ST_MALFORMED; break; }
+        const uint32_t offset = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8);   // :126
+        ip += 2;
+        if (offset == 0) { st = ST_OFFSET_ZERO; break; }         // :128
+        uint32_t ml = token & 15u;                               // :131
+        if (ml == 15u) {                                         // :132-138
+            uint32_t b;
+            do {
+                if (ip >= n) { st = ST_MALFORMED; break; }
+                b = in[ip++]; ml += b;
+            } while (b == 255u);
+            if (st) break;
+        }
+        ml += 4;                                                 // :139
+        int64_t cs = op - (int64_t)offset;                       // :142
+        uint32_t rem = ml;
+        if (cs < 0) {                                            // :145-200 dictionary
+            int64_t from_dict = -cs;
+            if (from_dict > ml) from_dict = ml;
+            const int64_t di = dict_len + cs;
+            if (di < 0 || di + from_dict > dict_len) { st = ST_DICT_OOB; break; }   // :150-152
+            if (op + ml > out_total) { st = ST_OUTPUT_TOO_SMALL; break; }
+            warp_copy(out0 + op, dict + di, (uint32_t)from_dict, lane);
+            op += from_dict; rem -= (uint32_t)from_dict;
+        } else if (op + ml > out_total) { st = ST_OUTPUT_TOO_SMALL; break; }
+        __syncwarp();                                            // literals / dictionary bytes visible to all lanes
+        if (rem) warp_match_copy(out0 + op, offset, rem, lane);  // :194-199, :202-271
+        op += rem;
+        __syncwarp();
+    }
+    *status = st;
+    return (uint32_t)(op - out_pos);
+}
+
+// Batched decode, one warp per block, blocks handed out by an atomic counter.
+// hist_frame != 0: block i's output array starts at dst[0] (history = dict ++ dst[0..dst_off[i]));
+// otherwise each block's array starts at its own dst_off[i].
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_decompress_blocks(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
+                    const uint32_t *__restrict__ src_len, uint32_t nblocks, uint8_t *dst,
+                    const uint64_t *__restrict__ dst_off, const uint32_t *__restrict__ dst_cap,
+                    const uint8_t *__restrict__ dict, uint32_t dict_len, int hist_frame,
+                    const uint8_t *__restrict__ stored /* nullable: 1 = raw copy (frame stored block) */,
+                    uint32_t *__restrict__ out_len, uint8_t *__restrict__ status, uint32_t *counter) {
+    const uint32_t lane = lane_id();
+    for (;;) {
+        const uint32_t b = next_block(counter, lane);
+        if (b >= nblocks) break;
+        uint32_t st;
+        uint32_t w;
+        if (stored && stored[b]) {                               // bufferDecompress.js:147-149
+            w = src_len[b];
+            st = ST_OK;
+            if (w > dst_cap[b]) { st = ST_OUTPUT_TOO_SMALL; w = 0; }
+            else warp_copy(dst + dst_off[b], src + src_off[b], w, lane);
+        } else if (hist_frame) w = decompress_block_warp(src + src_off[b], src_len[b], dst, (int64_t)dst_off[b],
+                                                  (int64_t)dst_off[b] + dst_cap[b], dict, dict_len, &st);
+        else w = decompress_block_warp(src + src_off[b], src_len[b], dst + dst_off[b], 0, dst_cap[b], dict, dict_len, &st);
+        if (lane == 0) { out_len[b] = w; status[b] = (uint8_t)st; }
+    }
+}
+
+// Serial chain decode: one warp, consecutive blocks of one frame in order (linked blocks read the previous
+// blocks' output, bufferDecompress.js:153).  kind[k]: bit31 of the frame's size word (stored block).
+__global__ void __launch_bounds__(32)
+k_decompress_chain(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
+                   const uint32_t *__restrict__ src_len, const uint8_t *__restrict__ stored, uint32_t nblocks,
+                   uint8_t *dst, uint64_t dst_total, const uint8_t *__restrict__ dict, uint32_t dict_len,
+                   uint32_t *__restrict__ out_len, uint8_t *__restrict__ status, uint64_t *total_out) {
+    const uint32_t lane = lane_id();
+    int64_t op = 0;
+    uint32_t st = ST_OK;
+    for (uint32_t b = 0; b < nblocks; ++b) {
+        uint32_t w = 0;
+        if (st == ST_OK) {
+            if (stored[b]) {
+                w = src_len[b];
+                if (op + w > (int64_t)dst_total) { st = ST_OUTPUT_TOO_SMALL; w = 0; }
+                else warp_copy(dst + op, src + src_off[b], w, lane);
+                __syncwarp();
+            } else {
+                w = decompress_block_warp(src + src_off[b], src_len[b], dst, op, (int64_t)dst_total, dict, dict_len, &st);
+            }
+        }
+        if (lane == 0) { out_len[b] = w; status[b] = (uint8_t)st; }
+        op += w;
+    }
+    if (lane == 0) *total_out = (uint64_t)op;
+}
+
+// ------------------------------------------------------------------ xxHash32 (src/xxhash32/xxhash32.js:21-97)
+constexpr uint32_t P32_1 = 2654435761u, P32_2 = 2246822519u, P32_3 = 3266489917u, P32_4 = 668265263u, P32_5 = 374761393u;
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+__device__ __forceinline__ uint32_t xxh_round(uint32_t v, uint32_t w) { return rotl32(v + w * P32_2, 13) * P32_1; }   // :40-42
+
+// tail after the 16-byte stripes (:70-95); executed by one lane
+__device__ __forceinline__ uint32_t xxh_finish(uint32_t h, const uint8_t *p, const uint8_t *end, uint32_t len) {
+    h += len;
+    while (p + 4 <= end) { h = rotl32(h + ld32u(p) * P32_3, 17) * P32_4; p += 4; }
+    while (p < end) { h = rotl32(h + (uint32_t)(*p) * P32_5, 11) * P32_1; ++p; }
+    h ^= h >> 15; h *= P32_2; h ^= h >> 13; h *= P32_3; h ^= h >> 16;
+    return h;
+}
+
+// A quad of lanes hashes one item: lane a (0..3) owns accumulator v_{a+1} and reads word a of every stripe.
+// The four accumulators are independent serial chains (non-associative), so an item cannot be split further.
+__device__ __forceinline__ uint32_t xxh32_quad(const uint8_t *p, uint32_t len, uint32_t seed, uint32_t a, uint32_t quad_mask) {
+    const uint8_t *end = p + len;
+    uint32_t h;
+    uint32_t nstripes = len >> 4;
+    if (nstripes) {
+        uint32_t v = a == 0 ? seed + P32_1 + P32_2 : a == 1 ? seed + P32_2 : a == 2 ? seed : seed - P32_1;   // :29-32
+        const uint8_t *q = p + 4 * a;
+        uint32_t s = 0;
+        if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0) {
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(q);
+            for (; s + 8 <= nstripes; s += 8) {
+                uint32_t x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = w[(s + u) * 4];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v = xxh_round(v, x[u]);
+            }
+            for (; s < nstripes; ++s) v = xxh_round(v, w[s * 4]);
+        } else {
+            for (; s < nstripes; ++s) v = xxh_round(v, ld32u(q + 16 * s));
+        }
+        const uint32_t base = lane_id() & ~3u;
+        const uint32_t v1 = __shfl_sync(quad_mask, v, base), v2 = __shfl_sync(quad_mask, v, base + 1);
+        const uint32_t v3 = __shfl_sync(quad_mask, v, base + 2), v4 = __shfl_sync(quad_mask, v, base + 3);
+        h = rotl32(v1, 1) + rotl32(v2, 7) + rotl32(v3, 12) + rotl32(v4, 18);                  // :59-65
+    } else {
+        h = seed + P32_5;                                                                      // :67
+    }
+    return xxh_finish(h, p + (size_t)nstripes * 16, end, len);
+}
+
+// out[i] = xxh32(base + off[i], len[i]); if append != 0 the hash is also stored little-endian right after the
+// item's bytes (LZ4 frame block checksum).
+__global__ void __launch_bounds__(256)
+k_xxh32_batch(const uint8_t *__restrict__ base, const uint64_t *__restrict__ off, const uint32_t *__restrict__ len,
+              uint32_t n, uint32_t seed, uint32_t *__restrict__ out, uint8_t *append_base) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t item = tid >> 2, a = tid & 3u;
+    const uint32_t quad_mask = 0xFu << (lane_id() & ~3u);
+    if (item >= n) return;
+    const uint32_t h = xxh32_quad(base + off[item], len[item], seed, a, quad_mask);
+    if (a == 0) {
+        if (out) out[item] = h;
+        if (append_base) {
+            uint8_t *q = append_base + off[item] + len[item];
+            q[0] = (uint8_t)h; q[1] = (uint8_t)(h >> 8); q[2] = (uint8_t)(h >> 16); q[3] = (uint8_t)(h >> 24);
+        }
+    }
+}
+
+// One hash over one long buffer: a single quad is the whole parallelism the algorithm has.  The other 28
+// lanes of the warp stage the stream through shared memory so the four chain lanes never wait on HBM.
+__global__ void __launch_bounds__(32)
+k_xxh32_stream(const uint8_t *__restrict__ data, uint64_t len, uint32_t seed, uint32_t *out) {
+    __shared__ __align__(16) uint32_t buf[2][1024];              // 2 x 4 KiB = 2 x 256 stripes
+    const uint32_t lane = lane_id();
+    const uint64_t nstripes = len >> 4;
+    uint32_t v = lane == 0 ? seed + P32_1 + P32_2 : lane == 1 ? seed + P32_2 : lane == 2 ? seed : seed - P32_1;
+    const bool aligned = (reinterpret_cast<uintptr_t>(data) & 15u) == 0;
+    uint64_t s = 0;
+    if (aligned) {
+        const uint4 *g = reinterpret_cast<const uint4 *>(data);
+        const uint64_t nchunks = nstripes >> 8;                  // 256 stripes per chunk
+        uint4 r[8];
+        if (nchunks) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r[u] = g[u * 32 + lane];
+        }
+        for (uint64_t c = 0; c < nchunks; ++c) {
+            uint4 *b4 = reinterpret_cast<uint4 *>(buf[c & 1]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) b4[u * 32 + lane] = r[u];
+            if (c + 1 < nchunks) {
+                const uint4 *gn = g + (c + 1) * 256;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[u] = gn[u * 32 + lane];
+            }
+            __syncwarp();
+            if (lane < 4) {
+                const uint32_t *w = buf[c & 1] + lane;
+#pragma unroll 16
+                for (int t = 0; t < 256; ++t) v = xxh_round(v, w[t * 4]);
+            }
+            __syncwarp();
+        }
+        s = nchunks << 8;
+    }
+    if (lane < 4) {
+        const uint8_t *q = data + 4 * lane;
+        for (; s < nstripes; ++s) v = xxh_round(v, ld32u(q + 16 * s));
+    }
+    const uint32_t v1 = __shfl_sync(FULL, v, 0), v2 = __shfl_sync(FULL, v, 1), v3 = __shfl_sync(FULL, v, 2), v4 = __shfl_sync(FULL, v, 3);
+    if (lane == 0) {
+        uint32_t h = nstripes ? rotl32(v1, 1) + rotl32(v2, 7) + rotl32(v3, 12) + rotl32(v4, 18) : seed + P32_5;
+        *out = xxh_finish(h, data + nstripes * 16, data + len, (uint32_t)len);
+    }
+}
+
+// ------------------------------------------------------------------ frame packing (bufferCompress.js:209-239)
+// uniform block table for a contiguous buffer: off[i] = first + i*block, len[i] = min(block, total - i*block)
+__global__ void k_uniform_blocks(uint64_t first, uint64_t total, uint32_t block, uint32_t n, uint64_t *off, uint32_t *len,
+                                 uint64_t *dst_off, uint64_t dst_stride) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t o = (uint64_t)i * block;
+    off[i] = first + o;
+    len[i] = (uint32_t)((total - o) < block ? (total - o) : block);
+    if (dst_off) dst_off[i] = (uint64_t)i * dst_stride;
+}
+
+// Stored-block rule (:221-231): compressed iff 0 < comp < len.  body[i] = 4 + size (+4 with block checksum).
+// Single CTA: sizes + exclusive scan into pos[0..n] in one pass (n is at most a few hundred thousand).
+__global__ void __launch_bounds__(1024)
+k_frame_layout(const uint32_t *__restrict__ src_len, const uint32_t *__restrict__ comp_len, uint32_t n, int block_checksum,
+               uint64_t *pos /* n+1 */, uint64_t *data_off /* n: pos+4 */, uint32_t *data_len /* n */) {
+    __shared__ uint64_t warp_tot[32];
+    __shared__ uint64_t carry_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + tid;
+        uint64_t body = 0;
+        uint32_t sz = 0;
+        if (i < n) {
+            const uint32_t c = comp_len[i], L = src_len[i];
+            sz = (c > 0 && c < L) ? c : L;
+            body = 4ull + sz + (block_checksum ? 4ull : 0ull);
+        }
+        uint64_t x = body;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint64_t y = __shfl_up_sync(FULL, x, o); if (lane >= (uint32_t)o) x += y; }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t t = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint64_t y = __shfl_up_sync(FULL, t, o); if (lane >= (uint32_t)o) t += y; }
+            warp_tot[lane] = t;                                   // inclusive over warps
+        }
+        __syncthreads();
+        const uint64_t carry = carry_s;
+        const uint64_t excl = carry + (warp ? warp_tot[warp - 1] : 0) + x - body;
+        if (i < n) { pos[i] = excl; data_off[i] = excl + 4; data_len[i] = sz; }
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    if (tid == 0) pos[n] = carry_s;
+}
+
+// One CTA per block: size word + payload (compressed bytes, or the raw block when stored) into the segment.
+__global__ void __launch_bounds__(256)
+k_frame_gather(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ src_len,
+               const uint8_t *__restrict__ comp, const uint64_t *__restrict__ comp_off, const uint32_t *__restrict__ comp_len,
+               uint32_t n, const uint64_t *__restrict__ pos, uint8_t *__restrict__ seg) {
+    for (uint32_t b = blockIdx.x; b < n; b += gridDim.x) {
+        const uint32_t c = comp_len[b], L = src_len[b];
+        const bool compressed = c > 0 && c < L;
+        const uint32_t sz = compressed ? c : L;
+        const uint8_t *s = compressed ? comp + comp_off[b] : src + src_off[b];
+        uint8_t *d = seg + pos[b];
+        if (threadIdx.x < 4) {
+            const uint32_t word = compressed ? sz : (sz | 0x80000000u);
+            d[threadIdx.x] = (uint8_t)(word >> (8 * threadIdx.x));
+        }
+        d += 4;
+        const uint32_t head = static_cast<uint32_t>(-reinterpret_cast<intptr_t>(d)) & 3u;
+        const uint32_t h = head < sz ? head : sz;
+        if (threadIdx.x < h) d[threadIdx.x] = s[threadIdx.x];
+        const uint32_t nw = (sz - h) >> 2;
+        uint32_t *dw = reinterpret_cast<uint32_t *>(d + h);
+        const uint8_t *sb = s + h;
+        for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) dw[i] = ld32u(sb + 4 * i);
+        const uint32_t done = h + (nw << 2);
+        if (threadIdx.x < sz - done) d[done + threadIdx.x] = s[done + threadIdx.x];
+    }
+}
+
+}  // namespace dlz4

@@ -1,0 +1,223 @@
+"""GPU parity, raw block layer: the CUDA path (through the C ABI) vs the oracle, bit-exact.  Run with -m gpu."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import edge_corpora, golden_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dl():
+    import divortio_lz4_b200 as m
+    m.default_context()          # raises if the CUDA library or device is missing: no silent fallback
+    return m
+
+
+def _pack(items):
+    """Concatenate byte strings; returns (buffer, off, len) with deliberately odd alignment."""
+    off, ln, parts, pos = [], [], [], 0
+    for k, d in enumerate(items):
+        pad = (k * 7 + 3) % 13
+        parts.append(bytes(pad))
+        pos += pad
+        off.append(pos)
+        ln.append(len(d))
+        parts.append(d)
+        pos += len(d)
+    return np.frombuffer(b"".join(parts) + bytes(8), dtype=np.uint8), np.array(off, dtype=np.uint64), np.array(ln, dtype=np.uint32)
+
+
+def _check_blocks(dl, items, **kw):
+    buf, off, ln = _pack(items)
+    dst, doff, clen = dl.compress_blocks(buf, off, ln, **kw)
+    for i, d in enumerate(items):
+        got = dst[int(doff[i]):int(doff[i]) + int(clen[i])].tobytes()
+        yield i, got
+
+
+def test_compress_edge_corpora_bit_exact(dl):
+    corp = edge_corpora()
+    names = list(corp)
+    for i, got in _check_blocks(dl, [corp[n] for n in names]):
+        want = oracle.compress_block_bytes(corp[names[i]])
+        assert got == want, names[i]
+
+
+def test_compress_golden_blocks(dl, kats):
+    ins = golden_inputs()
+    recs = [r for r in kats["blocks"] if len(ins[r["input"]]) <= 65536]
+    for i, got in _check_blocks(dl, [ins[r["input"]] for r in recs]):
+        assert len(got) == recs[i]["len"] and oracle.xxh32(got) == recs[i]["xxh32"], recs[i]["input"]
+
+
+@pytest.mark.parametrize("kind", ["mixed", "log", "rand", "bench"])
+def test_compress_64k_blocks_of_corpus(dl, kind):
+    from divortio_lz4_b200 import corpus
+    n = 8 * 1024 * 1024 + 12345
+    data = {"mixed": lambda: corpus.mixed(2, n), "log": lambda: corpus.log(3, n), "rand": lambda: corpus.rand(4, n),
+            "bench": lambda: corpus.benchjson(n)}[kind]()
+    off = np.arange(0, n, 65536, dtype=np.uint64)
+    ln = np.minimum(65536, n - off).astype(np.uint32)
+    dst, doff, clen = dl.compress_blocks(data, off, ln)
+    odst, odoff, oclen = oracle.compress_blocks(data, off, ln)
+    assert np.array_equal(clen, oclen)
+    for i in range(len(off)):
+        a = dst[int(doff[i]):int(doff[i]) + int(clen[i])]
+        b = odst[int(odoff[i]):int(odoff[i]) + int(oclen[i])]
+        assert np.array_equal(a, b), (kind, i)
+
+
+@pytest.mark.parametrize("bs", [262144, 1048576, 4194304])
+def test_compress_large_blocks_use_int32_table(dl, bs):
+    from divortio_lz4_b200 import corpus
+    n = 3 * bs + 777
+    data = corpus.mixed(bs, n)
+    off = np.arange(0, n, bs, dtype=np.uint64)
+    ln = np.minimum(bs, n - off).astype(np.uint32)
+    dst, doff, clen = dl.compress_blocks(data, off, ln)
+    odst, odoff, oclen = oracle.compress_blocks(data, off, ln)
+    assert np.array_equal(clen, oclen)
+    for i in range(len(off)):
+        assert np.array_equal(dst[int(doff[i]):int(doff[i]) + int(clen[i])], odst[int(odoff[i]):int(odoff[i]) + int(oclen[i])]), i
+
+
+def test_compress_with_shared_prefix_three_table_modes(dl):
+    """BASELINE config 4 at test size: 4 KiB JSON messages with a 64 KiB dictionary as shared prefix."""
+    from divortio_lz4_b200 import corpus
+    nmsg = 512
+    msgs = corpus.jsonmsgs(4, 100, nmsg)
+    dic = corpus.json_dictionary(44)
+    off = np.arange(nmsg, dtype=np.uint64) * 4096
+    ln = np.full(nmsg, 4096, dtype=np.uint32)
+    work = np.concatenate([dic, np.zeros(8, dtype=np.uint8)])
+    tables = {
+        "none": (dl.WARM_NONE, None, None),
+        "jenkins": (dl.WARM_JENKINS, None, oracle.warm_table_jenkins(work, dic.size)),
+    }
+    primed = oracle.new_table()
+    oracle.compress_block(dic, 0, dic.size, primed)       # table state a raw-API user leaves behind
+    tables["primed"] = (dl.WARM_TABLE, primed, primed)
+    sizes = {}
+    for mode, (warm, init, oracle_table) in tables.items():
+        dst, doff, clen = dl.compress_blocks(msgs, off, ln, prefix=dic, warm=warm, init_table=init)
+        odst, odoff, oclen = oracle.compress_blocks_prefix(dic, oracle_table, msgs, off, ln)
+        assert np.array_equal(clen, oclen), mode
+        for i in range(nmsg):
+            assert np.array_equal(dst[int(doff[i]):int(doff[i]) + int(clen[i])],
+                                  odst[int(odoff[i]):int(odoff[i]) + int(oclen[i])]), (mode, i)
+        sizes[mode] = int(clen.sum())
+        # decode side: every message has its own output base whose index 0 is the dictionary boundary
+        out, olen, status = dl.decompress_blocks(dst, doff, clen, off, ln, dictionary=dic, hist_mode=dl.HIST_RAW)
+        assert not status.any() and np.array_equal(olen, ln)
+        assert np.array_equal(out[:nmsg * 4096], msgs)
+    assert sizes["primed"] < sizes["none"]                # only the kernel's own hash makes the prefix useful
+
+
+def test_decompress_edge_corpora(dl):
+    corp = edge_corpora()
+    names = list(corp)
+    blocks = [oracle.compress_block_bytes(corp[n]) for n in names]
+    buf, off, ln = _pack(blocks)
+    cap = np.array([len(corp[n]) for n in names], dtype=np.uint32)
+    doff = np.zeros(len(names), dtype=np.uint64)
+    doff[1:] = np.cumsum(cap.astype(np.uint64) + 5)[:-1]
+    out, olen, status = dl.decompress_blocks(buf, off, ln, doff, cap)
+    assert not status.any()
+    for i, n in enumerate(names):
+        assert int(olen[i]) == len(corp[n]), n
+        assert out[int(doff[i]):int(doff[i]) + int(olen[i])].tobytes() == corp[n], n
+
+
+def test_decompress_liblz4_blocks(dl):
+    import lz4f
+    if not lz4f.available():
+        pytest.skip("liblz4 not present")
+    corp = edge_corpora()
+    names = [n for n in corp if len(corp[n]) > 0]
+    blocks = []
+    for n in names:
+        d = np.frombuffer(corp[n], dtype=np.uint8)
+        o = np.zeros(lz4f.L.LZ4_compressBound(d.size), dtype=np.uint8)
+        k = lz4f.L.LZ4_compress_default(d.ctypes.data, o.ctypes.data, d.size, o.size)
+        blocks.append(o[:k].tobytes())
+    buf, off, ln = _pack(blocks)
+    cap = np.array([len(corp[n]) for n in names], dtype=np.uint32)
+    doff = np.zeros(len(names), dtype=np.uint64)
+    doff[1:] = np.cumsum(cap.astype(np.uint64))[:-1]
+    out, olen, status = dl.decompress_blocks(buf, off, ln, doff, cap)
+    assert not status.any()
+    for i, n in enumerate(names):
+        assert out[int(doff[i]):int(doff[i]) + int(olen[i])].tobytes() == corp[n], n
+
+
+def test_decompress_errors_match_oracle(dl):
+    cases = [
+        (b"\xF0\x20" + b"x" * 47, 16, None, 1),          # Output Buffer Too Small
+        (b"\x50abc", 16, None, 2),                        # Malformed Input
+        (b"\x10a\x00\x00\x00", 16, None, 3),              # Invalid Offset 0
+        (b"\x10a\x05\x00\x00", 16, None, 4),              # Dictionary Offset Out of Bounds
+        (b"\x1Fa\x01\x00\xFF\xFF", 5000, None, 2),        # length run hits the end of input
+        (b"\x1Fa\x01\x00\xFF\x10\x00", 64, None, 1),      # match longer than the output
+    ]
+    for blk, cap, dic, want in cases:
+        out = np.zeros(cap, dtype=np.uint8)
+        with pytest.raises(oracle.OracleError) as e1:
+            oracle.decompress_block(blk, 0, len(blk), out, 0, dic)
+        assert -e1.value.code == want
+        with pytest.raises(dl.LZ4Error) as e2:
+            dl.decompressBlock(blk, 0, len(blk), np.zeros(cap, dtype=np.uint8), 0, dic)
+        assert e2.value.status == want and str(e2.value) == oracle.MESSAGES[-want]
+    # batch: one bad block must not disturb its neighbours
+    good = oracle.compress_block_bytes(b"neighbour " * 30)
+    buf, off, ln = _pack([good, b"\x10a\x00\x00\x00", good])
+    cap = np.array([300, 16, 300], dtype=np.uint32)
+    doff = np.array([0, 300, 316], dtype=np.uint64)
+    out, olen, status = dl.decompress_blocks(buf, off, ln, doff, cap, check=False)
+    assert status.tolist() == [0, 3, 0]
+    assert out[:300].tobytes() == b"neighbour " * 30 == out[316:616].tobytes()
+
+
+def test_dictionary_reference_resolves(dl):
+    out = np.zeros(16, dtype=np.uint8)
+    n = dl.decompressBlock(b"\x10a\x05\x00\x00", 0, 5, out, 0, b"WXYZ")
+    assert n == 5 and out[:5].tobytes() == b"aWXYZ"
+
+
+def test_single_block_raw_api_roundtrips_table_state(dl):
+    """LZ4.compressRaw semantics incl. the in/out hash table (linked use across calls)."""
+    from divortio_lz4_b200 import corpus
+    data = corpus.log(7, 150000)
+    t_gpu, t_cpu = np.zeros(16384, dtype=np.int32), oracle.new_table()
+    for start, n in ((0, 65536), (65536, 65536), (131072, 150000 - 131072)):
+        out = np.zeros(dl.compress_bound(n) + 10, dtype=np.uint8)
+        k = dl.compressBlock(data, out, start, n, t_gpu, 10)
+        k_cpu, o_cpu = oracle.compress_block(data, start, n, t_cpu)
+        assert k == k_cpu and out[10:10 + k].tobytes() == o_cpu[:k_cpu].tobytes()
+        assert np.array_equal(t_gpu, t_cpu)
+    # -1 filled table == empty table (tests/raw/raw.test.mjs:14); undersized output truncates silently
+    t = np.full(16384, -1, dtype=np.int32)
+    small = np.zeros(20, dtype=np.uint8)
+    msg = b"hello hello hello hello hello hello hello, and a tail that does not repeat: 0123456789"
+    k = dl.compressBlock(msg, small, 0, len(msg), t, 0)
+    want = oracle.compress_block_bytes(msg)
+    assert k == len(want) > 20 and small.tobytes() == want[:20]
+    # decompressRaw into the middle of a larger array, history = earlier bytes of that array
+    blk = oracle.compress_block_bytes(data[:70000].tobytes(), 65536, 70000 - 65536, oracle.new_table())
+    arr = np.zeros(70000, dtype=np.uint8)
+    arr[:65536] = data[:65536]
+    n = dl.decompressBlock(blk, 0, len(blk), arr, 65536)
+    assert n == 70000 - 65536 and np.array_equal(arr, data[:70000])
+
+
+def test_xxh32_single_and_batch(dl):
+    corp = edge_corpora()
+    for name, d in corp.items():
+        assert dl.xxHash32(d) == oracle.xxh32(d), name
+        assert dl.xxHash32(d, 0x9E3779B1) == oracle.xxh32(d, 0x9E3779B1), name
+    names = list(corp)
+    buf, off, ln = _pack([corp[n] for n in names])
+    got = dl.xxh32_batch(buf, off, ln)
+    assert got.tolist() == [oracle.xxh32(corp[n]) for n in names]
+    assert dl.xxHash32(b"") == 0x02CC5D05 and dl.xxHash32("Hello World") == 0xB1FD16EE   # reference KATs

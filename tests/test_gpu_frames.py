@@ -1,0 +1,140 @@
+"""GPU parity, frame layer: compressBuffer / decompressBuffer through the C ABI vs the oracle, byte for byte.  -m gpu."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN_OPTS, edge_corpora, golden_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dl():
+    import divortio_lz4_b200 as m
+    m.default_context()
+    return m
+
+
+def _gpu_frame(dl, data, dictionary=None, max_block_size=4194304, block_independence=False, content_checksum=False,
+               add_content_size=True, block_checksum=False):
+    return dl.compressBuffer(data, dictionary, max_block_size, block_independence, content_checksum, add_content_size, None,
+                             block_checksum)
+
+
+def test_golden_fixture_frames(dl, kats):
+    ins = golden_inputs()
+    for rec in kats["frames"]:
+        f = _gpu_frame(dl, ins[rec["input"]], None, **GOLDEN_OPTS[rec["opts"]])
+        assert len(f) == rec["len"] and oracle.xxh32(f) == rec["xxh32"], rec
+        if "hex" in rec:
+            assert f.hex() == rec["hex"]
+        assert dl.decompressBuffer(f) == ins[rec["input"]]
+
+
+def test_reference_golden_decode_frames(dl, kats):
+    for k in kats["reference_golden"]["decode_frames"]:
+        assert dl.decompressBuffer(bytes.fromhex(k["hex"])) == k["text"].encode()
+
+
+def test_dictionary_frames(dl, kats):
+    for rec in kats["dictionary"]:
+        data = bytes.fromhex(rec["input_hex"])
+        d = bytes.fromhex(rec["dict_hex"]) if "dict_hex" in rec else data[:rec["dict_len"]]
+        if rec["name"] == "D1":
+            f = _gpu_frame(dl, data, d)
+        elif rec["name"].endswith("indep_cc"):
+            f = _gpu_frame(dl, data, d, 65536, True, True, True)
+        else:
+            f = _gpu_frame(dl, data, d, 65536, False, False, True)
+        assert f.hex() == rec["hex"], rec["name"]
+        assert dl.decompressBuffer(f, d) == data
+
+
+@pytest.mark.parametrize("indep", [False, True])
+@pytest.mark.parametrize("cc", [False, True])
+@pytest.mark.parametrize("bc", [False, True])
+def test_edge_corpora_all_flag_combinations(dl, indep, cc, bc):
+    for name, data in edge_corpora().items():
+        f = _gpu_frame(dl, data, None, 65536, indep, cc, True, bc)
+        assert f == oracle.compress_buffer(data, None, 65536, indep, cc, True, None, bc), name
+        assert dl.decompressBuffer(f, None, True, True) == data, name
+
+
+@pytest.mark.parametrize("bs", [65536, 262144, 1048576, 4194304])
+@pytest.mark.parametrize("indep", [False, True])
+def test_multiblock_mixed_corpus(dl, bs, indep):
+    from divortio_lz4_b200 import corpus
+    n = 9 * 1024 * 1024 + 4321
+    data = corpus.mixed(bs + indep, n)
+    f = _gpu_frame(dl, data, None, bs, indep, True, True, True)
+    want = oracle.compress_buffer(data, None, bs, indep, True, True, None, True)
+    assert len(f) == len(want) and f == want
+    assert dl.decompressBuffer(f, None, True, True) == data.tobytes()
+
+
+def test_dictionary_multiblock_both_modes(dl):
+    from divortio_lz4_b200 import corpus
+    data = corpus.jsonmsgs(4, 0, 100).tobytes()                    # 400 KiB
+    for dic in (corpus.json_dictionary(44).tobytes(), corpus.jsonmsgs(45, 0, 40).tobytes()[:100000], b"tiny"):
+        for indep in (False, True):
+            f = _gpu_frame(dl, data, dic, 65536, indep, True)
+            assert f == oracle.compress_buffer(data, dic, 65536, indep, True), (len(dic), indep)
+            assert dl.decompressBuffer(f, dic) == data
+
+
+def test_block_size_quantisation_and_output_buffer(dl):
+    data = bytes(range(256)) * 1200                                   # 307200 bytes
+    for mbs in (0, 1, 65536, 65537, 262144, 262145, 1048576, 1048577, 4194304, 10 ** 9):
+        assert _gpu_frame(dl, data, None, mbs, True) == oracle.compress_buffer(data, None, mbs, True), mbs
+    out = np.zeros(dl.frame_bound(len(data)), dtype=np.uint8)
+    view = dl.compressBuffer(data, None, 65536, True, False, True, out)
+    assert view.base is out or view.base is out.base
+    assert view.tobytes() == oracle.compress_buffer(data, None, 65536, True)
+    # undersized outputBuffer: silently truncated, like typed-array stores past the end
+    small = np.zeros(100, dtype=np.uint8)
+    view = dl.compressBuffer(data, None, 65536, True, False, True, small)
+    assert view.tobytes() == oracle.compress_buffer(data, None, 65536, True)[:100]
+
+
+def test_decompress_errors(dl):
+    d = b"some payload that repeats, some payload that repeats" * 20
+    f = bytearray(_gpu_frame(dl, d, None, 4194304, False, True))
+    f[-1] ^= 0xFF
+    with pytest.raises(dl.LZ4Error, match="Content Checksum Error"):
+        dl.decompressBuffer(bytes(f))
+    assert dl.decompressBuffer(bytes(f), None, False) == d
+    with pytest.raises(dl.LZ4Error, match="Invalid Magic Number"):
+        dl.decompressBuffer(b"\x00\x01\x02\x03\x04\x05\x06\x07")
+    with pytest.raises(dl.LZ4Error, match="Unsupported Version 2"):
+        dl.decompressBuffer(bytes.fromhex("04224D18A0400000"))
+    g = bytearray(_gpu_frame(dl, d * 40, None, 65536, True, False, True, True))
+    g[40] ^= 0x01
+    with pytest.raises(dl.LZ4Error):
+        dl.decompressBuffer(bytes(g), None, True, True)
+
+
+def test_accepts_liblz4_cli_equivalent_frames(dl):
+    import lz4f
+    if not lz4f.available():
+        pytest.skip("liblz4 not present")
+    from divortio_lz4_b200 import corpus
+    data = corpus.mixed(12, 5 * 1024 * 1024 + 999).tobytes()
+    for bsid in (4, 5, 6, 7):
+        for linked in (False, True):
+            for size in (False, True):
+                for bc in (False, True):
+                    f = lz4f.compress_frame(data, bsid, linked, True, size, bc)
+                    assert dl.decompressBuffer(f, None, True, True) == data, (bsid, linked, size, bc)
+    assert dl.decompressBuffer(lz4f.compress_frame(b"", 4)) == b""
+
+
+def test_gpu_frames_decode_in_liblz4(dl):
+    import lz4f
+    if not lz4f.available():
+        pytest.skip("liblz4 not present")
+    from divortio_lz4_b200 import corpus
+    data = corpus.mixed(13, 3 * 1024 * 1024 + 17).tobytes()
+    for bs in (65536, 4194304):
+        for indep in (False, True):
+            f = _gpu_frame(dl, data, None, bs, indep, True, True, True)
+            assert lz4f.decompress_frame(f, len(data)) == data
