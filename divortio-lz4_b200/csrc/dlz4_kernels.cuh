@@ -11,6 +11,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <limits.h>
 
 namespace dlz4 {
 
@@ -211,6 +212,271 @@ __device__ uint32_t compress_block_warp(const Src &S, const int32_t start, const
     return (uint32_t)(d - out);
 }
 
+// ------------------------------------------------------------------ v2: dense-window compressor
+// Raw table access for the window path (write / read back / restore).
+__device__ __forceinline__ uint32_t tab_raw(const Tab16 &T, uint32_t h) { return T.t[h]; }
+__device__ __forceinline__ void tab_set_raw(Tab16 &T, uint32_t h, uint32_t v) { T.t[h] = (uint16_t)v; }
+__device__ __forceinline__ uint32_t tab_enc(const Tab16 &T, int32_t p) { return (uint32_t)(p - T.start) & 0xFFFFu; }
+__device__ __forceinline__ int32_t tab_dec(const Tab16 &T, uint32_t raw) { return T.start + (int32_t)raw; }
+__device__ __forceinline__ uint32_t tab_raw(const Tab32 &T, uint32_t h) { return (uint32_t)T.t[h]; }
+__device__ __forceinline__ void tab_set_raw(Tab32 &T, uint32_t h, uint32_t v) { T.t[h] = (int32_t)v; }
+__device__ __forceinline__ uint32_t tab_enc(const Tab32 &, int32_t p) { return (uint32_t)(p + 1); }
+__device__ __forceinline__ int32_t tab_dec(const Tab32 &, uint32_t raw) { return (int32_t)raw - 1; }
+
+// aligned word at byte index `idx` (multiple of 4 in address terms) of a read-only global buffer, 0 outside [lo, hi)
+__device__ __forceinline__ uint32_t ldg_word_guard(const uint8_t *base, int32_t idx, int32_t lo, int32_t hi) {
+    return (idx >= lo && idx < hi) ? __ldg(reinterpret_cast<const uint32_t *>(base + idx)) : 0u;
+}
+
+// One LZ4 block by one warp, contiguous read-only global source (`base` = virtual index 0).
+//
+// Dense path ("window"): while the skip schedule still steps by 1 (searchMatchCount <= 96 for all 32 probes) the next 32
+// probe positions are the 32 consecutive bytes w..w+31.  One pass
+//   (1) builds every lane's 16 source bytes from a register-resident copy of the forward 128-byte lines (shuffles, no
+//       memory access),
+//   (2) looks all 32 slots up, inserts all 32 positions and reads the slots back: if every lane reads its own position
+//       there is no same-slot pair inside the window, hence every lane's candidate is the table state from before the
+//       window, whatever the parse does inside it,
+//   (3) verifies the 32 candidates and pre-extends every verified one to at most 16 bytes, all lanes at once,
+//   (4) walks the window in registers only: first hit at or after `cur`, emit, jump behind the match, repeat,
+//   (5) un-inserts the positions the serial loop would never have probed (inside matches).
+// A window with a same-slot pair, the sparse schedule and the block tail fall back to the batch step of
+// compress_block_warp (exact for every case).
+template <class Tab>
+__device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, const int32_t start, const int32_t len, Tab &T,
+                                           uint8_t *const out) {
+    const uint32_t lane = lane_id();
+    const uint32_t lt = (1u << lane) - 1u;
+    const int32_t sEnd = start + len;
+    const int32_t mflimit = sEnd - 12;
+    const int32_t matchLimit = sEnd - 5;
+    int32_t sIndex = start, anchor = start;
+    uint32_t smc = 67;
+    uint8_t *d = out;
+    SrcFlat S{base};
+
+    // forward line cache: three 128-byte lines in registers, one word per lane each
+    const uint32_t gmis = (uint32_t)(reinterpret_cast<uintptr_t>(base) & 127u);
+    const int32_t wlo = start - (int32_t)((reinterpret_cast<uintptr_t>(base) + (uint32_t)start) & 3u);   // first word holding block bytes
+    const int32_t whi = sEnd;                                                                                // words starting below sEnd hold block bytes
+    int32_t la = INT32_MIN;
+    uint32_t LA = 0, LB = 0, LC = 0;
+
+    while (sIndex < mflimit) {
+        if (smc <= 96u && sIndex + 31 < mflimit) {
+            const int32_t w = sIndex;
+            const uint32_t wmis = (uint32_t)((reinterpret_cast<uintptr_t>(base) + (uint32_t)w) & 3u);
+            const int32_t wa = w - (int32_t)wmis;                                   // word-aligned window base
+            const int32_t line = wa - (int32_t)(((uint32_t)wa + gmis) & 127u);      // 128-byte line holding wa
+            if (line != la) {
+                const int32_t li = line + 4 * (int32_t)lane;
+                if (line == la + 128) { LA = LB; LB = LC; }
+                else if (line == la + 256) { LA = LC; LB = ldg_word_guard(base, li + 128, wlo, whi); }
+                else { LA = ldg_word_guard(base, li, wlo, whi); LB = ldg_word_guard(base, li + 128, wlo, whi); }
+                LC = ldg_word_guard(base, li + 256, wlo, whi);
+                la = line;
+            }
+            // Tw = word (wa/4 + lane): the 128 bytes from wa
+            const uint32_t j0 = (uint32_t)(wa - la) >> 2;
+            const uint32_t ji = (j0 + lane) & 31u;
+            const uint32_t xa = __shfl_sync(FULL, LA, ji), xb = __shfl_sync(FULL, LB, ji);
+            const uint32_t Tw = (j0 + lane < 32u) ? xa : xb;
+            // 16 source bytes of position p = w + lane
+            const int32_t p = w + (int32_t)lane;
+            const uint32_t o = wmis + lane, wi = o >> 2, sh = (o & 3u) * 8u;
+            const uint32_t t0 = __shfl_sync(FULL, Tw, wi), t1 = __shfl_sync(FULL, Tw, wi + 1), t2 = __shfl_sync(FULL, Tw, wi + 2),
+                           t3 = __shfl_sync(FULL, Tw, wi + 3), t4 = __shfl_sync(FULL, Tw, wi + 4);
+            const uint32_t S0 = __funnelshift_r(t0, t1, sh), S1 = __funnelshift_r(t1, t2, sh), S2 = __funnelshift_r(t2, t3, sh),
+                           S3 = __funnelshift_r(t3, t4, sh);
+            const uint32_t h = (S0 * 2654435761u) >> 18;
+            // (2) lookup + insert + read back
+            const uint32_t old = tab_raw(T, h);
+            const uint32_t mine = tab_enc(T, p);
+            __syncwarp();
+            tab_set_raw(T, h, mine);
+            __syncwarp();
+            const uint32_t rb = tab_raw(T, h);
+            const uint32_t conflict = __ballot_sync(FULL, rb != mine);
+            if (conflict) {
+                __syncwarp();
+                tab_set_raw(T, h, old);                 // same-slot lanes all hold the same `old`
+                __syncwarp();
+            } else {
+                // (3) verify + pre-extend
+                const int32_t cand = tab_dec(T, old);
+                const bool ok = cand >= 0 && cand != p && (((uint32_t)(p - cand)) >> 16) == 0;
+                bool hit = false;
+                int32_t ml = 0;
+                if (ok) {
+                    const uint32_t cmis = (uint32_t)((reinterpret_cast<uintptr_t>(base) + (uint32_t)cand) & 3u);
+                    const uint32_t *cw = reinterpret_cast<const uint32_t *>(base + (cand - (int32_t)cmis));
+                    const uint32_t csh = cmis * 8u;
+                    const uint32_t c0 = __ldg(cw), c1 = __ldg(cw + 1);
+                    if (__funnelshift_r(c0, c1, csh) == S0) {
+                        hit = true;
+                        const uint32_t c2 = __ldg(cw + 2), c3 = __ldg(cw + 3);
+                        // the 5th word is only needed for a misaligned candidate; never touch a word that starts at or after sEnd
+                        const uint32_t c4 = (cmis && cand - (int32_t)cmis + 16 < whi) ? __ldg(cw + 4) : 0u;
+                        const uint32_t x1 = S1 ^ __funnelshift_r(c1, c2, csh), x2 = S2 ^ __funnelshift_r(c2, c3, csh),
+                                       x3 = S3 ^ __funnelshift_r(c3, c4, csh);
+                        int32_t n = x1 ? ((__ffs(x1) - 1) >> 3) : x2 ? 4 + ((__ffs(x2) - 1) >> 3) : x3 ? 8 + ((__ffs(x3) - 1) >> 3) : 12;
+                        const int32_t lim = matchLimit - p;          // >= 8 because p < mflimit
+                        ml = 4 + n;
+                        ml = ml < lim ? ml : lim;
+                    }
+                }
+                // (4) resolve
+                uint32_t cur = 0, probed = 0, smc_cur = smc;
+                for (;;) {
+                    const uint32_t hits = __ballot_sync(FULL, hit && lane >= cur);
+                    if (!hits) {
+                        probed |= ~((1u << cur) - 1u);
+                        smc = smc_cur + (32u - cur);
+                        cur = 32;
+                        break;
+                    }
+                    const int hl = __ffs(hits) - 1;
+                    probed |= ((2u << hl) - 1u) & ~((1u << cur) - 1u);
+                    int32_t mlh = __shfl_sync(FULL, ml, hl);
+                    const int32_t m0 = __shfl_sync(FULL, cand, hl);
+                    const int32_t s0 = w + hl;
+                    if (mlh == 16 && matchLimit - s0 > 16) {
+                        // long match: continue the extension cooperatively, 128 bytes per round (as compress_block_warp)
+                        for (int32_t eb = 16;; eb += 128) {
+                            const int32_t q = s0 + eb + 4 * (int32_t)lane;
+                            int32_t nv = matchLimit - q;
+                            nv = nv > 4 ? 4 : nv;
+                            int32_t eq = 0;
+                            if (nv > 0) {
+                                const uint32_t x = S.ld32(q) ^ S.ld32(m0 + eb + 4 * (int32_t)lane);
+                                eq = x ? ((__ffs(x) - 1) >> 3) : 4;
+                                eq = eq < nv ? eq : nv;
+                            }
+                            const uint32_t stop = __ballot_sync(FULL, eq < 4);
+                            if (stop) {
+                                const int l = __ffs(stop) - 1;
+                                mlh = eb + 4 * l + __shfl_sync(FULL, eq, l);
+                                break;
+                            }
+                        }
+                    }
+                    // emit
+                    const uint32_t lit = (uint32_t)(s0 - anchor);
+                    const uint32_t code = (uint32_t)(mlh - 4);
+                    const uint32_t offset = (uint32_t)(s0 - m0);
+                    if (lit < 15u && code < 15u) {
+                        // common case: token, <15 literals, offset -- literals straight from the register window when they lie in it
+                        uint32_t v;
+                        if (anchor >= wa) {
+                            const uint32_t ob = (uint32_t)(anchor - wa) + lane;
+                            v = __shfl_sync(FULL, Tw, (ob >> 2) & 31u) >> ((ob & 3u) * 8u);
+                        } else {
+                            v = lane < lit ? (uint32_t)__ldg(base + anchor + lane) : 0u;
+                        }
+                        if (lane < lit) d[1 + lane] = (uint8_t)v;
+                        // lanes 29,30,31: token, offset low, offset high
+                        if (lane >= 29u) {
+                            const uint32_t k = lane - 29u;
+                            const uint32_t val = k == 0 ? ((lit << 4) | code) : k == 1 ? offset : (offset >> 8);
+                            d[k == 0 ? 0u : lit + k] = (uint8_t)val;
+                        }
+                        d += lit + 3u;
+                    } else {
+                        d = emit_literals(d, S, anchor, lit, code < 15u ? code : 15u, lane);
+                        if (lane == 0) { d[0] = (uint8_t)offset; d[1] = (uint8_t)(offset >> 8); }
+                        d += 2;
+                        if (code >= 15u) {
+                            const uint32_t rest = code - 15u, n255 = rest / 255u;
+                            for (uint32_t i = lane; i < n255; i += 32) d[i] = 255;
+                            if (lane == 0) d[n255] = (uint8_t)(rest - n255 * 255u);
+                            d += n255 + 1;
+                        }
+                    }
+                    anchor = s0 + mlh;
+                    cur = (uint32_t)hl + (uint32_t)mlh;
+                    smc_cur = 67;
+                    smc = 67;
+                    if (cur >= 32u) break;
+                }
+                // (5) un-insert what the serial loop never probed
+                if (!((probed >> lane) & 1u)) tab_set_raw(T, h, old);
+                __syncwarp();
+                sIndex = w + (int32_t)cur;
+                continue;
+            }
+        }
+
+        // ---- batch step (identical to compress_block_warp's loop body)
+        const uint32_t base_sum = skip_sum(smc);
+        const int32_t p = sIndex + (int32_t)(skip_sum(smc + lane) - base_sum);
+        const bool valid = p < mflimit;
+        uint32_t seq = 0, h = 0x10000u + lane;
+        int32_t cand = -1;
+        if (valid) {
+            seq = S.ld32(p);
+            h = (seq * 2654435761u) >> 18;
+            cand = T.get(h);
+        }
+        const uint32_t same = __match_any_sync(FULL, h);
+        const uint32_t prev = same & lt;
+        const int j = prev ? 31 - __clz(prev) : (int)lane;
+        const int32_t pj = __shfl_sync(FULL, p, j);
+        const uint32_t sj = __shfl_sync(FULL, seq, j);
+        uint32_t cseq = sj;
+        if (prev) cand = pj;
+        const bool ok = valid && cand >= 0 && cand != p && (((uint32_t)(p - cand)) >> 16) == 0;
+        if (ok && !prev) cseq = S.ld32(cand);
+        const bool hit = ok && cseq == seq;
+        const uint32_t hits = __ballot_sync(FULL, hit);
+        const uint32_t vmask = __ballot_sync(FULL, valid);
+        const int hl = __ffs(hits) - 1;
+        const uint32_t commit = hits ? ((2u << hl) - 1u) : vmask;
+        if (((commit >> lane) & 1u) && ((same & commit) >> lane) == 1u) T.put(h, p);
+        __syncwarp();
+        if (!hits) {
+            if (vmask != FULL) break;
+            sIndex += (int32_t)(skip_sum(smc + 32u) - base_sum);
+            smc += 32u;
+            continue;
+        }
+        const int32_t s0 = __shfl_sync(FULL, p, hl);
+        const int32_t m0 = __shfl_sync(FULL, cand, hl);
+        smc = 67;
+        int32_t ml;
+        for (int32_t eb = 4;; eb += 128) {
+            const int32_t q = s0 + eb + 4 * (int32_t)lane;
+            int32_t nv = matchLimit - q;
+            nv = nv > 4 ? 4 : nv;
+            int32_t eq = 0;
+            if (nv > 0) {
+                const uint32_t x = S.ld32(q) ^ S.ld32(m0 + eb + 4 * (int32_t)lane);
+                eq = x ? ((__ffs(x) - 1) >> 3) : 4;
+                eq = eq < nv ? eq : nv;
+            }
+            const uint32_t stop = __ballot_sync(FULL, eq < 4);
+            if (stop) {
+                const int l = __ffs(stop) - 1;
+                ml = eb + 4 * l + __shfl_sync(FULL, eq, l);
+                break;
+            }
+        }
+        const uint32_t code = (uint32_t)(ml - 4);
+        d = emit_literals(d, S, anchor, (uint32_t)(s0 - anchor), code < 15u ? code : 15u, lane);
+        const uint32_t offset = (uint32_t)(s0 - m0);
+        if (lane == 0) { d[0] = (uint8_t)offset; d[1] = (uint8_t)(offset >> 8); }
+        d += 2;
+        if (code >= 15u) {
+            const uint32_t rest = code - 15u, n255 = rest / 255u;
+            for (uint32_t i = lane; i < n255; i += 32) d[i] = 255;
+            if (lane == 0) d[n255] = (uint8_t)(rest - n255 * 255u);
+            d += n255 + 1;
+        }
+        sIndex = anchor = s0 + ml;
+    }
+    d = emit_literals(d, S, anchor, (uint32_t)(sEnd - anchor), 0u, lane);
+    return (uint32_t)(d - out);
+}
+
 // ------------------------------------------------------------------ compress kernels
 __device__ __forceinline__ uint32_t next_block(uint32_t *counter, uint32_t lane) {
     uint32_t b = 0;
@@ -235,7 +501,39 @@ k_compress_fresh16(const uint8_t *__restrict__ src, const uint64_t *__restrict__
         uint4 *t4 = reinterpret_cast<uint4 *>(tab);
         for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
-        SrcFlat S{src + src_off[b]};
+        Tab16 T{tab, 0};
+        const uint32_t c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b]);
+        if (lane == 0) comp_len[b] = c;
+        __syncwarp();
+    }
+}
+
+// EXPERIMENT (DLZ4_EXP=smem): same as k_compress_fresh16 but the 64 KiB block is staged in shared memory first
+// (96 KiB per warp -> 2 warps per SM); calibrates the all-shared-memory latency per sequence.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_compress_fresh16_smem(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
+                        const uint32_t *__restrict__ src_len, uint32_t nblocks, uint8_t *__restrict__ dst,
+                        const uint64_t *__restrict__ dst_off, uint32_t *__restrict__ comp_len, uint32_t *counter) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    uint8_t *mine = smem + warp * (65536 + 16 + kHashEntries * 2);
+    uint16_t *tab = reinterpret_cast<uint16_t *>(mine + 65536 + 16);
+    for (;;) {
+        const uint32_t b = next_block(counter, lane);
+        if (b >= nblocks) break;
+        const uint32_t len = src_len[b];
+        if (len > 65536u) { if (lane == 0) comp_len[b] = 0xFFFFFFFFu; continue; }
+        uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+        for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+        const uint8_t *g = src + src_off[b];
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);     // keep the global alignment in smem
+        const uint4 *g4 = reinterpret_cast<const uint4 *>(g - mis);
+        uint4 *s4 = reinterpret_cast<uint4 *>(mine);
+        const uint32_t n16 = (len + mis + 15) >> 4;
+        for (uint32_t i = lane; i < n16; i += 32) s4[i] = g4[i];
+        __syncwarp();
+        SrcFlat S{mine + mis};
         Tab16 T{tab, 0};
         const uint32_t c = compress_block_warp(S, 0, (int32_t)len, T, dst + dst_off[b]);
         if (lane == 0) comp_len[b] = c;
