@@ -110,14 +110,7 @@ int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, 
                     const uint64_t *dst_off, uint32_t *comp_len, cudaStream_t st) {
     if (n == 0) return DLZ4_OK;
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(uint32_t), st));
-    static const char *exp = getenv("DLZ4_EXP");
-    if (exp && !strcmp(exp, "smem") && max_len <= 65536 && prefix_len == 0 && init_table == nullptr) {
-        const int smem_bytes = 2 * (65536 + 16 + kHashEntries * 2);
-        static bool once = false;
-        if (!once) { CK(cudaFuncSetAttribute(k_compress_fresh16_smem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); once = true; }
-        const int grid = (int)std::min<uint64_t>((n + 1) / 2, (uint64_t)ctx->sm_count);
-        k_compress_fresh16_smem<2><<<grid, 64, smem_bytes, st>>>(src, src_off, src_len, n, dst, dst_off, comp_len, ctx->d_counter);
-    } else if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr) {
+    if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr) {
         const int grid = (int)std::min<uint64_t>((n + kWarpsFresh16 - 1) / kWarpsFresh16, (uint64_t)ctx->sm_count);
         k_compress_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * kHashEntries * 2, st>>>(
             src, src_off, src_len, n, dst, dst_off, comp_len, ctx->d_counter);

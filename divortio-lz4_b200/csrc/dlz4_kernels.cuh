@@ -508,39 +508,6 @@ k_compress_fresh16(const uint8_t *__restrict__ src, const uint64_t *__restrict__
     }
 }
 
-// EXPERIMENT (DLZ4_EXP=smem): same as k_compress_fresh16 but the 64 KiB block is staged in shared memory first
-// (96 KiB per warp -> 2 warps per SM); calibrates the all-shared-memory latency per sequence.
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1)
-k_compress_fresh16_smem(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
-                        const uint32_t *__restrict__ src_len, uint32_t nblocks, uint8_t *__restrict__ dst,
-                        const uint64_t *__restrict__ dst_off, uint32_t *__restrict__ comp_len, uint32_t *counter) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    uint8_t *mine = smem + warp * (65536 + 16 + kHashEntries * 2);
-    uint16_t *tab = reinterpret_cast<uint16_t *>(mine + 65536 + 16);
-    for (;;) {
-        const uint32_t b = next_block(counter, lane);
-        if (b >= nblocks) break;
-        const uint32_t len = src_len[b];
-        if (len > 65536u) { if (lane == 0) comp_len[b] = 0xFFFFFFFFu; continue; }
-        uint4 *t4 = reinterpret_cast<uint4 *>(tab);
-        for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
-        const uint8_t *g = src + src_off[b];
-        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);     // keep the global alignment in smem
-        const uint4 *g4 = reinterpret_cast<const uint4 *>(g - mis);
-        uint4 *s4 = reinterpret_cast<uint4 *>(mine);
-        const uint32_t n16 = (len + mis + 15) >> 4;
-        for (uint32_t i = lane; i < n16; i += 32) s4[i] = g4[i];
-        __syncwarp();
-        SrcFlat S{mine + mis};
-        Tab16 T{tab, 0};
-        const uint32_t c = compress_block_warp(S, 0, (int32_t)len, T, dst + dst_off[b]);
-        if (lane == 0) comp_len[b] = c;
-        __syncwarp();
-    }
-}
-
 // Independent blocks of any size, optional shared prefix and initial table: the reference's Int32 table,
 // 64 KiB of shared memory per warp.
 template <int WARPS>
@@ -569,8 +536,7 @@ k_compress_generic32(const uint8_t *__restrict__ src, const uint64_t *__restrict
             SrcSplit S{prefix, (int32_t)prefix_len, src + src_off[b]};
             c = compress_block_warp(S, (int32_t)prefix_len, (int32_t)src_len[b], T, dst + dst_off[b]);
         } else {
-            SrcFlat S{src + src_off[b]};
-            c = compress_block_warp(S, 0, (int32_t)src_len[b], T, dst + dst_off[b]);
+            c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)src_len[b], T, dst + dst_off[b]);
         }
         if (lane == 0) comp_len[b] = c;
         __syncwarp();
@@ -594,12 +560,11 @@ k_compress_chain(const uint8_t *__restrict__ work, int32_t start, int32_t total_
     for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) t4[i] = g4[i];
     __syncwarp();
     Tab32 T{tab};
-    SrcFlat S{work};
     const int32_t end = start + total_len;
     for (uint32_t k = 0; k < nblocks; ++k) {
         const int32_t pos = start + (int32_t)k * block_size;
         const int32_t blen = (end - pos) < block_size ? (end - pos) : block_size;
-        const uint32_t c = compress_block_warp(S, pos, blen, T, dst + (uint64_t)k * dst_stride);
+        const uint32_t c = compress_block_warp_v2(work, pos, blen, T, dst + (uint64_t)k * dst_stride);
         if (lane == 0) comp_len[k] = c;
         __syncwarp();
     }

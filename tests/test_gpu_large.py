@@ -1,0 +1,115 @@
+"""Full-size GPU checks at BASELINE.json sizes: the oracle still finishes in seconds at 1 GiB (C, ~0.7 GB/s), so sizes and
+per-block checksums of every compressed block are compared against it, plus size-independent properties (round trip on
+the device, checksum of checksums).  Run with -m gpu."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    import divortio_lz4_b200 as dl
+    from divortio_lz4_b200 import corpus, device as dev
+    return dl, corpus, dev, torch, dl.default_context()
+
+
+def test_config2_1gib_mixed_64k_blocks(env):
+    """BASELINE configs[1]: MIXED(2, 2^30), 16384 x 64 KiB independent blocks, device-resident batch."""
+    dl, corpus, dev, torch, ctx = env
+    n, block = 1 << 30, 65536
+    host = corpus.mixed(2, n)
+    d = torch.device("cuda", ctx.device)
+    src = torch.from_numpy(host).to(d)
+    stride = (dl.compress_bound(block) + 15) & ~15
+    off, ln, nblk, coff = dev.uniform_blocks(n, block, d, stride)
+    comp = torch.empty(nblk * stride + 64, dtype=torch.uint8, device=d)
+    clen = torch.zeros(nblk, dtype=torch.int32, device=d)
+    dev.compress_blocks_dev(ctx, src, off, ln, block, comp, coff, clen)
+    out = torch.empty(n + 64, dtype=torch.uint8, device=d)
+    olen = torch.zeros(nblk, dtype=torch.int32, device=d)
+    st = torch.zeros(nblk, dtype=torch.uint8, device=d)
+    dev.decompress_blocks_dev(ctx, comp, coff, clen, out, off, ln, olen, st)
+    hashes = torch.zeros(nblk, dtype=torch.int32, device=d)
+    dev.xxh32_batch_dev(ctx, comp, coff, clen, hashes)
+    torch.cuda.synchronize()
+    # properties
+    assert int(st.max()) == 0 and torch.equal(olen, ln) and torch.equal(out[:n], src[:n])
+    # oracle on the full corpus
+    h_off = np.arange(nblk, dtype=np.uint64) * block
+    h_len = np.full(nblk, block, dtype=np.uint32)
+    odst, odoff, oclen = oracle.compress_blocks(host, h_off, h_len)
+    assert np.array_equal(clen.cpu().numpy().astype(np.uint32), oclen)
+    ohash = oracle.xxh32_batch(odst, odoff, oclen)
+    assert np.array_equal(hashes.cpu().numpy().view(np.uint32), ohash)          # every block's bytes, via its checksum
+    # checksum of checksums (one number to quote)
+    assert oracle.xxh32(ohash.tobytes()) == oracle.xxh32(hashes.cpu().numpy().tobytes())
+
+
+def test_config3_shape_4m_blocks_block_and_content_checksums(env):
+    """BASELINE configs[2] shape at one call's worth (the reference takes len|0 < 2 GiB per call): 4 MiB blocks,
+    blockChecksum + contentChecksum, frame bytes vs oracle; sharded by block range over 4 emulated ranks."""
+    dl, corpus, dev, torch, ctx = env
+    from divortio_lz4_b200 import sharded
+    n = 512 * 1024 * 1024 + 4321
+    host = corpus.mixed(3, n)
+    want = oracle.compress_buffer(host, None, 4194304, True, True, True, None, True)
+    got = dl.compressBuffer(host, None, 4194304, True, True, True, None, True)
+    assert len(got) == len(want) and got == want
+    assert dl.decompressBuffer(got, None, True, True) == host.tobytes()
+    # the same frame from 4 block-range shards, concatenated on the host (ranks emulated one after the other on this GPU)
+    store = {}
+
+    def make_gather(r):
+        def g(seg):
+            store[r] = seg
+            return [store[k] for k in range(4)] if r == 0 else None
+        return g
+
+    frame = None
+    for r in (1, 2, 3, 0):
+        frame = sharded.compress_sharded(host, 4194304, True, True, True, rank=r, world=4, gather=make_gather(r))
+    assert frame == want
+
+
+def test_config4_shape_small_messages_with_dictionary(env):
+    """BASELINE configs[3] at 65536 messages: 4 KiB JSON messages, 64 KiB dictionary prefix, primed table."""
+    dl, corpus, dev, torch, ctx = env
+    nmsg = 65536
+    msgs = corpus.jsonmsgs(4, 0, nmsg)
+    dic = corpus.json_dictionary(44)
+    off = np.arange(nmsg, dtype=np.uint64) * 4096
+    ln = np.full(nmsg, 4096, dtype=np.uint32)
+    primed = oracle.new_table()
+    oracle.compress_block(dic, 0, dic.size, primed)
+    dst, doff, clen = dl.compress_blocks(msgs, off, ln, prefix=dic, warm=dl.WARM_TABLE, init_table=primed)
+    odst, odoff, oclen = oracle.compress_blocks_prefix(dic, primed, msgs, off, ln)
+    assert np.array_equal(clen, oclen)
+    assert np.array_equal(dl.xxh32_batch(dst, doff, clen), oracle.xxh32_batch(odst, odoff, oclen))
+    out, olen, status = dl.decompress_blocks(dst, doff, clen, off, ln, dictionary=dic)
+    assert not status.any() and np.array_equal(out[:msgs.size], msgs)
+
+
+def test_config5_shape_decode_reference_and_cli_frames_linked_and_independent(env):
+    """BASELINE configs[4] shape: decode-only of oracle (reference-format) and liblz4 (CLI-format) frames."""
+    import lz4f
+    dl, corpus, dev, torch, ctx = env
+    n = 256 * 1024 * 1024
+    host = corpus.mixed(5, n)
+    raw = host.tobytes()
+    frames = [oracle.compress_buffer(host, None, 4194304, True, True, True),
+              oracle.compress_buffer(host, None, 65536, True, False, True)]
+    if lz4f.available():
+        frames += [lz4f.compress_frame(raw, 7, False, True, False, False), lz4f.compress_frame(raw, 4, False, True, False, True)]
+    for f in frames:
+        assert dl.decompressBuffer(f, None, True, True) == raw
+    # linked-block frames are the serial chain: smaller input
+    small = host[:24 * 1024 * 1024]
+    linked = [oracle.compress_buffer(small, None, 4194304, False, True, True)]
+    if lz4f.available():
+        linked.append(lz4f.compress_frame(small.tobytes(), 7, True, True, False, False))
+    for f in linked:
+        assert dl.decompressBuffer(f) == small.tobytes()
