@@ -232,15 +232,18 @@ __device__ __forceinline__ uint32_t ldg_word_guard(const uint8_t *base, int32_t 
 //
 // Dense path ("window"): while the skip schedule still steps by 1 (searchMatchCount <= 96 for all 32 probes) the next 32
 // probe positions are the 32 consecutive bytes w..w+31.  One pass
-//   (1) builds every lane's 16 source bytes from a register-resident copy of the forward 128-byte lines (shuffles, no
-//       memory access),
-//   (2) looks all 32 slots up, inserts all 32 positions and reads the slots back: if every lane reads its own position
-//       there is no same-slot pair inside the window, hence every lane's candidate is the table state from before the
-//       window, whatever the parse does inside it,
-//   (3) verifies the 32 candidates and pre-extends every verified one to at most 16 bytes, all lanes at once,
-//   (4) walks the window in registers only: first hit at or after `cur`, emit, jump behind the match, repeat,
-//   (5) un-inserts the positions the serial loop would never have probed (inside matches).
-// A window with a same-slot pair, the sparse schedule and the block tail fall back to the batch step of
+//   (A) builds every lane's 32 source bytes from a register-resident copy of the forward 128-byte lines (shuffles only),
+//       looks all 32 slots up and issues every candidate's 9 words in one go (one L2 round trip per window); in the shadow
+//       of those loads it inserts all 32 positions and reads the slots back: if every lane reads its own position there is
+//       no same-slot pair inside the window, hence every lane's candidate is the table state from before the window
+//       whatever the parse does inside it; then verifies the candidates and pre-extends verified ones to 32 bytes,
+//   (B) walks the window in registers only (first hit at or after `cur`, jump behind the match), handing every match head
+//       its output offset,
+//   (C) emits in parallel: a literal lane stores its own byte, a head lane its own token / length bytes / offset.  Literal
+//       lanes behind the last match are written provisionally (their sequence is still open); only a run that reaches 15
+//       literals needs them moved, which re-copies from memory (3 % of sequences on text),
+//   (D) un-inserts the positions the serial loop would never have probed (inside matches).
+// A window with a same-slot pair, the sparse schedule and the last bytes of a block fall back to the batch step of
 // compress_block_warp (exact for every case).
 template <class Tab>
 __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, const int32_t start, const int32_t len, Tab &T,
@@ -252,7 +255,8 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
     const int32_t matchLimit = sEnd - 5;
     int32_t sIndex = start, anchor = start;
     uint32_t smc = 67;
-    uint8_t *d = out;
+    uint32_t D = 0;              // output offset of the open sequence's token
+    uint32_t pend = 0;           // literals of the open sequence already stored provisionally at out[D+1 ..)
     SrcFlat S{base};
 
     // forward line cache: three 128-byte lines in registers, one word per lane each
@@ -263,7 +267,7 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
     uint32_t LA = 0, LB = 0, LC = 0;
 
     while (sIndex < mflimit) {
-        if (smc <= 96u && sIndex + 31 < mflimit) {
+        if (smc <= 96u && sIndex + 67 <= sEnd) {
             const int32_t w = sIndex;
             const uint32_t wmis = (uint32_t)((reinterpret_cast<uintptr_t>(base) + (uint32_t)w) & 3u);
             const int32_t wa = w - (int32_t)wmis;                                   // word-aligned window base
@@ -276,21 +280,33 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
                 LC = ldg_word_guard(base, li + 256, wlo, whi);
                 la = line;
             }
-            // Tw = word (wa/4 + lane): the 128 bytes from wa
+            // ---- (A) source bytes, lookup, candidate loads
             const uint32_t j0 = (uint32_t)(wa - la) >> 2;
             const uint32_t ji = (j0 + lane) & 31u;
             const uint32_t xa = __shfl_sync(FULL, LA, ji), xb = __shfl_sync(FULL, LB, ji);
-            const uint32_t Tw = (j0 + lane < 32u) ? xa : xb;
-            // 16 source bytes of position p = w + lane
+            const uint32_t Tw = (j0 + lane < 32u) ? xa : xb;                        // word (wa/4 + lane)
             const int32_t p = w + (int32_t)lane;
             const uint32_t o = wmis + lane, wi = o >> 2, sh = (o & 3u) * 8u;
-            const uint32_t t0 = __shfl_sync(FULL, Tw, wi), t1 = __shfl_sync(FULL, Tw, wi + 1), t2 = __shfl_sync(FULL, Tw, wi + 2),
-                           t3 = __shfl_sync(FULL, Tw, wi + 3), t4 = __shfl_sync(FULL, Tw, wi + 4);
-            const uint32_t S0 = __funnelshift_r(t0, t1, sh), S1 = __funnelshift_r(t1, t2, sh), S2 = __funnelshift_r(t2, t3, sh),
-                           S3 = __funnelshift_r(t3, t4, sh);
-            const uint32_t h = (S0 * 2654435761u) >> 18;
-            // (2) lookup + insert + read back
+            uint32_t tw[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) tw[k] = __shfl_sync(FULL, Tw, wi + k);
+            uint32_t Sw[8];                                                         // bytes p .. p+31
+#pragma unroll
+            for (int k = 0; k < 8; ++k) Sw[k] = __funnelshift_r(tw[k], tw[k + 1], sh);
+            const uint32_t h = (Sw[0] * 2654435761u) >> 18;
             const uint32_t old = tab_raw(T, h);
+            const int32_t cand = tab_dec(T, old);
+            const bool ok = cand >= 0 && cand != p && (((uint32_t)(p - cand)) >> 16) == 0;
+            uint32_t cwd[9];
+            uint32_t csh = 0;
+            if (ok) {                       // cand + 35 < p + 35 <= w + 66 < sEnd: all nine words hold block bytes
+                const uint32_t cmis = (uint32_t)((reinterpret_cast<uintptr_t>(base) + (uint32_t)cand) & 3u);
+                const uint32_t *cw = reinterpret_cast<const uint32_t *>(base + (cand - (int32_t)cmis));
+                csh = cmis * 8u;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) cwd[k] = __ldg(cw + k);
+            }
+            // insert + read back while the loads are in flight
             const uint32_t mine = tab_enc(T, p);
             __syncwarp();
             tab_set_raw(T, h, mine);
@@ -302,47 +318,36 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
                 tab_set_raw(T, h, old);                 // same-slot lanes all hold the same `old`
                 __syncwarp();
             } else {
-                // (3) verify + pre-extend
-                const int32_t cand = tab_dec(T, old);
-                const bool ok = cand >= 0 && cand != p && (((uint32_t)(p - cand)) >> 16) == 0;
                 bool hit = false;
                 int32_t ml = 0;
-                if (ok) {
-                    const uint32_t cmis = (uint32_t)((reinterpret_cast<uintptr_t>(base) + (uint32_t)cand) & 3u);
-                    const uint32_t *cw = reinterpret_cast<const uint32_t *>(base + (cand - (int32_t)cmis));
-                    const uint32_t csh = cmis * 8u;
-                    const uint32_t c0 = __ldg(cw), c1 = __ldg(cw + 1);
-                    if (__funnelshift_r(c0, c1, csh) == S0) {
-                        hit = true;
-                        const uint32_t c2 = __ldg(cw + 2), c3 = __ldg(cw + 3);
-                        // the 5th word is only needed for a misaligned candidate; never touch a word that starts at or after sEnd
-                        const uint32_t c4 = (cmis && cand - (int32_t)cmis + 16 < whi) ? __ldg(cw + 4) : 0u;
-                        const uint32_t x1 = S1 ^ __funnelshift_r(c1, c2, csh), x2 = S2 ^ __funnelshift_r(c2, c3, csh),
-                                       x3 = S3 ^ __funnelshift_r(c3, c4, csh);
-                        int32_t n = x1 ? ((__ffs(x1) - 1) >> 3) : x2 ? 4 + ((__ffs(x2) - 1) >> 3) : x3 ? 8 + ((__ffs(x3) - 1) >> 3) : 12;
-                        const int32_t lim = matchLimit - p;          // >= 8 because p < mflimit
-                        ml = 4 + n;
-                        ml = ml < lim ? ml : lim;
+                if (ok && __funnelshift_r(cwd[0], cwd[1], csh) == Sw[0]) {
+                    hit = true;
+                    int32_t n = 28;
+#pragma unroll
+                    for (int k = 7; k >= 1; --k) {
+                        const uint32_t x = Sw[k] ^ __funnelshift_r(cwd[k], cwd[k + 1], csh);
+                        if (x) n = 4 * (k - 1) + ((__ffs(x) - 1) >> 3);
                     }
+                    const int32_t lim = matchLimit - p;          // >= 31 here
+                    ml = 4 + n;
+                    ml = ml < lim ? ml : lim;
                 }
-                // (4) resolve
-                uint32_t cur = 0, probed = 0, smc_cur = smc;
-                for (;;) {
-                    const uint32_t hits = __ballot_sync(FULL, hit && lane >= cur);
-                    if (!hits) {
-                        probed |= ~((1u << cur) - 1u);
-                        smc = smc_cur + (32u - cur);
-                        cur = 32;
-                        break;
-                    }
-                    const int hl = __ffs(hits) - 1;
-                    probed |= ((2u << hl) - 1u) & ~((1u << cur) - 1u);
+                // ---- (B) resolve
+                const uint32_t hm = __ballot_sync(FULL, hit);
+                const int32_t a_rel0 = anchor - w;               // <= 0: literals pending from earlier windows
+                int32_t a_rel = a_rel0;
+                uint32_t cur = 0, heads = 0, inside = 0, smc_cur = smc;
+                uint32_t myD = 0, myLit = 0, myMl = 0;
+                while (cur < 32u) {
+                    const uint32_t m = hm & (FULL << cur);
+                    if (!m) break;
+                    const int hl = __ffs(m) - 1;
                     int32_t mlh = __shfl_sync(FULL, ml, hl);
-                    const int32_t m0 = __shfl_sync(FULL, cand, hl);
                     const int32_t s0 = w + hl;
-                    if (mlh == 16 && matchLimit - s0 > 16) {
-                        // long match: continue the extension cooperatively, 128 bytes per round (as compress_block_warp)
-                        for (int32_t eb = 16;; eb += 128) {
+                    if (mlh == 32 && matchLimit - s0 > 32) {
+                        // long match: continue cooperatively, 128 bytes per round
+                        const int32_t m0 = __shfl_sync(FULL, cand, hl);
+                        for (int32_t eb = 32;; eb += 128) {
                             const int32_t q = s0 + eb + 4 * (int32_t)lane;
                             int32_t nv = matchLimit - q;
                             nv = nv > 4 ? 4 : nv;
@@ -360,46 +365,69 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
                             }
                         }
                     }
-                    // emit
-                    const uint32_t lit = (uint32_t)(s0 - anchor);
+                    const uint32_t lit = (uint32_t)(hl - a_rel);
                     const uint32_t code = (uint32_t)(mlh - 4);
-                    const uint32_t offset = (uint32_t)(s0 - m0);
-                    if (lit < 15u && code < 15u) {
-                        // common case: token, <15 literals, offset -- literals straight from the register window when they lie in it
-                        uint32_t v;
-                        if (anchor >= wa) {
-                            const uint32_t ob = (uint32_t)(anchor - wa) + lane;
-                            v = __shfl_sync(FULL, Tw, (ob >> 2) & 31u) >> ((ob & 3u) * 8u);
-                        } else {
-                            v = lane < lit ? (uint32_t)__ldg(base + anchor + lane) : 0u;
+                    const uint32_t litx = lit >= 15u ? 1u + (lit - 15u) / 255u : 0u;
+                    const uint32_t mlx = code >= 15u ? 1u + (code - 15u) / 255u : 0u;
+                    if (lane == (uint32_t)hl) { myD = D; myLit = lit; myMl = (uint32_t)mlh; }
+                    D += 3u + litx + lit + mlx;
+                    heads |= 1u << hl;
+                    a_rel = hl + mlh;
+                    cur = (uint32_t)a_rel;
+                    inside |= (cur < 32u ? ((1u << cur) - 1u) : FULL) & ~((2u << hl) - 1u);
+                    smc_cur = 67;
+                }
+                // ---- (D) un-insert what the serial loop never probed
+                if ((inside >> lane) & 1u) tab_set_raw(T, h, old);
+                // ---- (C) parallel emission
+                if (heads) {
+                    const int fh = __ffs(heads) - 1, lh = 31 - __clz(heads);
+                    const uint32_t lit0 = __shfl_sync(FULL, myLit, fh);
+                    if (a_rel0 < 0 && lit0 >= 15u) {
+                        // the open run reached 15 literals: its provisional bytes sit one length field too low -> re-copy them
+                        const uint32_t D0 = __shfl_sync(FULL, myD, fh);
+                        warp_copy(out + D0 + 2u + (lit0 - 15u) / 255u, base + anchor, (uint32_t)(-a_rel0), lane);
+                    }
+                    const uint32_t above = (heads >> lane) >> 1;
+                    const int nh = (int)lane + __ffs(above);                 // next head above this lane (if any)
+                    const uint32_t Dn = __shfl_sync(FULL, myD, nh & 31), litn = __shfl_sync(FULL, myLit, nh & 31);
+                    const uint32_t is_lit = ~inside & ~heads & ((1u << lh) - 1u);
+                    if ((is_lit >> lane) & 1u) {
+                        const uint32_t litx = litn >= 15u ? 1u + (litn - 15u) / 255u : 0u;
+                        out[Dn + 1u + litx + litn - (uint32_t)(nh - (int)lane)] = (uint8_t)Sw[0];
+                    }
+                    if ((heads >> lane) & 1u) {
+                        uint8_t *q = out + myD;
+                        const uint32_t code = myMl - 4u;
+                        q[0] = (uint8_t)(((myLit < 15u ? myLit : 15u) << 4) | (code < 15u ? code : 15u));
+                        q += 1;
+                        if (myLit >= 15u) {
+                            uint32_t rest = myLit - 15u;
+                            while (rest >= 255u) { *q++ = 255; rest -= 255u; }
+                            *q++ = (uint8_t)rest;
                         }
-                        if (lane < lit) d[1 + lane] = (uint8_t)v;
-                        // lanes 29,30,31: token, offset low, offset high
-                        if (lane >= 29u) {
-                            const uint32_t k = lane - 29u;
-                            const uint32_t val = k == 0 ? ((lit << 4) | code) : k == 1 ? offset : (offset >> 8);
-                            d[k == 0 ? 0u : lit + k] = (uint8_t)val;
-                        }
-                        d += lit + 3u;
-                    } else {
-                        d = emit_literals(d, S, anchor, lit, code < 15u ? code : 15u, lane);
-                        if (lane == 0) { d[0] = (uint8_t)offset; d[1] = (uint8_t)(offset >> 8); }
-                        d += 2;
+                        q += myLit;
+                        const uint32_t offset = (uint32_t)(p - cand);
+                        q[0] = (uint8_t)offset;
+                        q[1] = (uint8_t)(offset >> 8);
                         if (code >= 15u) {
-                            const uint32_t rest = code - 15u, n255 = rest / 255u;
-                            for (uint32_t i = lane; i < n255; i += 32) d[i] = 255;
-                            if (lane == 0) d[n255] = (uint8_t)(rest - n255 * 255u);
-                            d += n255 + 1;
+                            uint32_t rest = code - 15u;
+                            q += 2;
+                            while (rest >= 255u) { *q++ = 255; rest -= 255u; }
+                            *q = (uint8_t)rest;
                         }
                     }
-                    anchor = s0 + mlh;
-                    cur = (uint32_t)hl + (uint32_t)mlh;
-                    smc_cur = 67;
+                    anchor = w + a_rel;
+                    pend = 0;
                     smc = 67;
-                    if (cur >= 32u) break;
                 }
-                // (5) un-insert what the serial loop never probed
-                if (!((probed >> lane) & 1u)) tab_set_raw(T, h, old);
+                // literal lanes behind the last match: provisional bytes of the still-open sequence
+                if (cur < 32u) {
+                    if (lane >= cur) out[D + 1u + pend + (lane - cur)] = (uint8_t)Sw[0];
+                    pend += 32u - cur;
+                    smc = smc_cur + (32u - cur);
+                    cur = 32;
+                }
                 __syncwarp();
                 sIndex = w + (int32_t)cur;
                 continue;
@@ -461,7 +489,7 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
             }
         }
         const uint32_t code = (uint32_t)(ml - 4);
-        d = emit_literals(d, S, anchor, (uint32_t)(s0 - anchor), code < 15u ? code : 15u, lane);
+        uint8_t *d = emit_literals(out + D, S, anchor, (uint32_t)(s0 - anchor), code < 15u ? code : 15u, lane);
         const uint32_t offset = (uint32_t)(s0 - m0);
         if (lane == 0) { d[0] = (uint8_t)offset; d[1] = (uint8_t)(offset >> 8); }
         d += 2;
@@ -471,9 +499,11 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
             if (lane == 0) d[n255] = (uint8_t)(rest - n255 * 255u);
             d += n255 + 1;
         }
+        D = (uint32_t)(d - out);
+        pend = 0;
         sIndex = anchor = s0 + ml;
     }
-    d = emit_literals(d, S, anchor, (uint32_t)(sEnd - anchor), 0u, lane);
+    uint8_t *d = emit_literals(out + D, S, anchor, (uint32_t)(sEnd - anchor), 0u, lane);
     return (uint32_t)(d - out);
 }
 
