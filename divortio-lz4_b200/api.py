@@ -29,7 +29,7 @@ __all__ = [
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdlz4_b200.so")
+LIB_PATH = os.environ.get("DLZ4_LIB") or os.path.join(_HERE, "csrc", "libdlz4_b200.so")
 
 WARM_NONE, WARM_JENKINS, WARM_TABLE = 0, 1, 2
 HIST_RAW, HIST_FRAME = 0, 1

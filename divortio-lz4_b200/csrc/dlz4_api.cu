@@ -254,6 +254,15 @@ void dlz4_shard_range(uint64_t nblocks, uint32_t world, uint32_t rank, uint64_t 
     if (count) *count = hi - lo;
 }
 
+#ifdef DLZ4_PHASE_TIMING
+// profiling build only: read and clear the per-phase cycle counters
+extern "C" int dlz4_phase_counters(unsigned long long *out16) {
+    if (cudaMemcpyFromSymbol(out16, dlz4::g_phase, 16 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+    unsigned long long z[16] = {0};
+    return cudaMemcpyToSymbol(dlz4::g_phase, z, sizeof z) != cudaSuccess;
+}
+#endif
+
 // ---- pinned host memory for callers that want the full PCIe rate (N-API external ArrayBuffers) ---------
 void *dlz4_pinned_alloc(uint64_t bytes) {
     void *p = nullptr;

@@ -15,6 +15,20 @@
 
 namespace dlz4 {
 
+// Phase timing (profiling build only: -DDLZ4_PHASE_TIMING): cycles per phase of the window path, summed over warps.
+#ifdef DLZ4_PHASE_TIMING
+__device__ unsigned long long g_phase[16];
+#define PT_DECL unsigned long long pt_acc[12] = {0,0,0,0,0,0,0,0,0,0,0,0}; long long pt_t = clock64();
+#define PT_MARK(i) { const long long pt_n = clock64(); pt_acc[i] += (unsigned long long)(pt_n - pt_t); pt_t = pt_n; }
+#define PT_COUNT(i, v) { pt_acc[i] += (v); }
+#define PT_FLUSH if (lane_id() == 0) { for (int pt_k = 0; pt_k < 12; ++pt_k) atomicAdd(&g_phase[pt_k], pt_acc[pt_k]); }
+#else
+#define PT_DECL
+#define PT_MARK(i)
+#define PT_COUNT(i, v)
+#define PT_FLUSH
+#endif
+
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int kHashEntries = 16384;
 
@@ -265,8 +279,10 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
     const int32_t whi = sEnd;                                                                                // words starting below sEnd hold block bytes
     int32_t la = INT32_MIN;
     uint32_t LA = 0, LB = 0, LC = 0;
+    PT_DECL
 
     while (sIndex < mflimit) {
+        PT_MARK(0)
         if (smc <= 96u && sIndex + 67 <= sEnd) {
             const int32_t w = sIndex;
             const uint32_t wmis = (uint32_t)((reinterpret_cast<uintptr_t>(base) + (uint32_t)w) & 3u);
@@ -280,6 +296,7 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
                 LC = ldg_word_guard(base, li + 256, wlo, whi);
                 la = line;
             }
+            PT_MARK(1)
             // ---- (A) source bytes, lookup, candidate loads
             const uint32_t j0 = (uint32_t)(wa - la) >> 2;
             const uint32_t ji = (j0 + lane) & 31u;
@@ -297,15 +314,16 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
             const uint32_t old = tab_raw(T, h);
             const int32_t cand = tab_dec(T, old);
             const bool ok = cand >= 0 && cand != p && (((uint32_t)(p - cand)) >> 16) == 0;
-            uint32_t cwd[9];
-            uint32_t csh = 0;
-            if (ok) {                       // cand + 35 < p + 35 <= w + 66 < sEnd: all nine words hold block bytes
-                const uint32_t cmis = (uint32_t)((reinterpret_cast<uintptr_t>(base) + (uint32_t)cand) & 3u);
-                const uint32_t *cw = reinterpret_cast<const uint32_t *>(base + (cand - (int32_t)cmis));
-                csh = cmis * 8u;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) cwd[k] = __ldg(cw + k);
+            // candidate bytes cand .. cand+35 as three aligned 16-byte loads (3 L1 wavefronts per lane instead of 9)
+            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;
+            uint32_t cs = 0;
+            if (ok) {                       // cand + 35 < p + 35 <= w + 66 < sEnd, and the 16-byte granules holding them
+                cs = (uint32_t)((reinterpret_cast<uintptr_t>(base) + (uint32_t)cand) & 15u);
+                const uint4 *cq = reinterpret_cast<const uint4 *>(base + (cand - (int32_t)cs));
+                q0 = __ldg(cq); q1 = __ldg(cq + 1);
+                if (cs + 36u > 32u) q2 = __ldg(cq + 2);
             }
+            PT_MARK(2)
             // insert + read back while the loads are in flight
             const uint32_t mine = tab_enc(T, p);
             __syncwarp();
@@ -313,25 +331,41 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
             __syncwarp();
             const uint32_t rb = tab_raw(T, h);
             const uint32_t conflict = __ballot_sync(FULL, rb != mine);
+            PT_MARK(3)
             if (conflict) {
                 __syncwarp();
                 tab_set_raw(T, h, old);                 // same-slot lanes all hold the same `old`
                 __syncwarp();
+                PT_COUNT(10, 1)
             } else {
                 bool hit = false;
                 int32_t ml = 0;
-                if (ok && __funnelshift_r(cwd[0], cwd[1], csh) == Sw[0]) {
-                    hit = true;
-                    int32_t n = 28;
+                if (ok) {
+                    // words at byte offset cs of (q0,q1,q2): shift by whole words with two select levels, then by bits
+                    uint32_t v[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+                    if (cs & 8u) {
 #pragma unroll
-                    for (int k = 7; k >= 1; --k) {
-                        const uint32_t x = Sw[k] ^ __funnelshift_r(cwd[k], cwd[k + 1], csh);
-                        if (x) n = 4 * (k - 1) + ((__ffs(x) - 1) >> 3);
+                        for (int k = 0; k < 10; ++k) v[k] = v[k + 2];
                     }
-                    const int32_t lim = matchLimit - p;          // >= 31 here
-                    ml = 4 + n;
-                    ml = ml < lim ? ml : lim;
+                    if (cs & 4u) {
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) v[k] = v[k + 1];
+                    }
+                    const uint32_t csh = (cs & 3u) * 8u;
+                    if (__funnelshift_r(v[0], v[1], csh) == Sw[0]) {
+                        hit = true;
+                        int32_t n = 28;
+#pragma unroll
+                        for (int k = 7; k >= 1; --k) {
+                            const uint32_t x = Sw[k] ^ __funnelshift_r(v[k], v[k + 1], csh);
+                            if (x) n = 4 * (k - 1) + ((__ffs(x) - 1) >> 3);
+                        }
+                        const int32_t lim = matchLimit - p;          // >= 31 here
+                        ml = 4 + n;
+                        ml = ml < lim ? ml : lim;
+                    }
                 }
+                PT_MARK(4)
                 // ---- (B) resolve
                 const uint32_t hm = __ballot_sync(FULL, hit);
                 const int32_t a_rel0 = anchor - w;               // <= 0: literals pending from earlier windows
@@ -377,6 +411,7 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
                     inside |= (cur < 32u ? ((1u << cur) - 1u) : FULL) & ~((2u << hl) - 1u);
                     smc_cur = 67;
                 }
+                PT_MARK(5)
                 // ---- (D) un-insert what the serial loop never probed
                 if ((inside >> lane) & 1u) tab_set_raw(T, h, old);
                 // ---- (C) parallel emission
@@ -421,6 +456,7 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
                     pend = 0;
                     smc = 67;
                 }
+                PT_MARK(6)
                 // literal lanes behind the last match: provisional bytes of the still-open sequence
                 if (cur < 32u) {
                     if (lane >= cur) out[D + 1u + pend + (lane - cur)] = (uint8_t)Sw[0];
@@ -430,6 +466,8 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
                 }
                 __syncwarp();
                 sIndex = w + (int32_t)cur;
+                PT_MARK(7)
+                PT_COUNT(9, 1)
                 continue;
             }
         }
@@ -502,8 +540,11 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
         D = (uint32_t)(d - out);
         pend = 0;
         sIndex = anchor = s0 + ml;
+        PT_MARK(8)
+        PT_COUNT(11, 1)
     }
     uint8_t *d = emit_literals(out + D, S, anchor, (uint32_t)(sEnd - anchor), 0u, lane);
+    PT_FLUSH
     return (uint32_t)(d - out);
 }
 
