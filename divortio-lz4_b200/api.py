@@ -243,13 +243,24 @@ def decompressBlock(input, inputOffset, inputSize, output, outputOffset, diction
     return int(written.value)
 
 
-def compress_blocks(src, off, length, prefix=None, warm=WARM_NONE, init_table=None, ctx=None):
-    """Batched compressBlock over independent blocks.  Returns (dst, dst_off, comp_len)."""
+def compress_blocks(src, off, length, prefix=None, warm=WARM_NONE, init_table=None, ctx=None, packed=False):
+    """Batched compressBlock over independent blocks.  Returns (dst, dst_off, comp_len).
+    packed=True: blocks are written back to back (dst_off = running sum of comp_len) through the chunked PCIe pipeline."""
     ctx = ctx or default_context()
     src = ensureBuffer(src)
     off = np.ascontiguousarray(off, dtype=np.uint64)
     length = np.ascontiguousarray(length, dtype=np.uint32)
     n = len(off)
+    if packed:
+        dst = np.empty(int((length.astype(np.uint64) + length.astype(np.uint64) // 255 + 16).sum()), dtype=np.uint8)
+        comp = np.zeros(n, dtype=np.uint32)
+        st = lib().dlz4_compress_blocks(ctx.handle, _ptr(src), src.size, _ptr(off), _ptr(length), n, None, 0, WARM_NONE, None,
+                                        _ptr(dst), dst.size, None, _ptr(comp))
+        ctx.check(st)
+        dst_off = np.zeros(n, dtype=np.uint64)
+        if n:
+            dst_off[1:] = np.cumsum(comp.astype(np.uint64))[:-1]
+        return dst[:int(comp.astype(np.uint64).sum())], dst_off, comp
     bounds = (length.astype(np.uint64) + length.astype(np.uint64) // 255 + 16 + 15) & ~np.uint64(15)
     dst_off = np.zeros(n, dtype=np.uint64)
     if n:
@@ -269,11 +280,11 @@ def decompress_blocks(src, off, length, dst_off, dst_cap, dictionary=None, hist_
     """Batched decompressBlock.  Returns (dst, out_len, status)."""
     ctx = ctx or default_context()
     src = ensureBuffer(src)
-    off = np.ascontiguousarray(off, dtype=np.uint64)
+    off = np.ascontiguousarray(off, dtype=np.uint64) if off is not None else None      # None: packed input
     length = np.ascontiguousarray(length, dtype=np.uint32)
     dst_off = np.ascontiguousarray(dst_off, dtype=np.uint64)
     dst_cap = np.ascontiguousarray(dst_cap, dtype=np.uint32)
-    n = len(off)
+    n = len(length)
     total = int((dst_off + dst_cap).max()) if n else 0
     dst = np.zeros(total, dtype=np.uint8)
     out_len = np.zeros(n, dtype=np.uint32)

@@ -28,7 +28,8 @@ struct Buf {
 struct dlz4_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr, side = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr, copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t evp[64] = {};           // event pool of the chunked host pipeline
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_side = nullptr, ev_fork = nullptr;
     uint32_t *d_counter = nullptr;      // work-queue heads (one per launch slot)
     uint32_t *d_hash = nullptr;         // small result slots
@@ -107,17 +108,18 @@ const uint32_t kBlockMax[8] = {0, 0, 0, 0, 65536, 262144, 1048576, 4194304};
 // ---- launch helpers ----------------------------------------------------------------------------------
 int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len, uint32_t n,
                     uint32_t max_len, const uint8_t *prefix, uint32_t prefix_len, const int32_t *init_table, uint8_t *dst,
-                    const uint64_t *dst_off, uint32_t *comp_len, cudaStream_t st) {
+                    const uint64_t *dst_off, uint32_t *comp_len, cudaStream_t st, uint32_t *counter = nullptr) {
     if (n == 0) return DLZ4_OK;
-    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(uint32_t), st));
+    if (!counter) counter = ctx->d_counter;
+    CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
     if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr) {
         const int grid = (int)std::min<uint64_t>((n + kWarpsFresh16 - 1) / kWarpsFresh16, (uint64_t)ctx->sm_count);
         k_compress_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * kHashEntries * 2, st>>>(
-            src, src_off, src_len, n, dst, dst_off, comp_len, ctx->d_counter);
+            src, src_off, src_len, n, dst, dst_off, comp_len, counter);
     } else {
         const int grid = (int)std::min<uint64_t>((n + kWarpsGeneric32 - 1) / kWarpsGeneric32, (uint64_t)ctx->sm_count);
         k_compress_generic32<kWarpsGeneric32><<<grid, kWarpsGeneric32 * 32, kWarpsGeneric32 * kHashEntries * 4, st>>>(
-            src, src_off, src_len, n, prefix, prefix_len, init_table, dst, dst_off, comp_len, ctx->d_counter);
+            src, src_off, src_len, n, prefix, prefix_len, init_table, dst, dst_off, comp_len, counter);
     }
     ctx->launches++;
     CK(cudaGetLastError());
@@ -182,6 +184,9 @@ int dlz4_init(int device, dlz4_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : ctx->evp) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaEventCreate(&ctx->ev0));
     CK(cudaEventCreate(&ctx->ev1));
     CK(cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming));
@@ -214,6 +219,9 @@ void dlz4_shutdown(dlz4_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (cudaEvent_t e : ctx->evp) if (e) cudaEventDestroy(e);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     delete ctx;
@@ -296,13 +304,111 @@ int dlz4_compress_blocks_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *
     return launch_compress(ctx, src, src_off, src_len, nblocks, max_block_len, prefix, prefix_len, table, dst, dst_off, comp_len, st);
 }
 
+// Chunked host pipeline: H2D of chunk c+1, kernels of chunk c and D2H of chunk c-1 overlap on three streams.
+// Blocks must be ascending and non-overlapping in `src`; output is packed (block i directly after block i-1).
+static const uint64_t kChunkBytesMin = 128ull << 20;       // >= 128 MiB of uncompressed bytes per chunk, at most 24 chunks
+
+static int compress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_bytes, const uint64_t *src_off,
+                                  const uint32_t *src_len, uint32_t n, uint32_t max_len, uint8_t *dst, uint64_t dst_bytes,
+                                  uint32_t *comp_len) {
+    const uint64_t stride = (dlz4_compress_bound(max_len) + 15) & ~15ull;
+    const uint64_t src_pad = (src_bytes + 15) & ~(uint64_t)15;
+    CKS(reserve(ctx, ctx->work, src_pad + 16));
+    CKS(reserve(ctx, ctx->comp, (uint64_t)n * stride + 64));
+    CKS(reserve(ctx, ctx->seg, (uint64_t)n * stride + 64));
+    CKS(reserve(ctx, ctx->meta, (size_t)n * (8 + 8 + 4 + 4) + ((size_t)n + 64) * 8 + 256));
+    CKS(reserve_pinned(ctx, ctx->pin, 64 * 8 + (size_t)n * 4));      // chunk totals + comp_len staging (pageable D2H would block)
+    uint8_t *d_src = (uint8_t *)ctx->work.p, *d_comp = (uint8_t *)ctx->comp.p, *d_pack = (uint8_t *)ctx->seg.p;
+    uint64_t *d_soff = (uint64_t *)ctx->meta.p, *d_coff = d_soff + n, *d_pos = d_coff + n;     // d_pos: per chunk n_c + 1 entries
+    uint32_t *d_slen = (uint32_t *)(d_pos + n + 64), *d_clen = d_slen + n;
+    volatile uint64_t *h_tot = (volatile uint64_t *)ctx->pin.p;
+    uint32_t *h_clen = (uint32_t *)((uint8_t *)ctx->pin.p + 64 * 8);
+    cudaStream_t sks[2] = {ctx->stream, ctx->side}, si = ctx->copy_in, so = ctx->copy_out;
+    cudaStream_t sk = sks[0];
+
+    // chunk boundaries by source bytes
+    std::vector<uint32_t> cb{0};
+    uint64_t total_src = 0;
+    for (uint32_t i = 0; i < n; ++i) total_src += src_len[i];
+    const uint64_t target = std::max<uint64_t>(kChunkBytesMin, total_src / 24 + 1);
+    uint64_t acc = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        acc += src_len[i];
+        if (acc >= target || i + 1 == n) { cb.push_back(i + 1); acc = 0; }
+    }
+    const uint32_t nc = (uint32_t)cb.size() - 1;            // <= 25
+    // descriptors once (compressed scratch is worst-case strided)
+    std::vector<uint64_t> coff(n);
+    for (uint32_t i = 0; i < n; ++i) coff[i] = (uint64_t)i * stride;
+    CK(cudaMemcpyAsync(d_soff, src_off, (size_t)n * 8, cudaMemcpyHostToDevice, sk));
+    CK(cudaMemcpyAsync(d_coff, coff.data(), (size_t)n * 8, cudaMemcpyHostToDevice, sk));
+    CK(cudaMemcpyAsync(d_slen, src_len, (size_t)n * 4, cudaMemcpyHostToDevice, sk));
+    CK(cudaEventRecord(ctx->ev0, sk));
+    CK(cudaEventRecord(ctx->ev_fork, sk));
+    CK(cudaStreamWaitEvent(sks[1], ctx->ev_fork, 0));          // descriptors are visible to the second compute stream
+
+    uint64_t host_pos = 0;
+    auto drain = [&](uint32_t c) -> int {          // chunk c's kernels are done: ship its packed bytes
+        CK(cudaEventSynchronize(ctx->evp[32 + c]));
+        const uint64_t tot = h_tot[c];
+        if (host_pos + tot > dst_bytes) return DLZ4_E_OUTPUT_TOO_SMALL;
+        if (tot) CK(cudaMemcpyAsync(dst + host_pos, d_pack + (uint64_t)cb[c] * stride, tot, cudaMemcpyDeviceToHost, so));
+        host_pos += tot;
+        return DLZ4_OK;
+    };
+    for (uint32_t c = 0; c < nc; ++c) {
+        const uint32_t b0 = cb[c], b1 = cb[c + 1], m = b1 - b0;
+        const uint64_t lo = src_off[b0], hi = src_off[b1 - 1] + src_len[b1 - 1];
+        if (hi > lo) CK(cudaMemcpyAsync(d_src + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, si));
+        CK(cudaEventRecord(ctx->evp[c], si));
+        // chunks alternate between two compute streams (own work-queue counter each) so the next chunk's CTAs take over
+        // SMs as the previous chunk's last blocks drain
+        sk = sks[c & 1];
+        CK(cudaStreamWaitEvent(sk, ctx->evp[c], 0));
+        CKS(launch_compress(ctx, d_src, d_soff + b0, d_slen + b0, m, max_len, nullptr, 0, nullptr, d_comp, d_coff + b0, d_clen + b0, sk,
+                            ctx->d_counter + 1 + (c & 1)));
+        uint64_t *pos = d_pos + b0 + c;                                   // m + 1 entries
+        k_frame_layout<<<1, 1024, 0, sk>>>(d_slen + b0, d_clen + b0, m, 0, pos, nullptr, nullptr, 1);
+        k_frame_gather<<<(int)std::min<uint64_t>(m, (uint64_t)ctx->sm_count * 8), 256, 0, sk>>>(
+            d_src, d_soff + b0, d_slen + b0, d_comp, d_coff + b0, d_clen + b0, m, pos, d_pack + (uint64_t)b0 * stride, 1);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync((void *)(h_tot + c), pos + m, 8, cudaMemcpyDeviceToHost, sk));
+        CK(cudaMemcpyAsync(h_clen + b0, d_clen + b0, (size_t)m * 4, cudaMemcpyDeviceToHost, sk));
+        CK(cudaEventRecord(ctx->evp[32 + c], sk));
+        if (c >= 1) CKS(drain(c - 1));
+    }
+    if (nc) CKS(drain(nc - 1));
+    CK(cudaStreamSynchronize(so));
+    CK(cudaStreamSynchronize(sks[1]));
+    CK(cudaEventRecord(ctx->ev1, sks[0]));
+    CK(cudaStreamSynchronize(sks[0]));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    memcpy(comp_len, h_clen, (size_t)n * 4);
+    for (uint32_t i = 0; i < n; ++i)
+        if (comp_len[i] == 0xFFFFFFFFu) return DLZ4_E_INVALID_ARG;
+    return DLZ4_OK;
+}
+
 int dlz4_compress_blocks(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_bytes, const uint64_t *src_off, const uint32_t *src_len,
                          uint32_t nblocks, const uint8_t *prefix, uint32_t prefix_len, int warm, const int32_t *init_table,
                          uint8_t *dst, uint64_t dst_bytes, const uint64_t *dst_off, uint32_t *comp_len) {
-    if (!ctx || (nblocks && (!src_off || !src_len || !dst_off || !comp_len || !dst))) return DLZ4_E_INVALID_ARG;
+    if (!ctx || (nblocks && (!src_off || !src_len || !comp_len || !dst))) return DLZ4_E_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     uint32_t max_len = 0;
+    if (!dst_off) {
+        // packed output: block i directly follows block i-1 in dst (offsets = running sum of comp_len)
+        if (prefix_len || warm != DLZ4_WARM_NONE) return DLZ4_E_INVALID_ARG;
+        for (uint32_t i = 0; i < nblocks; ++i) {
+            if (src_off[i] + src_len[i] > src_bytes) return DLZ4_E_INVALID_ARG;
+            if (i && src_off[i] < src_off[i - 1] + src_len[i - 1]) return DLZ4_E_INVALID_ARG;     // ascending, disjoint
+            if (src_len[i] > max_len) max_len = src_len[i];
+            if (src_len[i] > 0x7FFFFFF0u) return DLZ4_E_TOO_LARGE;
+        }
+        if (!nblocks) return DLZ4_OK;
+        return compress_blocks_packed(ctx, src, src_bytes, src_off, src_len, nblocks, max_len, dst, dst_bytes, comp_len);
+    }
     for (uint32_t i = 0; i < nblocks; ++i) {
         if (src_off[i] + src_len[i] > src_bytes) return DLZ4_E_INVALID_ARG;
         if (dst_off[i] + dlz4_compress_bound(src_len[i]) > dst_bytes) return DLZ4_E_OUTPUT_TOO_SMALL;
@@ -352,6 +458,60 @@ int dlz4_compress_blocks(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_bytes, 
     return DLZ4_OK;
 }
 
+// Decode side of the chunked pipeline: packed compressed input (block i directly after block i-1), ascending disjoint outputs.
+static int decompress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_bytes, const uint32_t *src_len, uint32_t n,
+                                    uint8_t *dst, uint64_t dst_bytes, const uint64_t *dst_off, const uint32_t *dst_cap,
+                                    const uint8_t *dict, uint32_t dict_len, int hist_mode, uint32_t *out_len, uint8_t *status) {
+    std::vector<uint64_t> soff(n + 1, 0);
+    uint64_t total_out = 0;
+    for (uint32_t i = 0; i < n; ++i) { soff[i + 1] = soff[i] + src_len[i]; total_out += dst_cap[i]; }
+    if (soff[n] > src_bytes) return DLZ4_E_INVALID_ARG;
+    const uint64_t src_pad = (soff[n] + 15) & ~(uint64_t)15;
+    CKS(reserve(ctx, ctx->work, src_pad + dict_len + 32));
+    CKS(reserve(ctx, ctx->out, dst_bytes + 64));
+    CKS(reserve(ctx, ctx->meta, (size_t)n * (8 + 8 + 4 + 4 + 4 + 1) + 64));
+    uint8_t *d_src = (uint8_t *)ctx->work.p, *d_dict = d_src + src_pad, *d_dst = (uint8_t *)ctx->out.p;
+    uint64_t *d_soff = (uint64_t *)ctx->meta.p, *d_doff = d_soff + n;
+    uint32_t *d_slen = (uint32_t *)(d_doff + n), *d_cap = d_slen + n, *d_olen = d_cap + n;
+    uint8_t *d_status = (uint8_t *)(d_olen + n);
+    cudaStream_t sk = ctx->stream, si = ctx->copy_in, so = ctx->copy_out;
+    const uint64_t target = std::max<uint64_t>(kChunkBytesMin, total_out / 24 + 1);
+    std::vector<uint32_t> cb{0};
+    uint64_t acc = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        acc += dst_cap[i];
+        if (acc >= target || i + 1 == n) { cb.push_back(i + 1); acc = 0; }
+    }
+    const uint32_t nc = (uint32_t)cb.size() - 1;
+    if (dict_len) CK(cudaMemcpyAsync(d_dict, dict, dict_len, cudaMemcpyHostToDevice, sk));
+    CK(cudaMemcpyAsync(d_soff, soff.data(), (size_t)n * 8, cudaMemcpyHostToDevice, sk));
+    CK(cudaMemcpyAsync(d_doff, dst_off, (size_t)n * 8, cudaMemcpyHostToDevice, sk));
+    CK(cudaMemcpyAsync(d_slen, src_len, (size_t)n * 4, cudaMemcpyHostToDevice, sk));
+    CK(cudaMemcpyAsync(d_cap, dst_cap, (size_t)n * 4, cudaMemcpyHostToDevice, sk));
+    CK(cudaEventRecord(ctx->ev0, sk));
+    for (uint32_t c = 0; c < nc; ++c) {
+        const uint32_t b0 = cb[c], b1 = cb[c + 1], m = b1 - b0;
+        if (soff[b1] > soff[b0]) CK(cudaMemcpyAsync(d_src + soff[b0], src + soff[b0], soff[b1] - soff[b0], cudaMemcpyHostToDevice, si));
+        CK(cudaEventRecord(ctx->evp[c], si));
+        CK(cudaStreamWaitEvent(sk, ctx->evp[c], 0));
+        CKS(launch_decompress(ctx, d_src, d_soff + b0, d_slen + b0, m, d_dst, d_doff + b0, d_cap + b0, dict_len ? d_dict : nullptr, dict_len,
+                              hist_mode == DLZ4_HIST_FRAME, nullptr, d_olen + b0, d_status + b0, sk));
+        CK(cudaEventRecord(ctx->evp[32 + c], sk));
+        CK(cudaStreamWaitEvent(so, ctx->evp[32 + c], 0));
+        const uint64_t lo = dst_off[b0], hi = dst_off[b1 - 1] + dst_cap[b1 - 1];
+        if (hi > lo) CK(cudaMemcpyAsync(dst + lo, d_dst + lo, hi - lo, cudaMemcpyDeviceToHost, so));
+    }
+    CK(cudaEventRecord(ctx->ev1, sk));
+    CK(cudaMemcpyAsync(out_len, d_olen, (size_t)n * 4, cudaMemcpyDeviceToHost, sk));
+    CK(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, sk));
+    CK(cudaStreamSynchronize(sk));
+    CK(cudaStreamSynchronize(so));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    for (uint32_t i = 0; i < n; ++i)
+        if (status[i]) return status[i];
+    return DLZ4_OK;
+}
+
 int dlz4_decompress_blocks_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len, uint32_t nblocks,
                                uint8_t *dst, const uint64_t *dst_off, const uint32_t *dst_cap, const uint8_t *dict, uint32_t dict_len,
                                int hist_mode, uint32_t *out_len, uint8_t *status, void *stream) {
@@ -364,9 +524,22 @@ int dlz4_decompress_blocks_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t
 int dlz4_decompress_blocks(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_bytes, const uint64_t *src_off, const uint32_t *src_len,
                            uint32_t nblocks, uint8_t *dst, uint64_t dst_bytes, const uint64_t *dst_off, const uint32_t *dst_cap,
                            const uint8_t *dict, uint32_t dict_len, int hist_mode, uint32_t *out_len, uint8_t *status) {
-    if (!ctx || (nblocks && (!src_off || !src_len || !dst_off || !dst_cap || !out_len || !status))) return DLZ4_E_INVALID_ARG;
+    if (!ctx || (nblocks && (!src_len || !dst_off || !dst_cap || !out_len || !status))) return DLZ4_E_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    if (!src_off) {
+        // packed input (what the packed compress call returns): block i starts at the running sum of src_len
+        if (!nblocks) return DLZ4_OK;
+        bool ascending = true;
+        for (uint32_t i = 0; i < nblocks; ++i) {
+            if (dst_off[i] + dst_cap[i] > dst_bytes) return DLZ4_E_INVALID_ARG;
+            if (i && dst_off[i] < dst_off[i - 1] + dst_cap[i - 1]) ascending = false;
+        }
+        if (!ascending) return DLZ4_E_INVALID_ARG;
+        if (dict_len > 65536) { dict += dict_len - 65536; dict_len = 65536; }
+        return decompress_blocks_packed(ctx, src, src_bytes, src_len, nblocks, dst, dst_bytes, dst_off, dst_cap, dict, dict_len,
+                                        hist_mode, out_len, status);
+    }
     for (uint32_t i = 0; i < nblocks; ++i) {
         if (src_off[i] + src_len[i] > src_bytes) return DLZ4_E_INVALID_ARG;
         if (dst_off[i] + dst_cap[i] > dst_bytes) return DLZ4_E_INVALID_ARG;
@@ -546,12 +719,12 @@ int dlz4_frame_pack_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_o
     CKS(reserve(ctx, ctx->aux, (size_t)nblocks * 12 + kHashEntries * 4 + 256));
     uint64_t *d_doff = (uint64_t *)((uint8_t *)ctx->aux.p + kHashEntries * 4 + 64);
     uint32_t *d_dlen = (uint32_t *)(d_doff + nblocks);
-    k_frame_layout<<<1, 1024, 0, st>>>(src_len, comp_len, nblocks, block_checksum, block_pos, d_doff, d_dlen);
+    k_frame_layout<<<1, 1024, 0, st>>>(src_len, comp_len, nblocks, block_checksum, block_pos, d_doff, d_dlen, 0);
     ctx->launches++;
     CK(cudaGetLastError());
     if (nblocks) {
         const int grid = (int)std::min<uint64_t>(nblocks, (uint64_t)ctx->sm_count * 8);
-        k_frame_gather<<<grid, 256, 0, st>>>(src, src_off, src_len, comp, comp_off, comp_len, nblocks, block_pos, segment);
+        k_frame_gather<<<grid, 256, 0, st>>>(src, src_off, src_len, comp, comp_off, comp_len, nblocks, block_pos, segment, 0);
         ctx->launches++;
         CK(cudaGetLastError());
         if (block_checksum) CKS(launch_xxh32_batch(ctx, segment, d_doff, d_dlen, nblocks, 0, nullptr, segment, st));

@@ -924,9 +924,10 @@ __global__ void k_uniform_blocks(uint64_t first, uint64_t total, uint32_t block,
 
 // Stored-block rule (:221-231): compressed iff 0 < comp < len.  body[i] = 4 + size (+4 with block checksum).
 // Single CTA: sizes + exclusive scan into pos[0..n] in one pass (n is at most a few hundred thousand).
+// raw != 0: plain concatenation of the compressed blocks (packed batch output): body[i] = comp_len[i], no size word.
 __global__ void __launch_bounds__(1024)
 k_frame_layout(const uint32_t *__restrict__ src_len, const uint32_t *__restrict__ comp_len, uint32_t n, int block_checksum,
-               uint64_t *pos /* n+1 */, uint64_t *data_off /* n: pos+4 */, uint32_t *data_len /* n */) {
+               uint64_t *pos /* n+1 */, uint64_t *data_off /* n: pos+4 */, uint32_t *data_len /* n */, int raw) {
     __shared__ uint64_t warp_tot[32];
     __shared__ uint64_t carry_s;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -938,8 +939,8 @@ k_frame_layout(const uint32_t *__restrict__ src_len, const uint32_t *__restrict_
         uint32_t sz = 0;
         if (i < n) {
             const uint32_t c = comp_len[i], L = src_len[i];
-            sz = (c > 0 && c < L) ? c : L;
-            body = 4ull + sz + (block_checksum ? 4ull : 0ull);
+            sz = raw ? c : ((c > 0 && c < L) ? c : L);
+            body = raw ? (uint64_t)sz : 4ull + sz + (block_checksum ? 4ull : 0ull);
         }
         uint64_t x = body;
 #pragma unroll
@@ -955,7 +956,7 @@ k_frame_layout(const uint32_t *__restrict__ src_len, const uint32_t *__restrict_
         __syncthreads();
         const uint64_t carry = carry_s;
         const uint64_t excl = carry + (warp ? warp_tot[warp - 1] : 0) + x - body;
-        if (i < n) { pos[i] = excl; data_off[i] = excl + 4; data_len[i] = sz; }
+        if (i < n) { pos[i] = excl; if (data_off) { data_off[i] = excl + 4; data_len[i] = sz; } }
         __syncthreads();
         if (tid == 1023) carry_s = carry + warp_tot[31];
         __syncthreads();
@@ -967,18 +968,20 @@ k_frame_layout(const uint32_t *__restrict__ src_len, const uint32_t *__restrict_
 __global__ void __launch_bounds__(256)
 k_frame_gather(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ src_len,
                const uint8_t *__restrict__ comp, const uint64_t *__restrict__ comp_off, const uint32_t *__restrict__ comp_len,
-               uint32_t n, const uint64_t *__restrict__ pos, uint8_t *__restrict__ seg) {
+               uint32_t n, const uint64_t *__restrict__ pos, uint8_t *__restrict__ seg, int raw) {
     for (uint32_t b = blockIdx.x; b < n; b += gridDim.x) {
         const uint32_t c = comp_len[b], L = src_len[b];
-        const bool compressed = c > 0 && c < L;
+        const bool compressed = raw || (c > 0 && c < L);
         const uint32_t sz = compressed ? c : L;
         const uint8_t *s = compressed ? comp + comp_off[b] : src + src_off[b];
         uint8_t *d = seg + pos[b];
-        if (threadIdx.x < 4) {
-            const uint32_t word = compressed ? sz : (sz | 0x80000000u);
-            d[threadIdx.x] = (uint8_t)(word >> (8 * threadIdx.x));
+        if (!raw) {
+            if (threadIdx.x < 4) {
+                const uint32_t word = compressed ? sz : (sz | 0x80000000u);
+                d[threadIdx.x] = (uint8_t)(word >> (8 * threadIdx.x));
+            }
+            d += 4;
         }
-        d += 4;
         const uint32_t head = static_cast<uint32_t>(-reinterpret_cast<intptr_t>(d)) & 3u;
         const uint32_t h = head < sz ? head : sz;
         if (threadIdx.x < h) d[threadIdx.x] = s[threadIdx.x];

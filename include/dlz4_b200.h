@@ -85,6 +85,10 @@ void dlz4_shard_range(uint64_t nblocks, uint32_t world, uint32_t rank, uint64_t 
  *   "dict ++ msg" working buffer, srcStart = prefix_len); warm selects the initial table.
  *   Bytes are identical to the reference for the same (prefix, table, block).
  * Pointers of the _dev variants are device pointers (off/len arrays too).
+ *   Host variant only: dst_off == NULL selects PACKED output -- block i is written directly behind block i-1 (its offset
+ *   is the running sum of comp_len[]); blocks must then be ascending and disjoint in src, and the call runs as a chunked
+ *   pipeline (H2D of chunk c+1, kernels of chunk c, D2H of chunk c-1 overlap), moving only real bytes over PCIe.
+ *   dlz4_decompress_blocks accepts that layout with src_off == NULL.
  *   max_block_len: an upper bound of src_len[] known to the caller (0xFFFFFFFF if unknown); blocks of at most
  *   64 KiB with no prefix and DLZ4_WARM_NONE run on the 16-bit-table kernel (7 blocks in flight per SM instead of 3).
  */

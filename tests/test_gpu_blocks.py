@@ -221,3 +221,18 @@ def test_xxh32_single_and_batch(dl):
     got = dl.xxh32_batch(buf, off, ln)
     assert got.tolist() == [oracle.xxh32(corp[n]) for n in names]
     assert dl.xxHash32(b"") == 0x02CC5D05 and dl.xxHash32("Hello World") == 0xB1FD16EE   # reference KATs
+
+
+def test_packed_pipelined_host_path(dl):
+    """dst_off == NULL: packed output through the chunked H2D/compute/D2H pipeline; bytes identical to the strided call."""
+    from divortio_lz4_b200 import corpus
+    n = 300 * 1024 * 1024 + 777                       # > 2 chunks of 128 MiB
+    data = corpus.mixed(31, n)
+    off = np.arange(0, n, 65536, dtype=np.uint64)
+    ln = np.minimum(65536, n - off).astype(np.uint32)
+    dst, doff, clen = dl.compress_blocks(data, off, ln, packed=True)
+    odst, odoff, oclen = oracle.compress_blocks(data, off, ln)
+    assert np.array_equal(clen, oclen) and dst.size == int(clen.sum())
+    assert np.array_equal(oracle.xxh32_batch(dst, doff, clen), oracle.xxh32_batch(odst, odoff, oclen))
+    out, olen, status = dl.decompress_blocks(dst, None, clen, off, ln)
+    assert not status.any() and np.array_equal(olen, ln) and np.array_equal(out[:n], data)
