@@ -281,7 +281,10 @@ def run_b200(args):
                     if e2e else None),
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_compress_fresh16", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(ach / peak, 5), "traffic": None,
+                         "frac": round(ach / peak, 5),
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload, ncu --set full
+                         # (profiles/r01_bench_compress_full.txt: 1.0805 GB + 0.4451 GB)
+                         "traffic": 1525600000 if n == (1 << 30) else None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
                          "algorithmic_bytes_per_launch": n + csize},
             "detail": {"compress_gbs": round(args.steps * total / tc / 1e9, 3), "decompress_gbs": round(args.steps * total / td / 1e9, 3),
