@@ -739,6 +739,99 @@ __device__ uint32_t decompress_block_warp(const uint8_t *__restrict__ in, const 
     return (uint32_t)(op - out_pos);
 }
 
+// decompressBlock, leaner formulation (the one the kernels use): 32-bit indices relative to the block's own output
+// start `ob`, `hist` = bytes of earlier output directly before `ob` that may serve as history (frame mode; at most
+// 65536 matter because offsets are 16-bit), and literals + match of a sequence written in ONE merged pass whenever the
+// match source lies entirely before the bytes of that pass (offset >= min(lit + matchLen, 32), the common case on text):
+// lane j < lit takes in[...], lane j >= lit takes out[... - offset]; 32 bytes per round, coalesced.
+// Error checks happen in the reference's order (blockDecompress.js:74,75,128,151) so the first error reported is the same.
+__device__ uint32_t decompress_block_warp_v2(const uint8_t *__restrict__ in, const uint32_t n, uint8_t *const ob,
+                                             const uint32_t cap, const uint32_t hist, const uint8_t *__restrict__ dict,
+                                             const uint32_t dict_len, uint32_t *status) {
+    const uint32_t lane = lane_id();
+    uint32_t ip = 0, op = 0;
+    uint32_t st = ST_OK;
+    while (ip < n) {                                             // :55
+        const uint32_t token = in[ip++];                         // :58
+        uint32_t lit = token >> 4;                               // :61
+        if (lit == 15u) {                                        // :62-68
+            uint32_t b;
+            do {
+                if (ip >= n) { st = ST_MALFORMED; break; }
+                b = in[ip++]; lit += b;
+            } while (b == 255u);
+            if (st) break;
+        }
+        if ((uint64_t)op + lit > cap) { st = ST_OUTPUT_TOO_SMALL; break; }      // :74
+        if ((uint64_t)ip + lit > n) { st = ST_MALFORMED; break; }              // :75
+        const uint32_t litp = ip;
+        ip += lit;
+        if (ip >= n) {                                           // :123 last sequence: literals only
+            if (lit) warp_copy(ob + op, in + litp, lit, lane);
+            op += lit;
+            break;
+        }
+        if (ip + 2 > n) { if (lit) warp_copy(ob + op, in + litp, lit, lane); st = ST_MALFORMED; break; }
+        const uint32_t offset = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8);   // :126
+        ip += 2;
+        if (offset == 0) { st = ST_OFFSET_ZERO; break; }         // :128
+        uint32_t ml = token & 15u;                               // :131
+        if (ml == 15u) {                                         // :132-138
+            uint32_t b;
+            do {
+                if (ip >= n) { st = ST_MALFORMED; break; }
+                b = in[ip++]; ml += b;
+            } while (b == 255u);
+            if (st) break;
+        }
+        ml += 4;                                                 // :139
+        const int64_t src_rel = (int64_t)op + lit - offset;      // :142, relative to ob
+        if (src_rel < -(int64_t)hist) {
+            // :145-200 the match starts in the dictionary (ob - hist is output index 0)
+            if (lit) warp_copy(ob + op, in + litp, lit, lane);
+            op += lit;
+            const int64_t cs = src_rel + hist;                   // < 0
+            int64_t from_dict = -cs;
+            if (from_dict > ml) from_dict = ml;
+            const int64_t di = (int64_t)dict_len + cs;
+            if (di < 0 || di + from_dict > dict_len) { st = ST_DICT_OOB; break; }   // :150-152
+            if ((uint64_t)op + ml > cap) { st = ST_OUTPUT_TOO_SMALL; break; }
+            warp_copy(ob + op, dict + di, (uint32_t)from_dict, lane);
+            op += (uint32_t)from_dict;
+            const uint32_t rem = ml - (uint32_t)from_dict;
+            __syncwarp();
+            if (rem) warp_match_copy(ob + op, offset, rem, lane);
+            op += rem;
+            __syncwarp();
+            continue;
+        }
+        const uint32_t total = lit + ml;
+        if ((uint64_t)op + total > cap) {                        // literals fit (checked above), the match does not
+            st = ST_OUTPUT_TOO_SMALL;
+            break;
+        }
+        if (offset >= (total < 32u ? total : 32u)) {
+            // merged pass: every source byte of a round was written before that round
+            uint8_t *const d = ob + op;
+            const uint8_t *const ls = in + litp;
+            const uint8_t *const ms = d - offset;                // ms[j] is the match source of output byte j (j >= lit)
+            for (uint32_t base = 0; base < total; base += 32) {
+                const uint32_t j = base + lane;
+                if (j < total) d[j] = j < lit ? ls[j] : ms[j];
+                __syncwarp();
+            }
+        } else {
+            if (lit) warp_copy(ob + op, in + litp, lit, lane);
+            __syncwarp();
+            warp_match_copy(ob + op + lit, offset, ml, lane);
+            __syncwarp();
+        }
+        op += total;
+    }
+    *status = st;
+    return op;
+}
+
 // Batched decode, one warp per block, blocks handed out by an atomic counter.
 // hist_frame != 0: block i's output array starts at dst[0] (history = dict ++ dst[0..dst_off[i]));
 // otherwise each block's array starts at its own dst_off[i].
@@ -761,9 +854,11 @@ k_decompress_blocks(const uint8_t *__restrict__ src, const uint64_t *__restrict_
             st = ST_OK;
             if (w > dst_cap[b]) { st = ST_OUTPUT_TOO_SMALL; w = 0; }
             else warp_copy(dst + dst_off[b], src + src_off[b], w, lane);
-        } else if (hist_frame) w = decompress_block_warp(src + src_off[b], src_len[b], dst, (int64_t)dst_off[b],
-                                                  (int64_t)dst_off[b] + dst_cap[b], dict, dict_len, &st);
-        else w = decompress_block_warp(src + src_off[b], src_len[b], dst + dst_off[b], 0, dst_cap[b], dict, dict_len, &st);
+        } else {
+            const uint64_t o = dst_off[b];
+            const uint32_t hist = hist_frame ? (uint32_t)(o < 65536ull ? o : 65536ull) : 0u;
+            w = decompress_block_warp_v2(src + src_off[b], src_len[b], dst + o, dst_cap[b], hist, dict, dict_len, &st);
+        }
         if (lane == 0) { out_len[b] = w; status[b] = (uint8_t)st; }
     }
 }
@@ -787,7 +882,9 @@ k_decompress_chain(const uint8_t *__restrict__ src, const uint64_t *__restrict__
                 else warp_copy(dst + op, src + src_off[b], w, lane);
                 __syncwarp();
             } else {
-                w = decompress_block_warp(src + src_off[b], src_len[b], dst, op, (int64_t)dst_total, dict, dict_len, &st);
+                const uint64_t room = dst_total - (uint64_t)op;
+                w = decompress_block_warp_v2(src + src_off[b], src_len[b], dst + op, (uint32_t)(room < 0xFFFFFFFFull ? room : 0xFFFFFFFFull),
+                                             (uint32_t)(op < 65536 ? op : 65536), dict, dict_len, &st);
             }
         }
         if (lane == 0) { out_len[b] = w; status[b] = (uint8_t)st; }
