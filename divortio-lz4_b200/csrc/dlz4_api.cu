@@ -114,11 +114,11 @@ int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, 
     CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
     if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr) {
         const int grid = (int)std::min<uint64_t>((n + kWarpsFresh16 - 1) / kWarpsFresh16, (uint64_t)ctx->sm_count);
-        k_compress_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * kHashEntries * 2, st>>>(
+        k_compress_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * (kHashEntries * 2 + kRingBytes), st>>>(
             src, src_off, src_len, n, dst, dst_off, comp_len, counter);
     } else {
         const int grid = (int)std::min<uint64_t>((n + kWarpsGeneric32 - 1) / kWarpsGeneric32, (uint64_t)ctx->sm_count);
-        k_compress_generic32<kWarpsGeneric32><<<grid, kWarpsGeneric32 * 32, kWarpsGeneric32 * kHashEntries * 4, st>>>(
+        k_compress_generic32<kWarpsGeneric32><<<grid, kWarpsGeneric32 * 32, kWarpsGeneric32 * (kHashEntries * 4 + kRingBytes), st>>>(
             src, src_off, src_len, n, prefix, prefix_len, init_table, dst, dst_off, comp_len, counter);
     }
     ctx->launches++;
@@ -158,7 +158,7 @@ int launch_xxh32_stream(dlz4_ctx *ctx, const uint8_t *data, uint64_t len, uint32
 
 int launch_chain(dlz4_ctx *ctx, const uint8_t *work, int32_t start, int32_t total, int32_t block, uint32_t nblocks,
                  int32_t *table_io, uint8_t *dst, uint64_t stride, uint32_t *comp_len, cudaStream_t st) {
-    k_compress_chain<<<1, 32, kHashEntries * 4, st>>>(work, start, total, block, nblocks, table_io, dst, stride, comp_len);
+    k_compress_chain<<<1, 32, kHashEntries * 4 + kRingBytes, st>>>(work, start, total, block, nblocks, table_io, dst, stride, comp_len);
     ctx->launches++;
     CK(cudaGetLastError());
     return DLZ4_OK;
@@ -196,10 +196,10 @@ int dlz4_init(int device, dlz4_ctx **out) {
     CK(cudaMalloc(&ctx->d_total, 64));
     CK(cudaMalloc(&ctx->d_table, kHashEntries * sizeof(int32_t)));
     CK(cudaFuncSetAttribute(k_compress_fresh16<kWarpsFresh16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            kWarpsFresh16 * kHashEntries * 2));
+                            kWarpsFresh16 * (kHashEntries * 2 + kRingBytes)));
     CK(cudaFuncSetAttribute(k_compress_generic32<kWarpsGeneric32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            kWarpsGeneric32 * kHashEntries * 4));
-    CK(cudaFuncSetAttribute(k_compress_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kHashEntries * 4));
+                            kWarpsGeneric32 * (kHashEntries * 4 + kRingBytes)));
+    CK(cudaFuncSetAttribute(k_compress_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kHashEntries * 4 + kRingBytes));
     return DLZ4_OK;
 }
 

@@ -237,6 +237,17 @@ __device__ __forceinline__ void tab_set_raw(Tab32 &T, uint32_t h, uint32_t v) { 
 __device__ __forceinline__ uint32_t tab_enc(const Tab32 &, int32_t p) { return (uint32_t)(p + 1); }
 __device__ __forceinline__ int32_t tab_dec(const Tab32 &, uint32_t raw) { return (int32_t)raw - 1; }
 
+// 4-byte cp.async (LDGSTS) into shared memory; src_size 0 zero-fills without touching global memory.
+__device__ __forceinline__ void cp_async4(uint32_t smem_addr, const void *gptr, uint32_t src_size) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(smem_addr), "l"(gptr), "r"(src_size) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+constexpr int kRingLines = 3;                      // forward ring: three 128-byte lines per warp
+constexpr int kRingBytes = kRingLines * 128;
+
 // aligned word at byte index `idx` (multiple of 4 in address terms) of a read-only global buffer, 0 outside [lo, hi)
 __device__ __forceinline__ uint32_t ldg_word_guard(const uint8_t *base, int32_t idx, int32_t lo, int32_t hi) {
     return (idx >= lo && idx < hi) ? __ldg(reinterpret_cast<const uint32_t *>(base + idx)) : 0u;
@@ -261,7 +272,7 @@ __device__ __forceinline__ uint32_t ldg_word_guard(const uint8_t *base, int32_t 
 // compress_block_warp (exact for every case).
 template <class Tab>
 __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, const int32_t start, const int32_t len, Tab &T,
-                                           uint8_t *const out) {
+                                           uint8_t *const out, uint32_t *const ring /* kRingBytes of shared memory */) {
     const uint32_t lane = lane_id();
     const uint32_t lt = (1u << lane) - 1u;
     const int32_t sEnd = start + len;
@@ -273,12 +284,15 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
     uint32_t pend = 0;           // literals of the open sequence already stored provisionally at out[D+1 ..)
     SrcFlat S{base};
 
-    // forward line cache: three 128-byte lines in registers, one word per lane each
-    const uint32_t gmis = (uint32_t)(reinterpret_cast<uintptr_t>(base) & 127u);
-    const int32_t wlo = start - (int32_t)((reinterpret_cast<uintptr_t>(base) + (uint32_t)start) & 3u);   // first word holding block bytes
-    const int32_t whi = sEnd;                                                                                // words starting below sEnd hold block bytes
-    int32_t la = INT32_MIN;
-    uint32_t LA = 0, LB = 0, LC = 0;
+    // forward ring: the 128-byte lines around the window live in a 3-line shared-memory ring filled by cp.async one line
+    // ahead of use (no registers, no scoreboard dependency between the prefetch and the window's own loads)
+    const uintptr_t gaddr = reinterpret_cast<uintptr_t>(base);
+    const int32_t wlo = start - (int32_t)((gaddr + (uint32_t)start) & 3u);   // first word holding block bytes
+    const int32_t whi = sEnd;                                                  // words starting below sEnd hold block bytes
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint64_t line0 = (gaddr + (uint32_t)wlo) >> 7;                        // line of the block's first word
+    uint32_t next_line = 0;                                                    // next line (relative to line0) to fetch
+    bool ring_cold = true;
     PT_DECL
 
     while (sIndex < mflimit) {
@@ -287,21 +301,26 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
             const int32_t w = sIndex;
             const uint32_t wmis = (uint32_t)((reinterpret_cast<uintptr_t>(base) + (uint32_t)w) & 3u);
             const int32_t wa = w - (int32_t)wmis;                                   // word-aligned window base
-            const int32_t line = wa - (int32_t)(((uint32_t)wa + gmis) & 127u);      // 128-byte line holding wa
-            if (line != la) {
-                const int32_t li = line + 4 * (int32_t)lane;
-                if (line == la + 128) { LA = LB; LB = LC; }
-                else if (line == la + 256) { LA = LC; LB = ldg_word_guard(base, li + 128, wlo, whi); }
-                else { LA = ldg_word_guard(base, li, wlo, whi); LB = ldg_word_guard(base, li + 128, wlo, whi); }
-                LC = ldg_word_guard(base, li + 256, wlo, whi);
-                la = line;
+            const uintptr_t waddr = gaddr + (intptr_t)wa;
+            const uint32_t L = (uint32_t)((waddr >> 7) - line0);                    // line holding wa, relative to line0
+            if (ring_cold || next_line < L + 3u) {
+                if (ring_cold || next_line < L) next_line = L;                      // first window / jumped past the ring
+                ring_cold = false;
+                const bool one_ahead = next_line > L + 1u;                          // this refill only fetches line L+2
+                do {
+                    const int32_t idx = wlo - (int32_t)((gaddr + (uint32_t)wlo) & 127u) + (int32_t)(next_line << 7) + 4 * (int32_t)lane;
+                    const bool in = idx >= wlo && idx < whi;
+                    cp_async4(ring_s + (next_line % (uint32_t)kRingLines) * 128u + 4u * lane, base + (in ? idx : wlo), in ? 4u : 0u);
+                    cp_async_commit();
+                    ++next_line;
+                } while (next_line < L + 3u);
+                if (one_ahead) cp_async_wait<1>(); else cp_async_wait<0>();        // lines L and L+1 have landed
+                __syncwarp();
             }
             PT_MARK(1)
             // ---- (A) source bytes, lookup, candidate loads
-            const uint32_t j0 = (uint32_t)(wa - la) >> 2;
-            const uint32_t ji = (j0 + lane) & 31u;
-            const uint32_t xa = __shfl_sync(FULL, LA, ji), xb = __shfl_sync(FULL, LB, ji);
-            const uint32_t Tw = (j0 + lane < 32u) ? xa : xb;                        // word (wa/4 + lane)
+            const uint32_t wo = (uint32_t)(waddr & 127u) / 4u + lane;             // word offset from the start of line L
+            const uint32_t Tw = ring[((L + (wo >> 5)) % (uint32_t)kRingLines) * 32u + (wo & 31u)];   // word (wa/4 + lane)
             const int32_t p = w + (int32_t)lane;
             const uint32_t o = wmis + lane, wi = o >> 2, sh = (o & 3u) * 8u;
             uint32_t tw[9];
@@ -564,6 +583,7 @@ k_compress_fresh16(const uint8_t *__restrict__ src, const uint64_t *__restrict__
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     uint16_t *tab = reinterpret_cast<uint16_t *>(smem) + warp * kHashEntries;
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + WARPS * kHashEntries * 2 + warp * kRingBytes);
     for (;;) {
         const uint32_t b = next_block(counter, lane);
         if (b >= nblocks) break;
@@ -573,7 +593,7 @@ k_compress_fresh16(const uint8_t *__restrict__ src, const uint64_t *__restrict__
         for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         Tab16 T{tab, 0};
-        const uint32_t c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b]);
+        const uint32_t c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], ring);
         if (lane == 0) comp_len[b] = c;
         __syncwarp();
     }
@@ -590,6 +610,7 @@ k_compress_generic32(const uint8_t *__restrict__ src, const uint64_t *__restrict
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     int32_t *tab = reinterpret_cast<int32_t *>(smem) + warp * kHashEntries;
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + WARPS * kHashEntries * 4 + warp * kRingBytes);
     for (;;) {
         const uint32_t b = next_block(counter, lane);
         if (b >= nblocks) break;
@@ -607,7 +628,7 @@ k_compress_generic32(const uint8_t *__restrict__ src, const uint64_t *__restrict
             SrcSplit S{prefix, (int32_t)prefix_len, src + src_off[b]};
             c = compress_block_warp(S, (int32_t)prefix_len, (int32_t)src_len[b], T, dst + dst_off[b]);
         } else {
-            c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)src_len[b], T, dst + dst_off[b]);
+            c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)src_len[b], T, dst + dst_off[b], ring);
         }
         if (lane == 0) comp_len[b] = c;
         __syncwarp();
@@ -635,7 +656,8 @@ k_compress_chain(const uint8_t *__restrict__ work, int32_t start, int32_t total_
     for (uint32_t k = 0; k < nblocks; ++k) {
         const int32_t pos = start + (int32_t)k * block_size;
         const int32_t blen = (end - pos) < block_size ? (end - pos) : block_size;
-        const uint32_t c = compress_block_warp_v2(work, pos, blen, T, dst + (uint64_t)k * dst_stride);
+        const uint32_t c = compress_block_warp_v2(work, pos, blen, T, dst + (uint64_t)k * dst_stride,
+                                                  reinterpret_cast<uint32_t *>(smem + kHashEntries * 4));
         if (lane == 0) comp_len[k] = c;
         __syncwarp();
     }
