@@ -270,18 +270,31 @@ __device__ __forceinline__ uint32_t ldg_word_guard(const uint8_t *base, int32_t 
 //   (D) un-inserts the positions the serial loop would never have probed (inside matches).
 // A window with a same-slot pair, the sparse schedule and the last bytes of a block fall back to the batch step of
 // compress_block_warp (exact for every case).
+// Parse state of one block (what the serial loop carries from probe to probe, plus the output cursor).
+struct SpanState {
+    int32_t sIndex, anchor;
+    uint32_t smc;                // searchMatchCount
+    uint32_t D;                  // output offset of the open sequence's token
+    uint32_t pend;               // literals of the open sequence already stored provisionally at out[D+1 ..)
+};
+
+// Runs the single-warp parse from state `st`.  yield_room == 0: to the end of the block, final literals included; returns
+// the compressed size.  yield_room > 0 (team kernel): returns 0xFFFFFFFF as soon as the schedule is dense again
+// (smc <= 96) with at least yield_room bytes left, leaving the state in `st`; otherwise finishes the block as above.
 template <class Tab>
-__device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, const int32_t start, const int32_t len, Tab &T,
-                                           uint8_t *const out, uint32_t *const ring /* kRingBytes of shared memory */) {
+__device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const int32_t start, const int32_t len, Tab &T,
+                                       uint8_t *const out, uint32_t *const ring /* kRingBytes of shared memory */,
+                                       SpanState &st, const int32_t yield_room) {
     const uint32_t lane = lane_id();
     const uint32_t lt = (1u << lane) - 1u;
     const int32_t sEnd = start + len;
     const int32_t mflimit = sEnd - 12;
     const int32_t matchLimit = sEnd - 5;
-    int32_t sIndex = start, anchor = start;
-    uint32_t smc = 67;
-    uint32_t D = 0;              // output offset of the open sequence's token
-    uint32_t pend = 0;           // literals of the open sequence already stored provisionally at out[D+1 ..)
+    int32_t sIndex = st.sIndex, anchor = st.anchor;
+    uint32_t smc = st.smc;
+    uint32_t D = st.D;
+    uint32_t pend = st.pend;
+    bool progressed = false;
     SrcFlat S{base};
 
     // forward ring: the 128-byte lines around the window live in a 3-line shared-memory ring filled by cp.async one line
@@ -297,6 +310,11 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
 
     while (sIndex < mflimit) {
         PT_MARK(0)
+        if (yield_room > 0 && progressed && smc <= 96u && sIndex + yield_room <= sEnd) {
+            st.sIndex = sIndex; st.anchor = anchor; st.smc = smc; st.D = D; st.pend = pend;
+            return 0xFFFFFFFFu;
+        }
+        progressed = true;
         if (smc <= 96u && sIndex + 67 <= sEnd) {
             const int32_t w = sIndex;
             const uint32_t wmis = (uint32_t)((reinterpret_cast<uintptr_t>(base) + (uint32_t)w) & 3u);
@@ -565,6 +583,14 @@ __device__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, con
     uint8_t *d = emit_literals(out + D, S, anchor, (uint32_t)(sEnd - anchor), 0u, lane);
     PT_FLUSH
     return (uint32_t)(d - out);
+}
+
+// One LZ4 block by one warp, from a fresh parse state (see compress_span_warp).
+template <class Tab>
+__device__ __forceinline__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, const int32_t start, const int32_t len,
+                                                           Tab &T, uint8_t *const out, uint32_t *const ring) {
+    SpanState st{start, start, 67u, 0u, 0u};
+    return compress_span_warp(base, start, len, T, out, ring, st, 0);
 }
 
 // ------------------------------------------------------------------ compress kernels
