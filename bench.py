@@ -280,7 +280,7 @@ def run_b200(args):
             "e2e": ({"value": round(total / te / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
                     if e2e else None),
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_compress_fresh16", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_compress_fresh16h", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(ach / peak, 5),
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload, ncu --set full
                          # (profiles/r01_bench_compress_full.txt: 1.0805 GB + 0.4451 GB)

@@ -4,6 +4,7 @@
 #include "../../include/dlz4_b200.h"
 #include "dlz4_kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -35,6 +36,10 @@ struct dlz4_ctx {
     uint32_t *d_hash = nullptr;         // small result slots
     uint64_t *d_total = nullptr;
     int32_t *d_table = nullptr;         // int32[16384] scratch table
+    int hy_smem_warps = 0, hy_gl_warps = 0;   // hybrid compress kernel: warps with shared-memory / L2-resident tables per SM
+    uint16_t *d_gtabs = nullptr;        // sm_count x hy_gl_warps tables of 16384 x u16
+    size_t gtabs_bytes = 0;
+    cudaAccessPolicyWindow gtabs_window = {};   // L2 persistence for the tables (num_bytes == 0: unavailable)
     Buf work, comp, seg, out, meta, aux, pin;
     std::string last_error;
     uint64_t launches = 0;
@@ -112,7 +117,22 @@ int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, 
     if (n == 0) return DLZ4_OK;
     if (!counter) counter = ctx->d_counter;
     CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
-    if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr) {
+    if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr && ctx->hy_gl_warps > 0) {
+        const int wpc = ctx->hy_smem_warps + ctx->hy_gl_warps;
+        const int grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count);
+        const uint32_t active = (uint32_t)std::min<uint64_t>((n + grid - 1) / grid, (uint64_t)wpc);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(wpc * 32); cfg.stream = st;
+        cfg.dynamicSmemBytes = (size_t)ctx->hy_smem_warps * kHashEntries * 2 + (size_t)wpc * kRingBytes;
+        cudaLaunchAttribute at[1];
+        if (ctx->gtabs_window.num_bytes) {       // keep the L2-resident tables from being evicted by the streamed blocks
+            at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            at[0].val.accessPolicyWindow = ctx->gtabs_window;
+            cfg.attrs = at; cfg.numAttrs = 1;
+        }
+        CK(cudaLaunchKernelEx(&cfg, k_compress_fresh16h, src, src_off, src_len, n, dst, dst_off, comp_len, counter,
+                              (uint32_t)ctx->hy_smem_warps, ctx->d_gtabs, active));
+    } else if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr) {
         const int grid = (int)std::min<uint64_t>((n + kWarpsFresh16 - 1) / kWarpsFresh16, (uint64_t)ctx->sm_count);
         k_compress_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * (kHashEntries * 2 + kRingBytes), st>>>(
             src, src_off, src_len, n, dst, dst_off, comp_len, counter);
@@ -197,6 +217,36 @@ int dlz4_init(int device, dlz4_ctx **out) {
     CK(cudaMalloc(&ctx->d_table, kHashEntries * sizeof(int32_t)));
     CK(cudaFuncSetAttribute(k_compress_fresh16<kWarpsFresh16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kWarpsFresh16 * (kHashEntries * 2 + kRingBytes)));
+    {   // hybrid kernel shape (tuning knobs for experiments: DLZ4_HY_SMEM_WARPS / DLZ4_HY_GL_WARPS; 0 global warps = off)
+        const char *es = getenv("DLZ4_HY_SMEM_WARPS"), *eg = getenv("DLZ4_HY_GL_WARPS");
+        ctx->hy_smem_warps = es ? atoi(es) : 4;
+        ctx->hy_gl_warps = eg ? atoi(eg) : 24;
+        if (ctx->hy_smem_warps < 0) ctx->hy_smem_warps = 0;
+        if (ctx->hy_smem_warps > 7) ctx->hy_smem_warps = 7;
+        if (ctx->hy_gl_warps < 0) ctx->hy_gl_warps = 0;
+        if (ctx->hy_smem_warps + ctx->hy_gl_warps > kMaxWarpsHybrid) ctx->hy_gl_warps = kMaxWarpsHybrid - ctx->hy_smem_warps;
+        size_t sm = (size_t)ctx->hy_smem_warps * kHashEntries * 2 + (size_t)(ctx->hy_smem_warps + ctx->hy_gl_warps) * kRingBytes;
+        while (sm > 232448 && ctx->hy_gl_warps > 0) { ctx->hy_gl_warps--; sm -= kRingBytes; }
+        if (ctx->hy_gl_warps > 0) {
+            ctx->gtabs_bytes = (size_t)ctx->sm_count * ctx->hy_gl_warps * kHashEntries * 2;
+            CK(cudaMalloc(&ctx->d_gtabs, ctx->gtabs_bytes));
+            const char *ep = getenv("DLZ4_HY_PERSIST");
+            if (ep && atoi(ep) != 0 && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+                const size_t set_aside = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, ctx->gtabs_bytes);
+                CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
+                ctx->gtabs_window.base_ptr = ctx->d_gtabs;
+                ctx->gtabs_window.num_bytes = std::min<size_t>(ctx->gtabs_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+                ctx->gtabs_window.hitRatio = std::min(1.0f, (float)set_aside / (float)ctx->gtabs_window.num_bytes);
+                ctx->gtabs_window.hitProp = cudaAccessPropertyPersisting;
+                ctx->gtabs_window.missProp = cudaAccessPropertyStreaming;
+            }
+            if (getenv("DLZ4_DEBUG"))
+                fprintf(stderr, "dlz4: hybrid %d+%d warps, tables %zu MiB, L2 %d MiB, persisting max %d MiB, window max %d MiB, hitRatio %.2f\n",
+                        ctx->hy_smem_warps, ctx->hy_gl_warps, ctx->gtabs_bytes >> 20, prop.l2CacheSize >> 20,
+                        prop.persistingL2CacheMaxSize >> 20, prop.accessPolicyMaxWindowSize >> 20, ctx->gtabs_window.hitRatio);
+            CK(cudaFuncSetAttribute(k_compress_fresh16h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        }
+    }
     CK(cudaFuncSetAttribute(k_compress_generic32<kWarpsGeneric32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kWarpsGeneric32 * (kHashEntries * 4 + kRingBytes)));
     CK(cudaFuncSetAttribute(k_compress_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kHashEntries * 4 + kRingBytes));
@@ -215,6 +265,7 @@ void dlz4_shutdown(dlz4_ctx *ctx) {
     if (ctx->d_hash) cudaFree(ctx->d_hash);
     if (ctx->d_total) cudaFree(ctx->d_total);
     if (ctx->d_table) cudaFree(ctx->d_table);
+    if (ctx->d_gtabs) cudaFree(ctx->d_gtabs);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);

@@ -113,6 +113,14 @@ struct Tab16 {
     __device__ __forceinline__ int32_t get(uint32_t h) const { return start + (int32_t)t[h]; }
     __device__ __forceinline__ void put(uint32_t h, int32_t p) { t[h] = (uint16_t)(p - start); }
 };
+// Same encoding as Tab16, but the 32 KiB live in global memory and are accessed with .cg loads / stores: L2-resident
+// (126 MB of L2 hold ~2000 such tables next to the streamed data), never cached in L1.  Lets an SM run more block chains
+// than its shared memory has room for tables; ordering between lanes of the owning warp comes from __syncwarp().
+struct TabG16 {
+    uint16_t *t; int32_t start;
+    __device__ __forceinline__ int32_t get(uint32_t h) const { return start + (int32_t)__ldcg(t + h); }
+    __device__ __forceinline__ void put(uint32_t h, int32_t p) { __stcg(t + h, (uint16_t)(p - start)); }
+};
 // The reference's own representation: Int32, value = position + 1, <= 0 empty (blockCompress.js:54-55).
 struct Tab32 {
     int32_t *t;
@@ -232,6 +240,10 @@ __device__ __forceinline__ uint32_t tab_raw(const Tab16 &T, uint32_t h) { return
 __device__ __forceinline__ void tab_set_raw(Tab16 &T, uint32_t h, uint32_t v) { T.t[h] = (uint16_t)v; }
 __device__ __forceinline__ uint32_t tab_enc(const Tab16 &T, int32_t p) { return (uint32_t)(p - T.start) & 0xFFFFu; }
 __device__ __forceinline__ int32_t tab_dec(const Tab16 &T, uint32_t raw) { return T.start + (int32_t)raw; }
+__device__ __forceinline__ uint32_t tab_raw(const TabG16 &T, uint32_t h) { return __ldcg(T.t + h); }
+__device__ __forceinline__ void tab_set_raw(TabG16 &T, uint32_t h, uint32_t v) { __stcg(T.t + h, (uint16_t)v); }
+__device__ __forceinline__ uint32_t tab_enc(const TabG16 &T, int32_t p) { return (uint32_t)(p - T.start) & 0xFFFFu; }
+__device__ __forceinline__ int32_t tab_dec(const TabG16 &T, uint32_t raw) { return T.start + (int32_t)raw; }
 __device__ __forceinline__ uint32_t tab_raw(const Tab32 &T, uint32_t h) { return (uint32_t)T.t[h]; }
 __device__ __forceinline__ void tab_set_raw(Tab32 &T, uint32_t h, uint32_t v) { T.t[h] = (int32_t)v; }
 __device__ __forceinline__ uint32_t tab_enc(const Tab32 &, int32_t p) { return (uint32_t)(p + 1); }
@@ -361,18 +373,12 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
                 if (cs + 36u > 32u) q2 = __ldg(cq + 2);
             }
             PT_MARK(2)
-            // insert + read back while the loads are in flight
+            // two lanes of the window in one slot?  Then a later lane's candidate depends on the parse -> batch step.
+            // Nothing is inserted yet, so the table is still the exact pre-window state either way.
             const uint32_t mine = tab_enc(T, p);
-            __syncwarp();
-            tab_set_raw(T, h, mine);
-            __syncwarp();
-            const uint32_t rb = tab_raw(T, h);
-            const uint32_t conflict = __ballot_sync(FULL, rb != mine);
+            const uint32_t conflict = __ballot_sync(FULL, __match_any_sync(FULL, h) != (1u << lane));
             PT_MARK(3)
             if (conflict) {
-                __syncwarp();
-                tab_set_raw(T, h, old);                 // same-slot lanes all hold the same `old`
-                __syncwarp();
                 PT_COUNT(10, 1)
             } else {
                 bool hit = false;
@@ -449,8 +455,10 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
                     smc_cur = 67;
                 }
                 PT_MARK(5)
-                // ---- (D) un-insert what the serial loop never probed
-                if ((inside >> lane) & 1u) tab_set_raw(T, h, old);
+                // ---- (D) insert exactly the positions the serial loop probed: every lane of the window that is not inside a
+                //      match (heads and literals; lanes behind the last match are literals).  One store per probed lane, no
+                //      speculative insert to undo.
+                if (!((inside >> lane) & 1u)) tab_set_raw(T, h, mine);
                 // ---- (C) parallel emission
                 if (heads) {
                     const int fh = __ffs(heads) - 1, lh = 31 - __clz(heads);
@@ -620,6 +628,45 @@ k_compress_fresh16(const uint8_t *__restrict__ src, const uint64_t *__restrict__
         __syncwarp();
         Tab16 T{tab, 0};
         const uint32_t c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], ring);
+        if (lane == 0) comp_len[b] = c;
+        __syncwarp();
+    }
+}
+
+// Hybrid occupancy variant of k_compress_fresh16: the first `smem_warps` warps of a CTA keep their table in shared
+// memory, the remaining warps keep theirs in L2-resident global scratch (TabG16).  The parse is latency-bound with
+// 7 warps per SM (issue slots ~25 % busy); the extra chains fill the idle issue slots.
+constexpr int kMaxWarpsHybrid = 32;                // 64 registers x 32 lanes x 32 warps = the whole register file
+__global__ void __launch_bounds__(kMaxWarpsHybrid * 32, 1)
+k_compress_fresh16h(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
+                    const uint32_t *__restrict__ src_len, uint32_t nblocks, uint8_t *__restrict__ dst,
+                    const uint64_t *__restrict__ dst_off, uint32_t *__restrict__ comp_len, uint32_t *counter,
+                    uint32_t smem_warps, uint16_t *gtabs, uint32_t active_warps) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (warp >= active_warps) return;              // small batches: one chain per SM first, on the shared-memory tables
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + smem_warps * kHashEntries * 2 + warp * kRingBytes);
+    const bool in_smem = warp < smem_warps;
+    uint16_t *tab = in_smem ? reinterpret_cast<uint16_t *>(smem) + warp * kHashEntries
+                            : gtabs + ((size_t)blockIdx.x * (nwarps - smem_warps) + (warp - smem_warps)) * kHashEntries;
+    for (;;) {
+        const uint32_t b = next_block(counter, lane);
+        if (b >= nblocks) break;
+        const uint32_t len = src_len[b];
+        if (len > 65536u) { if (lane == 0) comp_len[b] = 0xFFFFFFFFu; continue; }
+        uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+        uint32_t c;
+        if (in_smem) {
+            for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+            Tab16 T{tab, 0};
+            c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], ring);
+        } else {
+            for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) __stcg(t4 + i, make_uint4(0, 0, 0, 0));
+            __syncwarp();
+            TabG16 T{tab, 0};
+            c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], ring);
+        }
         if (lane == 0) comp_len[b] = c;
         __syncwarp();
     }

@@ -1,5 +1,5 @@
 """Kernel micro-bench: device-resident compress / decompress of 64 KiB blocks per corpus kind (CUDA events).
-Usage: python divortio-lz4_b200/tools/kbench.py [MiB]"""
+Usage: python divortio-lz4_b200/tools/kbench.py [MiB] [block] [kind,kind...]"""
 import os
 import sys
 
@@ -21,7 +21,10 @@ def main():
     kinds = {"log": lambda: corpus.log(3, n), "zero": lambda: corpus.zero(n), "rand": lambda: corpus.rand(4, n),
              "mixed": lambda: corpus.mixed(2, n), "bench": lambda: corpus.benchjson(n)}
     stride = (dl.compress_bound(block) + 15) & ~15
+    only = sys.argv[3].split(",") if len(sys.argv) > 3 else list(kinds)
     for kind, gen in kinds.items():
+        if kind not in only:
+            continue
         src = torch.from_numpy(gen()).to(d)
         off, ln, nblk, coff = dev.uniform_blocks(n, block, d, stride)
         comp = torch.empty(nblk * stride + 64, dtype=torch.uint8, device=d)

@@ -1,0 +1,66 @@
+// gather3.cu -- isolates the slow case found by gather2: a scattered st.cg issued while the ld.cg of the same
+// address is still in flight.  Variants differ only in the store's address / data dependency.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+// V=0: store to the slot just loaded, data independent of the load        V=1: same, but data depends on the loaded value
+// V=2: store to slot h^1 (same sector), independent                      V=3: store to an unrelated random slot, independent
+// V=4: V=1 + read back the slot after __syncwarp                          V=5: V=0 with 32-bit table entries
+// V=6: V=0 but atomicExch (returns old, one round trip)                   V=7: load only, next iteration depends on it
+template <int V>
+__global__ void k(uint16_t *tabs, int iters, unsigned long long *cycles, uint32_t *sink) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const size_t wid = (size_t)blockIdx.x * nw + warp;
+    uint16_t *t = tabs + wid * 32768;                       // 64 KiB apart so the 32-bit variant fits
+    uint32_t *t32 = reinterpret_cast<uint32_t *>(t);
+    uint32_t x = lane * 2654435761u + warp * 40503u + blockIdx.x, acc = 0;
+    __syncwarp();
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+        x = x * 1664525u + 1013904223u;
+        const uint32_t h = (x >> 10) & 16383u;
+        uint32_t mine = (uint32_t)(i * 32 + lane + 1) & 0xffffu;
+        uint32_t v;
+        if (V == 5) { v = __ldcg(t32 + h); __stcg(t32 + h, mine); }
+        else if (V == 6) { v = atomicExch(t32 + h, mine); }
+        else {
+            v = __ldcg(t + h);
+            if (V == 1 || V == 4) asm volatile("and.b32 %0, %0, %1;" : "+r"(mine) : "r"(v | 0xffffu));
+            uint32_t hs = h;
+            if (V == 2) hs = h ^ 1u;
+            if (V == 3) hs = ((x * 2246822519u) >> 12) & 16383u;
+            if (V != 7) __stcg(t + hs, (uint16_t)mine);
+            if (V == 4) { __syncwarp(); acc += __ldcg(t + h); }
+        }
+        acc += v;
+        x ^= v;
+        __syncwarp();
+    }
+    const long long t1 = clock64();
+    if (lane == 0) atomicAdd(cycles, (unsigned long long)(t1 - t0));
+    if (acc == 0xdeadbeef) *sink = acc;
+}
+template <int V> void run(int sms, int w, uint16_t *tabs, unsigned long long *cyc, uint32_t *sink, const char *name) {
+    const int iters = 1000;
+    k<V><<<sms, w * 32>>>(tabs, iters, cyc, sink); cudaDeviceSynchronize(); cudaMemset(cyc, 0, 8);
+    k<V><<<sms, w * 32>>>(tabs, iters, cyc, sink); cudaDeviceSynchronize();
+    unsigned long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("%-62s warps/SM %2d : %8.1f cycles/iter (%s)\n", name, w, (double)c / ((double)sms * w * iters), cudaGetErrorString(cudaGetLastError()));
+}
+int main() {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0); const int sms = p.multiProcessorCount;
+    const size_t nw = (size_t)sms * 16;
+    uint16_t *tabs; cudaMalloc(&tabs, nw * 65536); cudaMemset(tabs, 0, nw * 65536);
+    unsigned long long *cyc; cudaMalloc(&cyc, 8); uint32_t *sink; cudaMalloc(&sink, 4);
+    for (int w : {1, 7, 14}) {
+        run<7>(sms, w, tabs, cyc, sink, "ld.cg only (dependent chain)");
+        run<0>(sms, w, tabs, cyc, sink, "ld.cg + st.cg same slot, store data independent");
+        run<1>(sms, w, tabs, cyc, sink, "ld.cg + st.cg same slot, store data depends on load");
+        run<2>(sms, w, tabs, cyc, sink, "ld.cg + st.cg neighbour slot (same sector), independent");
+        run<3>(sms, w, tabs, cyc, sink, "ld.cg + st.cg unrelated slot, independent");
+        run<4>(sms, w, tabs, cyc, sink, "ld.cg + dependent st.cg + syncwarp + read back");
+        run<5>(sms, w, tabs, cyc, sink, "32-bit entries: ld.cg + st.cg same slot, independent");
+        run<6>(sms, w, tabs, cyc, sink, "32-bit entries: atomicExch");
+    }
+    return 0;
+}

@@ -1,0 +1,68 @@
+// gather4.cu -- candidate protocols for a hash table that lives in L2 (32-bit entries), per "window" of 32 lanes:
+//   P1  atomicExch insert (returns old) ............ filler ............ atomicExch un-insert on 2/3 of the lanes (result unused)
+//   P2  ld.cg lookup ............ filler ............ atomicExch insert on 1/3 of the lanes (result unused)
+//   P3  ld.cg lookup ............ filler ............ st.cg insert on 1/3 of the lanes
+//   P0  shared-memory table, ld + st + st (the reference point)
+// filler = FILL dependent IMADs (~4.5 cycles each) standing in for the rest of the window.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+template <int P, int FILL>
+__global__ void k(uint32_t *tabs, int iters, unsigned long long *cycles, uint32_t *sink) {
+    extern __shared__ uint32_t sm[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const size_t wid = (size_t)blockIdx.x * nw + warp;
+    uint32_t *t = P == 0 ? sm + warp * 4096 : tabs + wid * 16384;
+    const uint32_t mask = P == 0 ? 4095u : 16383u;
+    uint32_t x = lane * 2654435761u + warp * 40503u + blockIdx.x, acc = 0;
+    __syncwarp();
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+        x = x * 1664525u + 1013904223u;
+        const uint32_t h = (x >> 10) & mask;
+        const uint32_t mine = (uint32_t)(i * 32 + lane + 1);
+        uint32_t v;
+        if (P == 0) { v = t[h]; __syncwarp(); t[h] = mine; }
+        else if (P == 1) v = atomicExch(t + h, mine);
+        else v = __ldcg(t + h);
+        uint32_t f = v;
+#pragma unroll 1
+        for (int j = 0; j < FILL; ++j) f = f * 2654435761u + x;
+        acc += f;
+        const bool third = ((x >> 3) % 3u) == 0;
+        if (P == 0) { if (!third) t[h] = v; }
+        else if (P == 1) { if (!third) atomicExch(t + h, v); }
+        else if (P == 2) { if (third) atomicExch(t + h, mine); }
+        else { if (third) __stcg(t + h, mine); }
+        x ^= v + (f & 1);
+        __syncwarp();
+    }
+    const long long t1 = clock64();
+    if (lane == 0) atomicAdd(cycles, (unsigned long long)(t1 - t0));
+    if (acc == 0xdeadbeef) *sink = acc;
+}
+template <int P, int FILL> void run(int sms, int w, uint32_t *tabs, unsigned long long *cyc, uint32_t *sink, const char *name) {
+    const int iters = 400;
+    const size_t smem = P == 0 ? (size_t)w * 16384 : 0;
+    if (P == 0) cudaFuncSetAttribute(k<P, FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<P, FILL><<<sms, w * 32, smem>>>(tabs, iters, cyc, sink); cudaDeviceSynchronize(); cudaMemset(cyc, 0, 8);
+    k<P, FILL><<<sms, w * 32, smem>>>(tabs, iters, cyc, sink); cudaDeviceSynchronize();
+    unsigned long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("%-44s fill %4d warps/SM %2d : %8.1f cycles/iter (%s)\n", name, FILL, w, (double)c / ((double)sms * w * iters), cudaGetErrorString(cudaGetLastError()));
+}
+int main() {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0); const int sms = p.multiProcessorCount;
+    const size_t nw = (size_t)sms * 21;
+    uint32_t *tabs; cudaMalloc(&tabs, nw * 65536); cudaMemset(tabs, 0, nw * 65536);
+    unsigned long long *cyc; cudaMalloc(&cyc, 8); uint32_t *sink; cudaMalloc(&sink, 4);
+    for (int w : {7, 14, 21}) {
+        if (w <= 13) run<0, 500>(sms, w, tabs, cyc, sink, "P0 smem ld+st, st un-insert");
+        run<1, 500>(sms, w, tabs, cyc, sink, "P1 exch insert, exch un-insert 2/3");
+        run<2, 500>(sms, w, tabs, cyc, sink, "P2 ld.cg lookup, exch insert 1/3");
+        run<3, 500>(sms, w, tabs, cyc, sink, "P3 ld.cg lookup, st.cg insert 1/3");
+        run<1, 200>(sms, w, tabs, cyc, sink, "P1 exch insert, exch un-insert 2/3");
+        run<2, 200>(sms, w, tabs, cyc, sink, "P2 ld.cg lookup, exch insert 1/3");
+        run<3, 200>(sms, w, tabs, cyc, sink, "P3 ld.cg lookup, st.cg insert 1/3");
+    }
+    return 0;
+}
