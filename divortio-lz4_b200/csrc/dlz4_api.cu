@@ -18,6 +18,7 @@ namespace {
 constexpr int kWarpsFresh16 = 7;     // 7 x 32 KiB tables = 224 KiB of the 227 KiB a CTA may own
 constexpr int kWarpsGeneric32 = 3;   // 3 x 64 KiB
 constexpr int kWarpsDecode = 8;
+constexpr int kGtabRegions = 5;      // L2-table regions: work-queue counter 0 (device API) and 1..4 (pipeline lanes)
 
 struct Buf {
     void *p = nullptr;
@@ -30,16 +31,18 @@ struct dlz4_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr, side = nullptr, copy_in = nullptr, copy_out = nullptr;
-    cudaEvent_t evp[64] = {};           // event pool of the chunked host pipeline
+    cudaStream_t lanes[4] = {};         // compute streams of the chunked host pipeline (chunks rotate over them)
+    uint64_t chunk_bytes = 128ull << 20; // target uncompressed bytes per pipeline chunk (DLZ4_CHUNK_MIB)
+    int n_lanes = 4;                    // compute streams in use (DLZ4_LANES)
+    cudaEvent_t evp[128] = {};          // event pool of the chunked host pipeline: [0,64) copies landed, [64,128) kernels done
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_side = nullptr, ev_fork = nullptr;
     uint32_t *d_counter = nullptr;      // work-queue heads (one per launch slot)
     uint32_t *d_hash = nullptr;         // small result slots
     uint64_t *d_total = nullptr;
     int32_t *d_table = nullptr;         // int32[16384] scratch table
-    int hy_smem_warps = 0, hy_gl_warps = 0;   // hybrid compress kernel: warps with shared-memory / L2-resident tables per SM
-    uint16_t *d_gtabs = nullptr;        // sm_count x hy_gl_warps tables of 16384 x u16
-    size_t gtabs_bytes = 0;
-    cudaAccessPolicyWindow gtabs_window = {};   // L2 persistence for the tables (num_bytes == 0: unavailable)
+    int hybrid = 1;                     // 64 KiB fresh blocks: hybrid kernel (L2-resident tables) instead of the 7-warp one
+    int hy_grid = 0;                    // CTAs that fill the device (sm_count x kHyCtasPerSm)
+    uint16_t *d_gtabs = nullptr;        // kGtabRegions x hy_grid x kHyGlWarps tables of 16384 x u16 (one region per stream lane)
     Buf work, comp, seg, out, meta, aux, pin;
     std::string last_error;
     uint64_t launches = 0;
@@ -113,25 +116,20 @@ const uint32_t kBlockMax[8] = {0, 0, 0, 0, 65536, 262144, 1048576, 4194304};
 // ---- launch helpers ----------------------------------------------------------------------------------
 int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len, uint32_t n,
                     uint32_t max_len, const uint8_t *prefix, uint32_t prefix_len, const int32_t *init_table, uint8_t *dst,
-                    const uint64_t *dst_off, uint32_t *comp_len, cudaStream_t st, uint32_t *counter = nullptr) {
+                    const uint64_t *dst_off, uint32_t *comp_len, cudaStream_t st, uint32_t *counter = nullptr, bool dense = false) {
     if (n == 0) return DLZ4_OK;
     if (!counter) counter = ctx->d_counter;
     CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
-    if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr && ctx->hy_gl_warps > 0) {
-        const int wpc = ctx->hy_smem_warps + ctx->hy_gl_warps;
-        const int grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count);
-        const uint32_t active = (uint32_t)std::min<uint64_t>((n + grid - 1) / grid, (uint64_t)wpc);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(wpc * 32); cfg.stream = st;
-        cfg.dynamicSmemBytes = (size_t)ctx->hy_smem_warps * kHashEntries * 2 + (size_t)wpc * kRingBytes;
-        cudaLaunchAttribute at[1];
-        if (ctx->gtabs_window.num_bytes) {       // keep the L2-resident tables from being evicted by the streamed blocks
-            at[0].id = cudaLaunchAttributeAccessPolicyWindow;
-            at[0].val.accessPolicyWindow = ctx->gtabs_window;
-            cfg.attrs = at; cfg.numAttrs = 1;
-        }
-        CK(cudaLaunchKernelEx(&cfg, k_compress_fresh16h, src, src_off, src_len, n, dst, dst_off, comp_len, counter,
-                              (uint32_t)ctx->hy_smem_warps, ctx->d_gtabs, active));
+    if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr && ctx->hybrid) {
+        // one table region per work-queue counter: kernels of different pipeline lanes run concurrently
+        const size_t region = (size_t)(counter - ctx->d_counter) % kGtabRegions;
+        // a batch on its own spreads over as many SMs as it has blocks (fewer active warps per CTA); a pipeline chunk
+        // (`dense`) packs 7 chains per CTA so that the chunks in flight on the other lanes find free CTA slots
+        const int grid = (int)std::min<uint64_t>(dense ? (n + kHyWarps - 1) / kHyWarps : n, (uint64_t)ctx->hy_grid);
+        const uint32_t active = dense ? (uint32_t)kHyWarps : (uint32_t)std::min<uint64_t>((n + grid - 1) / grid, (uint64_t)kHyWarps);
+        k_compress_fresh16h<<<grid, kHyWarps * 32, kHySmemBytes, st>>>(
+            src, src_off, src_len, n, dst, dst_off, comp_len, counter,
+            ctx->d_gtabs + region * (size_t)ctx->hy_grid * kHyGlWarps * kHashEntries, active);
     } else if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr) {
         const int grid = (int)std::min<uint64_t>((n + kWarpsFresh16 - 1) / kWarpsFresh16, (uint64_t)ctx->sm_count);
         k_compress_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * (kHashEntries * 2 + kRingBytes), st>>>(
@@ -148,12 +146,14 @@ int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, 
 
 int launch_decompress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len, uint32_t n,
                       uint8_t *dst, const uint64_t *dst_off, const uint32_t *dst_cap, const uint8_t *dict, uint32_t dict_len,
-                      int hist_frame, const uint8_t *stored, uint32_t *out_len, uint8_t *status, cudaStream_t st) {
+                      int hist_frame, const uint8_t *stored, uint32_t *out_len, uint8_t *status, cudaStream_t st,
+                      uint32_t *counter = nullptr) {
     if (n == 0) return DLZ4_OK;
-    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(uint32_t), st));
+    if (!counter) counter = ctx->d_counter;
+    CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
     const int grid = (int)std::min<uint64_t>((n + kWarpsDecode - 1) / kWarpsDecode, (uint64_t)ctx->sm_count * 8);
     k_decompress_blocks<kWarpsDecode><<<grid, kWarpsDecode * 32, 0, st>>>(src, src_off, src_len, n, dst, dst_off, dst_cap, dict,
-                                                                           dict_len, hist_frame, stored, out_len, status, ctx->d_counter);
+                                                                           dict_len, hist_frame, stored, out_len, status, counter);
     ctx->launches++;
     CK(cudaGetLastError());
     return DLZ4_OK;
@@ -211,42 +211,19 @@ int dlz4_init(int device, dlz4_ctx **out) {
     CK(cudaEventCreate(&ctx->ev1));
     CK(cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    for (cudaStream_t &l : ctx->lanes) CK(cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking));
+    if (const char *e = getenv("DLZ4_CHUNK_MIB")) ctx->chunk_bytes = (uint64_t)std::max(1, atoi(e)) << 20;
+    if (const char *e = getenv("DLZ4_LANES")) ctx->n_lanes = std::min(4, std::max(1, atoi(e)));
     CK(cudaMalloc(&ctx->d_counter, 64));
     CK(cudaMalloc(&ctx->d_hash, 64));
     CK(cudaMalloc(&ctx->d_total, 64));
     CK(cudaMalloc(&ctx->d_table, kHashEntries * sizeof(int32_t)));
     CK(cudaFuncSetAttribute(k_compress_fresh16<kWarpsFresh16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kWarpsFresh16 * (kHashEntries * 2 + kRingBytes)));
-    {   // hybrid kernel shape (tuning knobs for experiments: DLZ4_HY_SMEM_WARPS / DLZ4_HY_GL_WARPS; 0 global warps = off)
-        const char *es = getenv("DLZ4_HY_SMEM_WARPS"), *eg = getenv("DLZ4_HY_GL_WARPS");
-        ctx->hy_smem_warps = es ? atoi(es) : 4;
-        ctx->hy_gl_warps = eg ? atoi(eg) : 24;
-        if (ctx->hy_smem_warps < 0) ctx->hy_smem_warps = 0;
-        if (ctx->hy_smem_warps > 7) ctx->hy_smem_warps = 7;
-        if (ctx->hy_gl_warps < 0) ctx->hy_gl_warps = 0;
-        if (ctx->hy_smem_warps + ctx->hy_gl_warps > kMaxWarpsHybrid) ctx->hy_gl_warps = kMaxWarpsHybrid - ctx->hy_smem_warps;
-        size_t sm = (size_t)ctx->hy_smem_warps * kHashEntries * 2 + (size_t)(ctx->hy_smem_warps + ctx->hy_gl_warps) * kRingBytes;
-        while (sm > 232448 && ctx->hy_gl_warps > 0) { ctx->hy_gl_warps--; sm -= kRingBytes; }
-        if (ctx->hy_gl_warps > 0) {
-            ctx->gtabs_bytes = (size_t)ctx->sm_count * ctx->hy_gl_warps * kHashEntries * 2;
-            CK(cudaMalloc(&ctx->d_gtabs, ctx->gtabs_bytes));
-            const char *ep = getenv("DLZ4_HY_PERSIST");
-            if (ep && atoi(ep) != 0 && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
-                const size_t set_aside = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, ctx->gtabs_bytes);
-                CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
-                ctx->gtabs_window.base_ptr = ctx->d_gtabs;
-                ctx->gtabs_window.num_bytes = std::min<size_t>(ctx->gtabs_bytes, (size_t)prop.accessPolicyMaxWindowSize);
-                ctx->gtabs_window.hitRatio = std::min(1.0f, (float)set_aside / (float)ctx->gtabs_window.num_bytes);
-                ctx->gtabs_window.hitProp = cudaAccessPropertyPersisting;
-                ctx->gtabs_window.missProp = cudaAccessPropertyStreaming;
-            }
-            if (getenv("DLZ4_DEBUG"))
-                fprintf(stderr, "dlz4: hybrid %d+%d warps, tables %zu MiB, L2 %d MiB, persisting max %d MiB, window max %d MiB, hitRatio %.2f\n",
-                        ctx->hy_smem_warps, ctx->hy_gl_warps, ctx->gtabs_bytes >> 20, prop.l2CacheSize >> 20,
-                        prop.persistingL2CacheMaxSize >> 20, prop.accessPolicyMaxWindowSize >> 20, ctx->gtabs_window.hitRatio);
-            CK(cudaFuncSetAttribute(k_compress_fresh16h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        }
-    }
+    if (const char *e = getenv("DLZ4_HYBRID")) ctx->hybrid = atoi(e) != 0;      // 0: the 7-warp shared-memory-only kernel (A/B runs)
+    ctx->hy_grid = ctx->sm_count * kHyCtasPerSm;
+    CK(cudaMalloc(&ctx->d_gtabs, (size_t)kGtabRegions * ctx->hy_grid * kHyGlWarps * kHashEntries * 2));
+    CK(cudaFuncSetAttribute(k_compress_fresh16h, cudaFuncAttributeMaxDynamicSharedMemorySize, kHySmemBytes));
     CK(cudaFuncSetAttribute(k_compress_generic32<kWarpsGeneric32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kWarpsGeneric32 * (kHashEntries * 4 + kRingBytes)));
     CK(cudaFuncSetAttribute(k_compress_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kHashEntries * 4 + kRingBytes));
@@ -271,6 +248,7 @@ void dlz4_shutdown(dlz4_ctx *ctx) {
     if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (cudaEvent_t e : ctx->evp) if (e) cudaEventDestroy(e);
+    for (cudaStream_t l : ctx->lanes) if (l) { cudaStreamSynchronize(l); cudaStreamDestroy(l); }
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -355,9 +333,12 @@ int dlz4_compress_blocks_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *
     return launch_compress(ctx, src, src_off, src_len, nblocks, max_block_len, prefix, prefix_len, table, dst, dst_off, comp_len, st);
 }
 
-// Chunked host pipeline: H2D of chunk c+1, kernels of chunk c and D2H of chunk c-1 overlap on three streams.
+// Chunked host pipeline: H2D of later chunks, kernels of up to n_lanes chunks and D2H of finished chunks overlap (one copy-in
+// stream, n_lanes compute streams with a work-queue counter each, one copy-out stream).  128 MiB chunks measured best:
+// the drain is bounded below by the latency of one block chain (~3 ms for a 64 KiB text block) whatever the chunk size,
+// and smaller chunks only add launches (profiles/r01_e2e_chunk_sweep.txt).
 // Blocks must be ascending and non-overlapping in `src`; output is packed (block i directly after block i-1).
-static const uint64_t kChunkBytesMin = 128ull << 20;       // >= 128 MiB of uncompressed bytes per chunk, at most 24 chunks
+static const uint32_t kMaxChunks = 60;
 
 static int compress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_bytes, const uint64_t *src_off,
                                   const uint32_t *src_len, uint32_t n, uint32_t max_len, uint8_t *dst, uint64_t dst_bytes,
@@ -374,20 +355,21 @@ static int compress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t sr
     uint32_t *d_slen = (uint32_t *)(d_pos + n + 64), *d_clen = d_slen + n;
     volatile uint64_t *h_tot = (volatile uint64_t *)ctx->pin.p;
     uint32_t *h_clen = (uint32_t *)((uint8_t *)ctx->pin.p + 64 * 8);
-    cudaStream_t sks[2] = {ctx->stream, ctx->side}, si = ctx->copy_in, so = ctx->copy_out;
+    cudaStream_t *sks = ctx->lanes, si = ctx->copy_in, so = ctx->copy_out;
+    const uint32_t nl = (uint32_t)ctx->n_lanes;
     cudaStream_t sk = sks[0];
 
     // chunk boundaries by source bytes
     std::vector<uint32_t> cb{0};
     uint64_t total_src = 0;
     for (uint32_t i = 0; i < n; ++i) total_src += src_len[i];
-    const uint64_t target = std::max<uint64_t>(kChunkBytesMin, total_src / 24 + 1);
+    const uint64_t target = std::max<uint64_t>(ctx->chunk_bytes, total_src / kMaxChunks + 1);
     uint64_t acc = 0;
     for (uint32_t i = 0; i < n; ++i) {
         acc += src_len[i];
         if (acc >= target || i + 1 == n) { cb.push_back(i + 1); acc = 0; }
     }
-    const uint32_t nc = (uint32_t)cb.size() - 1;            // <= 25
+    const uint32_t nc = (uint32_t)cb.size() - 1;            // <= kMaxChunks + 1
     // descriptors once (compressed scratch is worst-case strided)
     std::vector<uint64_t> coff(n);
     for (uint32_t i = 0; i < n; ++i) coff[i] = (uint64_t)i * stride;
@@ -396,28 +378,33 @@ static int compress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t sr
     CK(cudaMemcpyAsync(d_slen, src_len, (size_t)n * 4, cudaMemcpyHostToDevice, sk));
     CK(cudaEventRecord(ctx->ev0, sk));
     CK(cudaEventRecord(ctx->ev_fork, sk));
-    CK(cudaStreamWaitEvent(sks[1], ctx->ev_fork, 0));          // descriptors are visible to the second compute stream
+    for (uint32_t l = 1; l < nl; ++l) CK(cudaStreamWaitEvent(sks[l], ctx->ev_fork, 0));   // descriptors visible to every lane
 
     uint64_t host_pos = 0;
     auto drain = [&](uint32_t c) -> int {          // chunk c's kernels are done: ship its packed bytes
-        CK(cudaEventSynchronize(ctx->evp[32 + c]));
+        CK(cudaEventSynchronize(ctx->evp[64 + c]));
         const uint64_t tot = h_tot[c];
         if (host_pos + tot > dst_bytes) return DLZ4_E_OUTPUT_TOO_SMALL;
         if (tot) CK(cudaMemcpyAsync(dst + host_pos, d_pack + (uint64_t)cb[c] * stride, tot, cudaMemcpyDeviceToHost, so));
         host_pos += tot;
         return DLZ4_OK;
     };
+    // everything is enqueued up front (the host only blocks in drain(), which needs each chunk's packed size to place it):
+    // all H2D copies on the copy-in stream, then every chunk's kernels on its lane, gated by the chunk's copy event
     for (uint32_t c = 0; c < nc; ++c) {
-        const uint32_t b0 = cb[c], b1 = cb[c + 1], m = b1 - b0;
+        const uint32_t b0 = cb[c], b1 = cb[c + 1];
         const uint64_t lo = src_off[b0], hi = src_off[b1 - 1] + src_len[b1 - 1];
         if (hi > lo) CK(cudaMemcpyAsync(d_src + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, si));
         CK(cudaEventRecord(ctx->evp[c], si));
-        // chunks alternate between two compute streams (own work-queue counter each) so the next chunk's CTAs take over
-        // SMs as the previous chunk's last blocks drain
-        sk = sks[c & 1];
+    }
+    for (uint32_t c = 0; c < nc; ++c) {
+        const uint32_t b0 = cb[c], b1 = cb[c + 1], m = b1 - b0;
+        // chunks rotate over the compute streams (own work-queue counter and L2-table region each): the next chunks' CTAs
+        // take over SM slots as the previous chunk's last blocks drain
+        sk = sks[c % nl];
         CK(cudaStreamWaitEvent(sk, ctx->evp[c], 0));
         CKS(launch_compress(ctx, d_src, d_soff + b0, d_slen + b0, m, max_len, nullptr, 0, nullptr, d_comp, d_coff + b0, d_clen + b0, sk,
-                            ctx->d_counter + 1 + (c & 1)));
+                            ctx->d_counter + 1 + (c % nl), nc > 1));
         uint64_t *pos = d_pos + b0 + c;                                   // m + 1 entries
         k_frame_layout<<<1, 1024, 0, sk>>>(d_slen + b0, d_clen + b0, m, 0, pos, nullptr, nullptr, 1);
         k_frame_gather<<<(int)std::min<uint64_t>(m, (uint64_t)ctx->sm_count * 8), 256, 0, sk>>>(
@@ -426,12 +413,11 @@ static int compress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t sr
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync((void *)(h_tot + c), pos + m, 8, cudaMemcpyDeviceToHost, sk));
         CK(cudaMemcpyAsync(h_clen + b0, d_clen + b0, (size_t)m * 4, cudaMemcpyDeviceToHost, sk));
-        CK(cudaEventRecord(ctx->evp[32 + c], sk));
-        if (c >= 1) CKS(drain(c - 1));
+        CK(cudaEventRecord(ctx->evp[64 + c], sk));
     }
-    if (nc) CKS(drain(nc - 1));
+    for (uint32_t c = 0; c < nc; ++c) CKS(drain(c));
     CK(cudaStreamSynchronize(so));
-    CK(cudaStreamSynchronize(sks[1]));
+    for (uint32_t l = 1; l < nl; ++l) { CK(cudaEventRecord(ctx->ev_side, sks[l])); CK(cudaStreamWaitEvent(sks[0], ctx->ev_side, 0)); }
     CK(cudaEventRecord(ctx->ev1, sks[0]));
     CK(cudaStreamSynchronize(sks[0]));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
@@ -525,8 +511,10 @@ static int decompress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t 
     uint64_t *d_soff = (uint64_t *)ctx->meta.p, *d_doff = d_soff + n;
     uint32_t *d_slen = (uint32_t *)(d_doff + n), *d_cap = d_slen + n, *d_olen = d_cap + n;
     uint8_t *d_status = (uint8_t *)(d_olen + n);
-    cudaStream_t sk = ctx->stream, si = ctx->copy_in, so = ctx->copy_out;
-    const uint64_t target = std::max<uint64_t>(kChunkBytesMin, total_out / 24 + 1);
+    cudaStream_t *sks = ctx->lanes, si = ctx->copy_in, so = ctx->copy_out;
+    const uint32_t nl = (uint32_t)ctx->n_lanes;
+    cudaStream_t sk = sks[0];
+    const uint64_t target = std::max<uint64_t>(ctx->chunk_bytes, total_out / kMaxChunks + 1);
     std::vector<uint32_t> cb{0};
     uint64_t acc = 0;
     for (uint32_t i = 0; i < n; ++i) {
@@ -540,18 +528,24 @@ static int decompress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t 
     CK(cudaMemcpyAsync(d_slen, src_len, (size_t)n * 4, cudaMemcpyHostToDevice, sk));
     CK(cudaMemcpyAsync(d_cap, dst_cap, (size_t)n * 4, cudaMemcpyHostToDevice, sk));
     CK(cudaEventRecord(ctx->ev0, sk));
+    CK(cudaEventRecord(ctx->ev_fork, sk));
+    for (uint32_t l = 1; l < nl; ++l) CK(cudaStreamWaitEvent(sks[l], ctx->ev_fork, 0));
+    // frame-history mode: a block may read the previous blocks' output, so chunks must run in order on one stream
+    const uint32_t lanes_used = hist_mode == DLZ4_HIST_FRAME ? 1u : nl;
     for (uint32_t c = 0; c < nc; ++c) {
         const uint32_t b0 = cb[c], b1 = cb[c + 1], m = b1 - b0;
         if (soff[b1] > soff[b0]) CK(cudaMemcpyAsync(d_src + soff[b0], src + soff[b0], soff[b1] - soff[b0], cudaMemcpyHostToDevice, si));
         CK(cudaEventRecord(ctx->evp[c], si));
-        CK(cudaStreamWaitEvent(sk, ctx->evp[c], 0));
+        cudaStream_t sc = sks[c % lanes_used];
+        CK(cudaStreamWaitEvent(sc, ctx->evp[c], 0));
         CKS(launch_decompress(ctx, d_src, d_soff + b0, d_slen + b0, m, d_dst, d_doff + b0, d_cap + b0, dict_len ? d_dict : nullptr, dict_len,
-                              hist_mode == DLZ4_HIST_FRAME, nullptr, d_olen + b0, d_status + b0, sk));
-        CK(cudaEventRecord(ctx->evp[32 + c], sk));
-        CK(cudaStreamWaitEvent(so, ctx->evp[32 + c], 0));
+                              hist_mode == DLZ4_HIST_FRAME, nullptr, d_olen + b0, d_status + b0, sc, ctx->d_counter + 1 + (c % lanes_used)));
+        CK(cudaEventRecord(ctx->evp[64 + c], sc));
+        CK(cudaStreamWaitEvent(so, ctx->evp[64 + c], 0));
         const uint64_t lo = dst_off[b0], hi = dst_off[b1 - 1] + dst_cap[b1 - 1];
         if (hi > lo) CK(cudaMemcpyAsync(dst + lo, d_dst + lo, hi - lo, cudaMemcpyDeviceToHost, so));
     }
+    for (uint32_t l = 1; l < lanes_used; ++l) { CK(cudaEventRecord(ctx->ev_side, sks[l])); CK(cudaStreamWaitEvent(sk, ctx->ev_side, 0)); }
     CK(cudaEventRecord(ctx->ev1, sk));
     CK(cudaMemcpyAsync(out_len, d_olen, (size_t)n * 4, cudaMemcpyDeviceToHost, sk));
     CK(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, sk));

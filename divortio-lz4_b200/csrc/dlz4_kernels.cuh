@@ -633,22 +633,27 @@ k_compress_fresh16(const uint8_t *__restrict__ src, const uint64_t *__restrict__
     }
 }
 
-// Hybrid occupancy variant of k_compress_fresh16: the first `smem_warps` warps of a CTA keep their table in shared
-// memory, the remaining warps keep theirs in L2-resident global scratch (TabG16).  The parse is latency-bound with
-// 7 warps per SM (issue slots ~25 % busy); the extra chains fill the idle issue slots.
-constexpr int kMaxWarpsHybrid = 32;                // 64 registers x 32 lanes x 32 warps = the whole register file
-__global__ void __launch_bounds__(kMaxWarpsHybrid * 32, 1)
+// Hybrid occupancy variant of k_compress_fresh16.  The parse is latency-bound (one dependent chain per block) and
+// shared memory holds only 7 tables per SM, so most chains keep their table in L2-resident global scratch instead
+// (TabG16): a CTA is 7 warps = 1 chain on a shared-memory table + 6 chains on L2 tables, and 4 such CTAs share an SM
+// (28 chains, 64 registers each).  Small CTAs let the chunks of the host pipeline -- launched on different streams --
+// co-reside on an SM.  `active_warps` < 7 spreads a small batch over more SMs, shared-memory warp first.
+constexpr int kHyWarps = 7;                        // warps per CTA: warp 0 shared-memory table, warps 1..6 L2 tables
+constexpr int kHyGlWarps = kHyWarps - 1;
+constexpr int kHyCtasPerSm = 4;
+constexpr int kHySmemBytes = kHashEntries * 2 + kHyWarps * kRingBytes;
+__global__ void __launch_bounds__(kHyWarps * 32, kHyCtasPerSm)
 k_compress_fresh16h(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
                     const uint32_t *__restrict__ src_len, uint32_t nblocks, uint8_t *__restrict__ dst,
                     const uint64_t *__restrict__ dst_off, uint32_t *__restrict__ comp_len, uint32_t *counter,
-                    uint32_t smem_warps, uint16_t *gtabs, uint32_t active_warps) {
+                    uint16_t *gtabs /* gridDim.x * kHyGlWarps tables */, uint32_t active_warps) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    if (warp >= active_warps) return;              // small batches: one chain per SM first, on the shared-memory tables
-    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + smem_warps * kHashEntries * 2 + warp * kRingBytes);
-    const bool in_smem = warp < smem_warps;
-    uint16_t *tab = in_smem ? reinterpret_cast<uint16_t *>(smem) + warp * kHashEntries
-                            : gtabs + ((size_t)blockIdx.x * (nwarps - smem_warps) + (warp - smem_warps)) * kHashEntries;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    if (warp >= active_warps) return;
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + kHashEntries * 2 + warp * kRingBytes);
+    const bool in_smem = warp == 0;
+    uint16_t *tab = in_smem ? reinterpret_cast<uint16_t *>(smem)
+                            : gtabs + ((size_t)blockIdx.x * kHyGlWarps + (warp - 1)) * kHashEntries;
     for (;;) {
         const uint32_t b = next_block(counter, lane);
         if (b >= nblocks) break;
