@@ -77,6 +77,7 @@ def lib():
         "dlz4_last_error": (C.c_char_p, [vp]),
         "dlz4_launch_count": (u64, [vp]),
         "dlz4_last_kernel_ms": (C.c_float, [vp]),
+        "dlz4_segment_stats": (None, [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "dlz4_pinned_alloc": (vp, [u64]),
         "dlz4_pinned_free": (None, [vp]),
         "dlz4_compress_bound": (u64, [u64]),
@@ -106,7 +107,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = [
-    "dlz4_init", "dlz4_shutdown", "dlz4_strerror", "dlz4_last_error", "dlz4_launch_count", "dlz4_last_kernel_ms",
+    "dlz4_init", "dlz4_shutdown", "dlz4_strerror", "dlz4_last_error", "dlz4_launch_count", "dlz4_last_kernel_ms", "dlz4_segment_stats",
     "dlz4_pinned_alloc", "dlz4_pinned_free", "dlz4_compress_bound", "dlz4_frame_bound", "dlz4_shard_range",
     "dlz4_compress_blocks_dev", "dlz4_compress_blocks", "dlz4_decompress_blocks_dev", "dlz4_decompress_blocks",
     "dlz4_compress_block", "dlz4_decompress_block", "dlz4_xxh32_batch_dev", "dlz4_xxh32_stream_dev", "dlz4_xxh32",
@@ -181,6 +182,13 @@ class Context(object):
     @property
     def last_kernel_ms(self):
         return float(lib().dlz4_last_kernel_ms(self._h))
+
+    @property
+    def segment_stats(self):
+        """(segments, re-run segments, rounds) of the most recent segment-parallel frame compression."""
+        a, b, c = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        lib().dlz4_segment_stats(self._h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
 
 
 _default = {}

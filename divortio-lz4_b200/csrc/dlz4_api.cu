@@ -45,6 +45,8 @@ struct dlz4_ctx {
     uint16_t *d_gtabs = nullptr;        // kGtabRegions x hy_grid x kHyGlWarps tables of 16384 x u16 (one region per stream lane)
     Buf work, comp, seg, out, meta, aux, pin;
     std::string last_error;
+    uint64_t seg_min_bytes = 256ull << 10;                   // frames at least this long use the segment-parallel engine (DLZ4_SEG_MIN_KIB)
+    uint32_t seg_jobs = 0, seg_reruns = 0, seg_rounds = 0;   // last segment-parallel call: segments, re-run segments, rounds
     uint64_t launches = 0;
     float last_ms = 0.f;
 };
@@ -176,6 +178,111 @@ int launch_xxh32_stream(dlz4_ctx *ctx, const uint8_t *data, uint64_t len, uint32
     return DLZ4_OK;
 }
 
+// Segment-parallel compression of large blocks / linked chains (k_compress_segments).  Blocks are the uniform blocks of
+// size B that tile [start, start + total) of the working buffer; linked: one chain carrying the table (init_table = its
+// initial state), otherwise every block is its own chain with a fresh table.  Output: d_comp + d_coff[b], d_clen[b].
+int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int64_t total, int64_t B, uint32_t n, bool linked,
+                       const int32_t *init_table, uint8_t *d_comp, const uint64_t *d_coff, uint32_t *d_clen, cudaStream_t st) {
+    if (n == 0) return DLZ4_OK;
+    // segment size: about 2048 segments over the call, at least 128 KiB; warm-up 512 KiB (tools/resync_stats.c)
+    int64_t S = 128 << 10;
+    while (S < total / 2048) S <<= 1;
+    if (const char *e = getenv("DLZ4_SEG_KIB")) S = (int64_t)std::max(64, atoi(e)) << 10;
+    int64_t W = 512 << 10;
+    if (const char *e = getenv("DLZ4_SEG_WARM_KIB")) W = (int64_t)std::max(0, atoi(e)) << 10;
+    if (!linked && S > B) S = B;
+    std::vector<SegJob> jobs;
+    std::vector<uint32_t> slot_first(n, 0), slot_count(n, 0);
+    uint32_t nslots = 0;
+    const uint32_t nchains = linked ? 1u : n;
+    for (uint32_t c = 0; c < nchains; ++c) {
+        const int64_t cs = linked ? start : start + (int64_t)c * B;
+        const int64_t ce = linked ? start + total : std::min<int64_t>(cs + B, start + total);
+        for (int64_t sb = cs; sb < ce; sb += S) {
+            SegJob J;
+            J.chain_start = (int32_t)cs; J.chain_end = (int32_t)ce;
+            J.seg_begin = (int32_t)sb; J.seg_end = (int32_t)std::min<int64_t>(sb + S, ce);
+            J.warm_begin = (int32_t)std::max<int64_t>(cs, sb - W);
+            J.flags = (sb == cs ? kSegFirst : 0u) | (J.seg_end == J.chain_end ? kSegLast : 0u);
+            const int64_t b0 = (sb - cs) / B, b1 = (J.seg_end - 1 - cs) / B;          // blocks of the chain this segment overlaps
+            J.first_block = (linked ? 0u : c) + (uint32_t)b0;
+            J.first_slot = nslots;
+            for (int64_t b = b0; b <= b1; ++b) {
+                const uint32_t g = (linked ? 0u : c) + (uint32_t)b;
+                if (!slot_count[g]) slot_first[g] = nslots;
+                slot_count[g]++;
+                nslots++;
+            }
+            jobs.push_back(J);
+        }
+    }
+    const uint32_t nj = (uint32_t)jobs.size();
+    const uint64_t bstride = (uint64_t)((B + (B >> 3) + 64 + 15) & ~15ll);
+    // device scratch, carved out of ctx->aux
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_tab = carve((size_t)nj * kHashEntries * 4), o_snap = carve((size_t)nj * kHashEntries * 4);
+    const size_t o_jobs = carve((size_t)nj * sizeof(SegJob)), o_list = carve((size_t)nj * 4);
+    const size_t o_ss = carve((size_t)nj * sizeof(SegState)), o_es = carve((size_t)nj * sizeof(SegState)), o_bad = carve(nj);
+    const size_t o_poff = carve((size_t)nslots * 4), o_plen = carve((size_t)nslots * 4);
+    const size_t o_sf = carve((size_t)n * 4), o_sc = carve((size_t)n * 4), o_buf = carve((size_t)n * bstride + 64);
+    CKS(reserve(ctx, ctx->aux, off));
+    uint8_t *A = (uint8_t *)ctx->aux.p;
+    int32_t *d_tab = (int32_t *)(A + o_tab), *d_snap = (int32_t *)(A + o_snap);
+    SegJob *d_jobs = (SegJob *)(A + o_jobs);
+    uint32_t *d_list = (uint32_t *)(A + o_list);
+    SegState *d_ss = (SegState *)(A + o_ss), *d_es = (SegState *)(A + o_es);
+    uint8_t *d_bad = A + o_bad;
+    uint32_t *d_poff = (uint32_t *)(A + o_poff), *d_plen = (uint32_t *)(A + o_plen), *d_sf = (uint32_t *)(A + o_sf), *d_sc = (uint32_t *)(A + o_sc);
+    uint8_t *d_buf = A + o_buf;
+    CK(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nj * sizeof(SegJob), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_sf, slot_first.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_sc, slot_count.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_plen, 0, (size_t)nslots * 4, st));
+    uint32_t *counter = ctx->d_counter + 8;
+    auto launch = [&](const uint32_t *list, uint32_t count) -> int {
+        CK(cudaMemsetAsync(counter, 0, 4, st));
+        const int grid = (int)std::min<uint64_t>(count, (uint64_t)ctx->sm_count * 4);
+        const uint32_t active = (uint32_t)std::min<uint64_t>((count + grid - 1) / grid, (uint64_t)kSegWarps);
+        k_compress_segments<<<grid, kSegWarps * 32, kSegWarps * kRingBytes, st>>>(d_work, d_jobs, list, count, (int32_t)B, init_table, d_tab, d_snap,
+                                                                                  d_ss, d_es, d_buf, bstride, d_poff, d_plen, counter, active);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return DLZ4_OK;
+    };
+    CKS(launch(nullptr, nj));
+    ctx->seg_jobs = nj; ctx->seg_reruns = 0; ctx->seg_rounds = 0;
+    bool speculative = false;
+    for (const SegJob &J : jobs) speculative |= !(J.flags & kSegFirst);
+    if (speculative) {
+        std::vector<uint8_t> bad(nj);
+        std::vector<uint32_t> list;
+        for (uint32_t round = 0; round <= nj; ++round) {
+            k_seg_verify<<<nj, 256, 0, st>>>(d_jobs, nj, d_tab, d_snap, d_ss, d_es, d_bad);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(bad.data(), d_bad, nj, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            list.clear();
+            for (uint32_t j = 1; j < nj; ++j)
+                if (bad[j] && !bad[j - 1]) list.push_back(j);          // predecessor's end state stands: re-run from it is exact
+            if (list.empty()) break;
+            for (uint32_t j : list) jobs[j].flags |= kSegRerun;
+            CK(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nj * sizeof(SegJob), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(d_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, st));
+            CKS(launch(d_list, (uint32_t)list.size()));
+            CK(cudaStreamSynchronize(st));                                // `list` / `jobs` are reused next round
+            ctx->seg_reruns += (uint32_t)list.size();
+            ctx->seg_rounds++;
+        }
+    }
+    k_seg_assemble<<<(int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(d_buf, bstride, d_sf, d_sc, d_poff, d_plen, n, d_comp,
+                                                                                             d_coff, d_clen);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DLZ4_OK;
+}
+
 int launch_chain(dlz4_ctx *ctx, const uint8_t *work, int32_t start, int32_t total, int32_t block, uint32_t nblocks,
                  int32_t *table_io, uint8_t *dst, uint64_t stride, uint32_t *comp_len, cudaStream_t st) {
     k_compress_chain<<<1, 32, kHashEntries * 4 + kRingBytes, st>>>(work, start, total, block, nblocks, table_io, dst, stride, comp_len);
@@ -220,6 +327,7 @@ int dlz4_init(int device, dlz4_ctx **out) {
     CK(cudaMalloc(&ctx->d_table, kHashEntries * sizeof(int32_t)));
     CK(cudaFuncSetAttribute(k_compress_fresh16<kWarpsFresh16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kWarpsFresh16 * (kHashEntries * 2 + kRingBytes)));
+    if (const char *e = getenv("DLZ4_SEG_MIN_KIB")) ctx->seg_min_bytes = (uint64_t)atoll(e) << 10;     // huge value: serial chain only
     if (const char *e = getenv("DLZ4_HYBRID")) ctx->hybrid = atoi(e) != 0;      // 0: the 7-warp shared-memory-only kernel (A/B runs)
     ctx->hy_grid = ctx->sm_count * kHyCtasPerSm;
     CK(cudaMalloc(&ctx->d_gtabs, (size_t)kGtabRegions * ctx->hy_grid * kHyGlWarps * kHashEntries * 2));
@@ -278,6 +386,11 @@ const char *dlz4_strerror(int status) {
 const char *dlz4_last_error(const dlz4_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 uint64_t dlz4_launch_count(const dlz4_ctx *ctx) { return ctx ? ctx->launches : 0; }
 float dlz4_last_kernel_ms(const dlz4_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
+void dlz4_segment_stats(const dlz4_ctx *ctx, uint32_t *segments, uint32_t *reruns, uint32_t *rounds) {
+    if (segments) *segments = ctx ? ctx->seg_jobs : 0;
+    if (reruns) *reruns = ctx ? ctx->seg_reruns : 0;
+    if (rounds) *rounds = ctx ? ctx->seg_rounds : 0;
+}
 
 uint64_t dlz4_compress_bound(uint64_t n) { return n + n / 255 + 16; }
 uint64_t dlz4_frame_bound(uint64_t n) { return 19 + n + (n / 65536 + 1) * 8 + 8 + 64; }
@@ -845,6 +958,7 @@ int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len,
 
     CK(cudaEventRecord(ctx->ev0, st));
     uint64_t seg_len = 0;
+    ctx->seg_jobs = ctx->seg_reruns = ctx->seg_rounds = 0;
     if (n) {
         k_uniform_blocks<<<(n + 255) / 256, 256, 0, st>>>((uint64_t)(d_in - d_work), input_len, B, n, d_soff, d_slen, d_coff, stride);
         ctx->launches++;
@@ -854,7 +968,11 @@ int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len,
             // linked blocks: one serial chain, table and history carried across blocks (:182,:219,:234)
             CK(cudaMemsetAsync(ctx->d_table, 0, kHashEntries * 4, st));
             if (dwin >= 4) { k_warm_jenkins<<<((int)dwin - 3 + 255) / 256, 256, 0, st>>>(d_work, (int32_t)dwin, ctx->d_table); ctx->launches++; }
-            CKS(launch_chain(ctx, d_work, (int32_t)dwin, (int32_t)input_len, (int32_t)B, n, ctx->d_table, d_comp, stride, d_clen, st));
+            if (input_len >= ctx->seg_min_bytes)
+                // long chain: speculative segments, verified against the serial parse's state (k_compress_segments)
+                CKS(compress_segmented(ctx, d_work, (int64_t)dwin, (int64_t)input_len, (int64_t)B, n, true, ctx->d_table, d_comp, d_coff, d_clen, st));
+            else
+                CKS(launch_chain(ctx, d_work, (int32_t)dwin, (int32_t)input_len, (int32_t)B, n, ctx->d_table, d_comp, stride, d_clen, st));
         } else {
             uint32_t first = 0;
             if (dwin) {
@@ -866,8 +984,13 @@ int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len,
                 CKS(launch_chain(ctx, d_work, (int32_t)dwin, l0, l0, 1, ctx->d_table, d_comp, stride, d_clen, st));
                 first = 1;
             }
-            CKS(launch_compress(ctx, d_work, d_soff + first, d_slen + first, n - first, B, nullptr, 0, nullptr, d_comp, d_coff + first,
-                                d_clen + first, st));
+            if (B > 65536 && n > first && input_len >= ctx->seg_min_bytes)
+                // large independent blocks: segments inside every block (the first segment of a block starts exactly)
+                CKS(compress_segmented(ctx, d_work, (int64_t)dwin + (int64_t)first * B, (int64_t)input_len - (int64_t)first * B, (int64_t)B,
+                                       n - first, false, nullptr, d_comp, d_coff + first, d_clen + first, st));
+            else
+                CKS(launch_compress(ctx, d_work, d_soff + first, d_slen + first, n - first, B, nullptr, 0, nullptr, d_comp, d_coff + first,
+                                    d_clen + first, st));
         }
         CKS(dlz4_frame_pack_dev(ctx, d_work, d_soff, d_slen, d_comp, d_coff, d_clen, n, opts->block_checksum, (uint8_t *)ctx->seg.p,
                                 d_pos, st));

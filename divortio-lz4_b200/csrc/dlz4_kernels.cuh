@@ -234,6 +234,13 @@ __device__ uint32_t compress_block_warp(const Src &S, const int32_t start, const
     return (uint32_t)(d - out);
 }
 
+// The reference's Int32 representation in L2-resident global memory (large blocks and linked chains; see TabG16).
+struct TabG32 {
+    int32_t *t;
+    __device__ __forceinline__ int32_t get(uint32_t h) const { return __ldcg(t + h) - 1; }
+    __device__ __forceinline__ void put(uint32_t h, int32_t p) { __stcg(t + h, p + 1); }
+};
+
 // ------------------------------------------------------------------ v2: dense-window compressor
 // Raw table access for the window path (write / read back / restore).
 __device__ __forceinline__ uint32_t tab_raw(const Tab16 &T, uint32_t h) { return T.t[h]; }
@@ -244,6 +251,10 @@ __device__ __forceinline__ uint32_t tab_raw(const TabG16 &T, uint32_t h) { retur
 __device__ __forceinline__ void tab_set_raw(TabG16 &T, uint32_t h, uint32_t v) { __stcg(T.t + h, (uint16_t)v); }
 __device__ __forceinline__ uint32_t tab_enc(const TabG16 &T, int32_t p) { return (uint32_t)(p - T.start) & 0xFFFFu; }
 __device__ __forceinline__ int32_t tab_dec(const TabG16 &T, uint32_t raw) { return T.start + (int32_t)raw; }
+__device__ __forceinline__ uint32_t tab_raw(const TabG32 &T, uint32_t h) { return (uint32_t)__ldcg(T.t + h); }
+__device__ __forceinline__ void tab_set_raw(TabG32 &T, uint32_t h, uint32_t v) { __stcg(T.t + h, (int32_t)v); }
+__device__ __forceinline__ uint32_t tab_enc(const TabG32 &, int32_t p) { return (uint32_t)(p + 1); }
+__device__ __forceinline__ int32_t tab_dec(const TabG32 &, uint32_t raw) { return (int32_t)raw - 1; }
 __device__ __forceinline__ uint32_t tab_raw(const Tab32 &T, uint32_t h) { return (uint32_t)T.t[h]; }
 __device__ __forceinline__ void tab_set_raw(Tab32 &T, uint32_t h, uint32_t v) { T.t[h] = (int32_t)v; }
 __device__ __forceinline__ uint32_t tab_enc(const Tab32 &, int32_t p) { return (uint32_t)(p + 1); }
@@ -288,15 +299,22 @@ struct SpanState {
     uint32_t smc;                // searchMatchCount
     uint32_t D;                  // output offset of the open sequence's token
     uint32_t pend;               // literals of the open sequence already stored provisionally at out[D+1 ..)
+    int32_t head;                // out: position of the match that made the span stop (kSpanStopped)
 };
 
-// Runs the single-warp parse from state `st`.  yield_room == 0: to the end of the block, final literals included; returns
-// the compressed size.  yield_room > 0 (team kernel): returns 0xFFFFFFFF as soon as the schedule is dense again
-// (smc <= 96) with at least yield_room bytes left, leaving the state in `st`; otherwise finishes the block as above.
-template <class Tab>
+// Runs the single-warp parse of the block [start, start + len) from state `st`.
+//   limit >= start + len : parses to the end of the block, emits the final literals, returns the compressed size.
+//   limit <  start + len : (segment-parallel compression) stops right after the first sequence whose match starts at a
+//                          position >= limit -- a point defined by the serial parse alone, so it is the same however the
+//                          probes were batched, and no literals are pending there -- leaves that state in `st`
+//                          (st.D = bytes emitted, st.head = that match's position) and returns kSpanStopped.  If the block
+//                          has no such sequence it is finished as above.
+// kEmit == false runs the identical parse without writing output (warm-up of a speculative segment).
+constexpr uint32_t kSpanStopped = 0xFFFFFFFFu;
+template <class Tab, bool kEmit>
 __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const int32_t start, const int32_t len, Tab &T,
                                        uint8_t *const out, uint32_t *const ring /* kRingBytes of shared memory */,
-                                       SpanState &st, const int32_t yield_room) {
+                                       SpanState &st, const int32_t limit) {
     const uint32_t lane = lane_id();
     const uint32_t lt = (1u << lane) - 1u;
     const int32_t sEnd = start + len;
@@ -306,7 +324,6 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
     uint32_t smc = st.smc;
     uint32_t D = st.D;
     uint32_t pend = st.pend;
-    bool progressed = false;
     SrcFlat S{base};
 
     // forward ring: the 128-byte lines around the window live in a 3-line shared-memory ring filled by cp.async one line
@@ -322,12 +339,7 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
 
     while (sIndex < mflimit) {
         PT_MARK(0)
-        if (yield_room > 0 && progressed && smc <= 96u && sIndex + yield_room <= sEnd) {
-            st.sIndex = sIndex; st.anchor = anchor; st.smc = smc; st.D = D; st.pend = pend;
-            return 0xFFFFFFFFu;
-        }
-        progressed = true;
-        if (smc <= 96u && sIndex + 67 <= sEnd) {
+        if (smc <= 96u && sIndex + 67 <= sEnd && sIndex + 32 <= limit) {
             const int32_t w = sIndex;
             const uint32_t wmis = (uint32_t)((reinterpret_cast<uintptr_t>(base) + (uint32_t)w) & 3u);
             const int32_t wa = w - (int32_t)wmis;                                   // word-aligned window base
@@ -461,6 +473,7 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
                 if (!((inside >> lane) & 1u)) tab_set_raw(T, h, mine);
                 // ---- (C) parallel emission
                 if (heads) {
+                  if (kEmit) {
                     const int fh = __ffs(heads) - 1, lh = 31 - __clz(heads);
                     const uint32_t lit0 = __shfl_sync(FULL, myLit, fh);
                     if (a_rel0 < 0 && lit0 >= 15u) {
@@ -497,6 +510,7 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
                             *q = (uint8_t)rest;
                         }
                     }
+                  }
                     anchor = w + a_rel;
                     pend = 0;
                     smc = 67;
@@ -504,7 +518,7 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
                 PT_MARK(6)
                 // literal lanes behind the last match: provisional bytes of the still-open sequence
                 if (cur < 32u) {
-                    if (lane >= cur) out[D + 1u + pend + (lane - cur)] = (uint8_t)Sw[0];
+                    if (kEmit && lane >= cur) out[D + 1u + pend + (lane - cur)] = (uint8_t)Sw[0];
                     pend += 32u - cur;
                     smc = smc_cur + (32u - cur);
                     cur = 32;
@@ -545,7 +559,7 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
         if (((commit >> lane) & 1u) && ((same & commit) >> lane) == 1u) T.put(h, p);
         __syncwarp();
         if (!hits) {
-            if (vmask != FULL) break;
+            if (vmask != FULL) break;                            // ran into mflimit: loop ends
             sIndex += (int32_t)(skip_sum(smc + 32u) - base_sum);
             smc += 32u;
             continue;
@@ -571,25 +585,33 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
                 break;
             }
         }
-        const uint32_t code = (uint32_t)(ml - 4);
-        uint8_t *d = emit_literals(out + D, S, anchor, (uint32_t)(s0 - anchor), code < 15u ? code : 15u, lane);
-        const uint32_t offset = (uint32_t)(s0 - m0);
-        if (lane == 0) { d[0] = (uint8_t)offset; d[1] = (uint8_t)(offset >> 8); }
-        d += 2;
-        if (code >= 15u) {
-            const uint32_t rest = code - 15u, n255 = rest / 255u;
-            for (uint32_t i = lane; i < n255; i += 32) d[i] = 255;
-            if (lane == 0) d[n255] = (uint8_t)(rest - n255 * 255u);
-            d += n255 + 1;
+        if (kEmit) {
+            const uint32_t code = (uint32_t)(ml - 4);
+            uint8_t *d = emit_literals(out + D, S, anchor, (uint32_t)(s0 - anchor), code < 15u ? code : 15u, lane);
+            const uint32_t offset = (uint32_t)(s0 - m0);
+            if (lane == 0) { d[0] = (uint8_t)offset; d[1] = (uint8_t)(offset >> 8); }
+            d += 2;
+            if (code >= 15u) {
+                const uint32_t rest = code - 15u, n255 = rest / 255u;
+                for (uint32_t i = lane; i < n255; i += 32) d[i] = 255;
+                if (lane == 0) d[n255] = (uint8_t)(rest - n255 * 255u);
+                d += n255 + 1;
+            }
+            D = (uint32_t)(d - out);
         }
-        D = (uint32_t)(d - out);
         pend = 0;
         sIndex = anchor = s0 + ml;
         PT_MARK(8)
         PT_COUNT(11, 1)
+        if (s0 >= limit) {                   // first sequence that starts in the next segment: hand the state over
+            st.sIndex = sIndex; st.anchor = anchor; st.smc = smc; st.D = D; st.pend = 0; st.head = s0;
+            PT_FLUSH
+            return kSpanStopped;
+        }
     }
-    uint8_t *d = emit_literals(out + D, S, anchor, (uint32_t)(sEnd - anchor), 0u, lane);
     PT_FLUSH
+    if (!kEmit) return 0u;
+    uint8_t *d = emit_literals(out + D, S, anchor, (uint32_t)(sEnd - anchor), 0u, lane);
     return (uint32_t)(d - out);
 }
 
@@ -597,8 +619,8 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
 template <class Tab>
 __device__ __forceinline__ uint32_t compress_block_warp_v2(const uint8_t *__restrict__ base, const int32_t start, const int32_t len,
                                                            Tab &T, uint8_t *const out, uint32_t *const ring) {
-    SpanState st{start, start, 67u, 0u, 0u};
-    return compress_span_warp(base, start, len, T, out, ring, st, 0);
+    SpanState st{start, start, 67u, 0u, 0u, -1};
+    return compress_span_warp<Tab, true>(base, start, len, T, out, ring, st, INT_MAX);
 }
 
 // ------------------------------------------------------------------ compress kernels
@@ -710,6 +732,171 @@ k_compress_generic32(const uint8_t *__restrict__ src, const uint64_t *__restrict
         }
         if (lane == 0) comp_len[b] = c;
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ segment-parallel compression (large blocks, linked chains)
+// The greedy parse forgets its past: a table entry older than 65535 bytes is rejected forever (blockCompress.js:62), and
+// slots are overwritten as the parse goes on, so a parse started from an EMPTY table a few hundred KiB early converges to
+// exactly the state of the true parse (tools/resync_stats.c: 384 KiB of warm-up suffice in 97 %, 512 KiB in > 99 % of the
+// cases on the synthetic corpora).  A chain of blocks that carry the table (linked blocks, bufferCompress.js:182,219,234)
+// or one large block is therefore cut into segments; one warp per segment
+//   1. warms up: parses [seg_begin - W, seg_begin) from an empty table without output, up to the first sequence that
+//      starts at or behind seg_begin, and snapshots that state (next position, head, whole table),
+//   2. parses on with output up to the first sequence that starts at or behind seg_end; the state it ends in stays in its
+//      table buffer.
+// k_seg_verify then compares every segment's snapshot with its predecessor's end state (entries older than 65535 bytes count
+// as empty).  Equal states make the speculative segment exact by induction from the chain's first segment, which starts
+// from the true initial table; a segment whose snapshot differs is re-run from its predecessor's end state (host loop),
+// so the bytes are always those of the serial loop -- speculation only decides how much runs in parallel.
+struct SegJob {
+    int32_t chain_start, chain_end;      // the chain: consecutive blocks of block_size from chain_start (the last may be short)
+    int32_t warm_begin;                  // where the warm-up parse starts (== seg_begin: no warm-up, exact start)
+    int32_t seg_begin, seg_end;
+    uint32_t first_slot;                 // piece slot of the first block this segment overlaps
+    uint32_t first_block;                // global index of that block
+    uint32_t flags;                      // kSegFirst | kSegLast | kSegRerun
+};
+enum : uint32_t { kSegFirst = 1u, kSegLast = 2u, kSegRerun = 4u };
+struct SegState { int32_t s, head; };    // next probe position (== anchor, searchMatchCount == 67 there) and the stopping head
+                                         // (-1: fresh start of the block that begins at s)
+// offset of the piece that starts at source offset x of its block (pieces of one block never overlap: a run of complete
+// sequences over n >= 4 source bytes takes at most n + n/255 bytes)
+__device__ __host__ __forceinline__ uint64_t seg_piece_offset(uint64_t x) { return x + (x >> 3); }
+
+template <bool kEmit>
+__device__ __forceinline__ void seg_run(const uint8_t *__restrict__ base, const SegJob &J, int32_t block_size, TabG32 &T,
+                                        uint32_t *ring, SegState &S, int32_t limit, uint8_t *blockbuf, uint64_t blockbuf_stride,
+                                        uint32_t *piece_off, uint32_t *piece_len, int32_t stop_fresh_at) {
+    // Runs blocks from state S until a span stops at `limit` (S = hand-over state) or a fresh block start >= stop_fresh_at
+    // (or the chain's end) is reached.
+    const uint32_t lane = lane_id();
+    for (;;) {
+        if (S.s >= J.chain_end) break;
+        const int32_t bi = (S.s - J.chain_start) / block_size;
+        const int32_t bstart = J.chain_start + bi * block_size;
+        const int32_t blen = (J.chain_end - bstart) < block_size ? (J.chain_end - bstart) : block_size;
+        const bool fresh = S.head < 0;
+        if (fresh && bstart >= stop_fresh_at) break;
+        if (!fresh && S.head >= limit) break;                    // the hand-over sequence already lies behind this segment
+        SpanState st{S.s, S.s, 67u, 0u, 0u, -1};
+        uint32_t r;
+        if (kEmit) {
+            const int32_t bfirst = (J.seg_begin - J.chain_start) / block_size;
+            const uint32_t slot = J.first_slot + (uint32_t)(bi - bfirst);
+            const uint32_t off = (uint32_t)seg_piece_offset((uint64_t)(S.s - bstart));
+            uint8_t *out = blockbuf + (uint64_t)(J.first_block + (uint32_t)(bi - bfirst)) * blockbuf_stride + off;
+            r = compress_span_warp<TabG32, true>(base, bstart, blen, T, out, ring, st, limit);
+            if (lane == 0) { piece_off[slot] = off; piece_len[slot] = r == kSpanStopped ? st.D : r; }
+        } else {
+            r = compress_span_warp<TabG32, false>(base, bstart, blen, T, nullptr, ring, st, limit);
+        }
+        if (r == kSpanStopped) { S.s = st.sIndex; S.head = st.head; break; }
+        S.s = bstart + blen; S.head = -1;                        // block finished: the next one starts fresh (table carried)
+    }
+}
+
+constexpr int kSegWarps = 7;
+__global__ void __launch_bounds__(kSegWarps * 32, 4)
+k_compress_segments(const uint8_t *__restrict__ base, const SegJob *__restrict__ jobs, const uint32_t *__restrict__ job_list,
+                    uint32_t njobs, int32_t block_size, const int32_t *__restrict__ init_table /* nullable: chain 0 */,
+                    int32_t *tables, int32_t *snaps, SegState *snap_state, SegState *end_state,
+                    uint8_t *blockbuf, uint64_t blockbuf_stride, uint32_t *piece_off, uint32_t *piece_len, uint32_t *counter,
+                    uint32_t active_warps) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    if (warp >= active_warps) return;
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + warp * kRingBytes);
+    for (;;) {
+        const uint32_t q = next_block(counter, lane);
+        if (q >= njobs) break;
+        const uint32_t j = job_list ? job_list[q] : q;
+        const SegJob J = jobs[j];
+        {   // this run's pieces replace whatever an earlier run of the segment left in its slots
+            const int32_t last_pos = (J.seg_end < J.chain_end ? J.seg_end : J.chain_end) - 1;
+            const uint32_t nslots = (uint32_t)((last_pos - J.chain_start) / block_size - (J.seg_begin - J.chain_start) / block_size) + 1u;
+            for (uint32_t i = lane; i < nslots; i += 32) piece_len[J.first_slot + i] = 0;
+        }
+        int32_t *tab = tables + (size_t)j * kHashEntries;
+        uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+        TabG32 T{tab};
+        SegState S;
+        if (J.flags & kSegRerun) {
+            // exact start: the predecessor's end state (its table buffer is final, nobody writes it during this launch)
+            const uint4 *p4 = reinterpret_cast<const uint4 *>(tables + (size_t)(j - 1) * kHashEntries);
+            uint4 *s4 = reinterpret_cast<uint4 *>(snaps + (size_t)j * kHashEntries);
+            for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) { const uint4 v = __ldcg(p4 + i); __stcg(t4 + i, v); __stcg(s4 + i, v); }
+            S = end_state[j - 1];
+            if (lane == 0) snap_state[j] = S;                    // the start is now exact as long as the predecessor's end stands
+            __syncwarp();
+        } else if (J.flags & kSegFirst) {
+            if (init_table && j == 0) {
+                const uint4 *i4 = reinterpret_cast<const uint4 *>(init_table);
+                for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) __stcg(t4 + i, i4[i]);
+            } else {
+                for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) __stcg(t4 + i, make_uint4(0, 0, 0, 0));
+            }
+            S.s = J.seg_begin; S.head = -1;
+            __syncwarp();
+        } else {
+            for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) __stcg(t4 + i, make_uint4(0, 0, 0, 0));
+            __syncwarp();
+            S.s = J.warm_begin; S.head = -1;
+            seg_run<false>(base, J, block_size, T, ring, S, J.seg_begin, nullptr, 0, nullptr, nullptr, J.seg_begin);
+            __syncwarp();
+            uint4 *s4 = reinterpret_cast<uint4 *>(snaps + (size_t)j * kHashEntries);
+            for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) __stcg(s4 + i, __ldcg(t4 + i));
+            if (lane == 0) snap_state[j] = S;
+        }
+        const bool last = (J.flags & kSegLast) != 0;
+        seg_run<true>(base, J, block_size, T, ring, S, last ? INT_MAX : J.seg_end, blockbuf, blockbuf_stride, piece_off, piece_len,
+                      last ? INT_MAX : J.seg_end);
+        if (lane == 0) end_state[j] = S;
+        __syncwarp();
+    }
+}
+
+// bad[j] = 1 when segment j's warm-up snapshot differs from its predecessor's end state (j not first in its chain).
+__global__ void __launch_bounds__(256)
+k_seg_verify(const SegJob *__restrict__ jobs, uint32_t njobs, const int32_t *__restrict__ tables, const int32_t *__restrict__ snaps,
+             const SegState *__restrict__ snap_state, const SegState *__restrict__ end_state, uint8_t *bad) {
+    const uint32_t j = blockIdx.x;
+    if (j >= njobs) return;
+    __shared__ int diff;
+    if (threadIdx.x == 0) diff = 0;
+    __syncthreads();
+    if (jobs[j].flags & kSegFirst) { if (threadIdx.x == 0) bad[j] = 0; return; }
+    const SegState a = snap_state[j], b = end_state[j - 1];
+    int d = (a.s != b.s) | (a.head != b.head);
+    const int32_t horizon = b.s - 65535;                         // older entries can never pass blockCompress.js:62 again
+    const int32_t *ta = snaps + (size_t)j * kHashEntries, *tb = tables + (size_t)(j - 1) * kHashEntries;
+    for (uint32_t i = threadIdx.x; i < kHashEntries; i += blockDim.x) {
+        int32_t x = ta[i] - 1, y = tb[i] - 1;
+        if (x < horizon) x = -1;
+        if (y < horizon) y = -1;
+        d |= x != y;
+    }
+    if (d) atomicOr(&diff, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) bad[j] = (uint8_t)diff;
+}
+
+// Concatenates the pieces of every block (slots [slot_first[b], +slot_count[b]), in order) into dst + dst_off[b].
+__global__ void __launch_bounds__(256)
+k_seg_assemble(const uint8_t *__restrict__ blockbuf, uint64_t blockbuf_stride, const uint32_t *__restrict__ slot_first,
+               const uint32_t *__restrict__ slot_count, const uint32_t *__restrict__ piece_off, const uint32_t *__restrict__ piece_len,
+               uint32_t nblocks, uint8_t *__restrict__ dst, const uint64_t *__restrict__ dst_off, uint32_t *__restrict__ comp_len) {
+    for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const uint8_t *src = blockbuf + (uint64_t)b * blockbuf_stride;
+        uint8_t *d = dst + dst_off[b];
+        uint32_t pos = 0;
+        for (uint32_t k = 0; k < slot_count[b]; ++k) {
+            const uint32_t sl = slot_first[b] + k, n = piece_len[sl];
+            const uint8_t *s = src + piece_off[sl];
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) d[pos + i] = s[i];
+            pos += n;
+        }
+        if (threadIdx.x == 0) comp_len[b] = pos;
     }
 }
 

@@ -64,6 +64,10 @@ const char *dlz4_last_error(const dlz4_ctx *ctx);
 uint64_t dlz4_launch_count(const dlz4_ctx *ctx);
 /* Device time in ms of the most recent host-pointer call's kernel section (CUDA events). */
 float dlz4_last_kernel_ms(const dlz4_ctx *ctx);
+/* Segment-parallel compression (linked-block chains, bufferCompress.js:182,219,234, and independent blocks > 64 KiB): how
+ * many segments the most recent frame call used, how many of them had to be re-run because the speculative start state
+ * differed from the serial parse's, and in how many rounds.  The output bytes are those of the serial loop either way. */
+void dlz4_segment_stats(const dlz4_ctx *ctx, uint32_t *segments, uint32_t *reruns, uint32_t *rounds);
 
 /* Page-locked host memory, so host-pointer calls copy at the full PCIe rate (an N-API addon backs its external
  * ArrayBuffers with it).  Any host pointer is accepted everywhere; pageable ones are simply slower. */
