@@ -45,6 +45,7 @@ struct dlz4_ctx {
     uint16_t *d_gtabs = nullptr;        // kGtabRegions x hy_grid x kHyGlWarps tables of 16384 x u16 (one region per stream lane)
     Buf work, comp, seg, out, meta, aux, pin;
     std::string last_error;
+    uint64_t jump_min_bytes = 256ull << 10;                  // frames at least this long may use the jump decoder (DLZ4_JUMP_MIN_KIB)
     uint64_t seg_min_bytes = 256ull << 10;                   // frames at least this long use the segment-parallel engine (DLZ4_SEG_MIN_KIB)
     uint32_t seg_jobs = 0, seg_reruns = 0, seg_rounds = 0;   // last segment-parallel call: segments, re-run segments, rounds
     uint64_t launches = 0;
@@ -283,6 +284,59 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
     return DLZ4_OK;
 }
 
+// Jump decoder (k_jd_*): token scan of every block, then pointer doubling inside units of <= 8 MiB of consecutive blocks.
+// Used for linked-block frames and for frames of few large blocks, where one warp per dependent stream would crawl.
+// On return *total = decoded bytes and status_h[i] = per-block status (first non-zero one is the frame's error).
+int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, const uint64_t *d_soff, const uint32_t *d_slen, const uint8_t *d_stored,
+                    const std::vector<uint32_t> &slen, uint32_t n, uint32_t B, uint8_t *d_out, uint64_t cap_total, const uint8_t *d_dict,
+                    uint32_t dwin, bool linked, uint32_t *d_olen, uint8_t *d_status, std::vector<uint8_t> &status_h, uint64_t *total,
+                    cudaStream_t st) {
+    std::vector<uint64_t> seq_base(n + 1, 0);
+    for (uint32_t i = 0; i < n; ++i) seq_base[i + 1] = seq_base[i] + slen[i] / 3 + B / 2048 + 8;
+    const uint32_t per_unit = std::max<uint32_t>(1u, (8u << 20) / B);
+    const uint32_t nunits = (n + per_unit - 1) / per_unit;
+    int rounds = 1;
+    while ((1ull << rounds) < (uint64_t)per_unit * B) ++rounds;          // chain depth <= unit bytes, halved per round
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_seq = carve((size_t)seq_base[n] * sizeof(JdSeq)), o_sb = carve((size_t)(n + 1) * 8), o_ns = carve((size_t)n * 4);
+    const size_t o_reach = carve((size_t)n * 4), o_base = carve((size_t)(n + 1) * 8), o_P = carve((size_t)per_unit * B * 4);
+    const size_t o_todo = carve((size_t)nunits * (rounds + 2) * 4);
+    CKS(reserve(ctx, ctx->aux, off));
+    uint8_t *A = (uint8_t *)ctx->aux.p;
+    JdSeq *d_seq = (JdSeq *)(A + o_seq);
+    uint64_t *d_sb = (uint64_t *)(A + o_sb), *d_base = (uint64_t *)(A + o_base);
+    uint32_t *d_ns = (uint32_t *)(A + o_ns), *d_reach = (uint32_t *)(A + o_reach), *d_todo = (uint32_t *)(A + o_todo);
+    int32_t *d_P = (int32_t *)(A + o_P);
+    CK(cudaMemcpyAsync(d_sb, seq_base.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_todo, 0, (size_t)nunits * (rounds + 2) * 4, st));
+    CK(cudaMemsetAsync(d_reach, 0, (size_t)n * 4, st));
+    CK(cudaMemsetAsync(ctx->d_counter, 0, 4, st));
+    k_jd_scan<<<(int)std::min<uint64_t>((n + 3) / 4, (uint64_t)ctx->sm_count * 8), 128, 0, st>>>(d_frame, d_soff, d_slen, d_stored, n, B, d_seq, d_sb, d_ns,
+                                                                                                 d_olen, d_reach, d_status, ctx->d_counter);
+    k_jd_bases<<<1, 32, 0, st>>>(d_olen, d_reach, n, dwin, linked ? 1 : 0, cap_total, d_base, d_status);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    status_h.assign(n, 0);
+    CK(cudaMemcpyAsync(status_h.data(), d_status, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(total, d_base + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < n; ++i)
+        if (status_h[i]) return DLZ4_OK;                                  // the caller maps the first status to the error
+    const int wide = ctx->sm_count * 8;
+    for (uint32_t u = 0; u < nunits; ++u) {
+        const uint32_t b0 = u * per_unit, b1 = std::min<uint32_t>(n, b0 + per_unit);
+        uint32_t *todo = d_todo + (size_t)u * (rounds + 2);
+        const uint32_t cpb = std::max<uint32_t>(1u, 2048u / (b1 - b0));
+        k_jd_fill<<<(b1 - b0) * cpb, 256, 0, st>>>(d_frame, d_soff, d_seq, d_sb, d_ns, d_base, b0, cpb, d_out, d_dict, dwin, linked ? 1 : 0, d_P, todo);
+        for (int r = 0; r < rounds; ++r) k_jd_round<<<wide, 256, 0, st>>>(d_P, d_base, b0, b1, todo + r, todo + r + 1);
+        k_jd_emit<<<wide, 256, 0, st>>>(d_P, d_base, b0, b1, d_out);
+        ctx->launches += 2 + rounds;
+    }
+    CK(cudaGetLastError());
+    return DLZ4_OK;
+}
+
 int launch_chain(dlz4_ctx *ctx, const uint8_t *work, int32_t start, int32_t total, int32_t block, uint32_t nblocks,
                  int32_t *table_io, uint8_t *dst, uint64_t stride, uint32_t *comp_len, cudaStream_t st) {
     k_compress_chain<<<1, 32, kHashEntries * 4 + kRingBytes, st>>>(work, start, total, block, nblocks, table_io, dst, stride, comp_len);
@@ -328,6 +382,7 @@ int dlz4_init(int device, dlz4_ctx **out) {
     CK(cudaFuncSetAttribute(k_compress_fresh16<kWarpsFresh16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kWarpsFresh16 * (kHashEntries * 2 + kRingBytes)));
     if (const char *e = getenv("DLZ4_SEG_MIN_KIB")) ctx->seg_min_bytes = (uint64_t)atoll(e) << 10;     // huge value: serial chain only
+    if (const char *e = getenv("DLZ4_JUMP_MIN_KIB")) ctx->jump_min_bytes = (uint64_t)atoll(e) << 10;
     if (const char *e = getenv("DLZ4_HYBRID")) ctx->hybrid = atoi(e) != 0;      // 0: the 7-warp shared-memory-only kernel (A/B runs)
     ctx->hy_grid = ctx->sm_count * kHyCtasPerSm;
     CK(cudaMalloc(&ctx->d_gtabs, (size_t)kGtabRegions * ctx->hy_grid * kHyGlWarps * kHashEntries * 2));
@@ -1151,8 +1206,14 @@ int dlz4_frame_decompress(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_le
     uint64_t total = 0;
     int first_status = 0;
     if (n) {
-        if (!info.block_independence) {
-            // linked blocks: each block may read the previous blocks' output -> serial chain (one warp)
+        const bool jump = frame_len >= ctx->jump_min_bytes && (!info.block_independence || (B > 65536 && n < 1024));
+        if (jump) {
+            // linked blocks (block k reads block k-1's output) or few large blocks: token scan + pointer doubling
+            CKS(decompress_jump(ctx, d_frame, d_soff, d_slen, d_stored, slen, n, B, d_out, cap_total, dwin ? d_dict : nullptr, (uint32_t)dwin,
+                                !info.block_independence, d_olen, d_status, status, &total, st));
+            for (uint32_t i = 0; i < n && !first_status; ++i) first_status = status[i];
+        } else if (!info.block_independence) {
+            // short linked frame: serial chain (one warp)
             k_decompress_chain<<<1, 32, 0, st>>>(d_frame, d_soff, d_slen, d_stored, n, d_out, cap_total, dwin ? d_dict : nullptr,
                                                 (uint32_t)dwin, d_olen, d_status, ctx->d_total);
             ctx->launches++;

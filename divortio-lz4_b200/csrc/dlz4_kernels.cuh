@@ -1180,6 +1180,288 @@ k_decompress_chain(const uint8_t *__restrict__ src, const uint64_t *__restrict__
     if (lane == 0) *total_out = (uint64_t)op;
 }
 
+// ------------------------------------------------------------------ jump decoder (linked frames, large blocks)
+// A linked-block frame (bufferDecompress.js:153, block k reads the output of block k-1) and a block of several MiB are one
+// dependent stream for the warp-per-block decoder above.  Every output byte, though, is either a literal of the compressed
+// stream or a copy of an EARLIER output byte, so decoding is pointer chasing and pointer chasing parallelises by doubling:
+//   k_jd_scan     one warp per block walks the tokens only (no copies) and writes one record per sequence;
+//   k_jd_bases    exclusive scan of the decoded block lengths, history / capacity checks in the reference's error order;
+//   per unit of <= 8 MiB of consecutive blocks (its 4-byte-per-byte pointer array stays in L2):
+//     k_jd_fill   P[x] = ~literal, or ~out[q] when the source q lies before the unit (already final), or q itself;
+//     k_jd_round  P[x] = P[P[x]] for unresolved x, repeated until none is left (chain depth halves per round);
+//     k_jd_emit   out[x] = ~P[x].
+// Units run in stream order, so a unit's sources in earlier units are final bytes.  Nothing here depends on how the
+// frame was parsed: the result is the byte-exact LZ4 decode whatever the dependency structure.
+struct JdSeq { uint32_t op, ip, lit, ml, off, pad0, pad1, pad2; };    // block-relative output / input positions
+constexpr uint32_t kJdChunk = 4096;                                    // long literal runs / matches are recorded in chunks
+
+__device__ __forceinline__ void jd_emit_rec(JdSeq *rec, uint32_t &ns, uint32_t op, uint32_t ip, uint32_t lit, uint32_t ml, uint32_t off,
+                                            uint32_t lane) {
+    // literals in chunks, then the match in chunks (each record is one warp-pass of work in k_jd_fill)
+    while (lit > kJdChunk) {
+        if (lane == 0) rec[ns] = JdSeq{op, ip, kJdChunk, 0u, 0u, 0u, 0u, 0u};
+        ++ns; op += kJdChunk; ip += kJdChunk; lit -= kJdChunk;
+    }
+    uint32_t first = ml > kJdChunk ? kJdChunk : ml;
+    if (lane == 0) rec[ns] = JdSeq{op, ip, lit, first, off, 0u, 0u, 0u};
+    ++ns; op += lit + first; ml -= first;
+    while (ml) {
+        first = ml > kJdChunk ? kJdChunk : ml;
+        if (lane == 0) rec[ns] = JdSeq{op, 0u, 0u, first, off, 0u, 0u, 0u};
+        ++ns; op += first; ml -= first;
+    }
+}
+
+// One token, uniform across the warp (the serial form of blockDecompress.js:55-139 without the copies): used for tokens the
+// speculative window below cannot size (long length runs, chunked records).  Returns false when the block ends here.
+__device__ __forceinline__ bool jd_scan_one(const uint8_t *__restrict__ in, uint32_t n, uint32_t block_max, JdSeq *rec, uint32_t &ns,
+                                            uint32_t &ip, uint64_t &op, uint32_t &rch, uint32_t &st, uint32_t lane) {
+    const uint32_t token = in[ip++];                             // :58
+    uint32_t lit = token >> 4;                                   // :61
+    if (lit == 15u) {                                            // :62-68
+        uint32_t v;
+        do {
+            if (ip >= n) { st = ST_MALFORMED; return false; }
+            v = in[ip++]; lit += v;
+        } while (v == 255u);
+    }
+    if (op + lit > block_max) { st = ST_OUTPUT_TOO_SMALL; return false; }              // :74 (a block never decodes past blockMaxSize)
+    if ((uint64_t)ip + lit > n) { st = ST_MALFORMED; return false; }                   // :75
+    const uint32_t litp = ip;
+    ip += lit;
+    if (ip >= n) {                                               // :123 last sequence: literals only
+        jd_emit_rec(rec, ns, (uint32_t)op, litp, lit, 0u, 0u, lane);
+        op += lit;
+        return false;
+    }
+    if (ip + 2 > n) { st = ST_MALFORMED; return false; }
+    const uint32_t offset = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8);             // :126
+    ip += 2;
+    if (offset == 0) { st = ST_OFFSET_ZERO; return false; }                            // :128
+    uint32_t ml = token & 15u;                                   // :131
+    if (ml == 15u) {                                             // :132-138
+        uint32_t v;
+        do {
+            if (ip >= n) { st = ST_MALFORMED; return false; }
+            v = in[ip++]; ml += v;
+        } while (v == 255u);
+    }
+    ml += 4;                                                     // :139
+    if (op + lit + ml > block_max) { st = ST_OUTPUT_TOO_SMALL; return false; }
+    const int64_t src_rel = (int64_t)op + lit - offset;          // :142
+    if (src_rel < 0 && (uint32_t)(-src_rel) > rch) rch = (uint32_t)(-src_rel);
+    jd_emit_rec(rec, ns, (uint32_t)op, litp, lit, ml, offset, lane);
+    op += lit + ml;
+    return true;
+}
+
+// Token walk of every block, one warp per block.  The token chain is serial (a token's position follows from the previous
+// token's lengths), so the warp speculates: lane l sizes the sequence that WOULD start at byte ip + l; the warp then hops
+// from lane 0 along the `next` links (two shuffles per real token instead of three dependent loads) and the lanes it
+// visited -- the real tokens -- check themselves in the reference's order and write their records together.
+// reach[b] = how far before its own start the block's matches read (checked against the history in k_jd_bases).
+__global__ void __launch_bounds__(128)
+k_jd_scan(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ src_len,
+          const uint8_t *__restrict__ stored, uint32_t nblocks, uint32_t block_max, JdSeq *seqs, const uint64_t *__restrict__ seq_base,
+          uint32_t *nseq, uint32_t *out_len, uint32_t *reach, uint8_t *status, uint32_t *counter) {
+    const uint32_t lane = lane_id();
+    const uint32_t lt = (1u << lane) - 1u;
+    for (;;) {
+        const uint32_t b = next_block(counter, lane);
+        if (b >= nblocks) break;
+        const uint8_t *in = src + src_off[b];
+        const uint32_t n = src_len[b];
+        JdSeq *rec = seqs + seq_base[b];
+        uint32_t ns = 0, ip = 0, rch = 0, st = ST_OK;
+        uint64_t op = 0;
+        if (stored[b]) {                                         // bufferDecompress.js:147-149: raw bytes
+            jd_emit_rec(rec, ns, 0u, 0u, n, 0u, 0u, lane);
+            op = n;
+            if (n > block_max) st = ST_OUTPUT_TOO_SMALL;
+        } else {
+            while (ip < n) {
+                // ---- every lane sizes "its" sequence
+                const uint32_t q = ip + lane;
+                uint32_t lit = 0, ml = 0, offset = 1, litp = 0, nxt = 1, err = ST_OK;
+                bool slow = false, last = false;
+                if (q < n) {
+                    const uint32_t token = in[q];
+                    uint32_t p = q + 1;
+                    lit = token >> 4;
+                    if (lit == 15u) {                            // at most 3 length bytes speculatively
+                        uint32_t v = 255u;
+                        for (int k = 0; k < 3 && v == 255u; ++k) {
+                            if (p >= n) { err = ST_MALFORMED; v = 0; break; }
+                            v = in[p++]; lit += v;
+                        }
+                        if (v == 255u) slow = true;
+                    }
+                    litp = p;
+                    const uint64_t endlit = (uint64_t)p + lit;
+                    if (!err && !slow) {
+                        if (endlit > n) err = ST_MALFORMED | 0x100u;          // :75 -- comes after the :74 capacity check
+                        else if (endlit == n) { last = true; nxt = n - ip; }
+                        else if (endlit + 2 > n) err = ST_MALFORMED | 0x200u;
+                        else {
+                            offset = (uint32_t)in[endlit] | ((uint32_t)in[endlit + 1] << 8);
+                            p = (uint32_t)endlit + 2;
+                            ml = token & 15u;
+                            if (offset == 0) err = ST_OFFSET_ZERO | 0x200u;
+                            else if (ml == 15u) {
+                                uint32_t v = 255u;
+                                for (int k = 0; k < 3 && v == 255u; ++k) {
+                                    if (p >= n) { err = ST_MALFORMED | 0x200u; v = 0; break; }
+                                    v = in[p++]; ml += v;
+                                }
+                                if (v == 255u) slow = true;
+                            }
+                            ml += 4;
+                            nxt = p - ip;
+                        }
+                    }
+                    if (lit > kJdChunk || ml > kJdChunk) slow = true;         // chunked records: serial form
+                }
+                // ---- hop along the real tokens
+                uint32_t cur = 0, real = 0, myop = 0;
+                uint64_t opw = op;
+                const uint32_t adv = lit + ml;
+                const uint32_t stopper = __ballot_sync(FULL, slow || err != ST_OK || last || q >= n);
+                while (cur < 32u) {
+                    real |= 1u << cur;
+                    if (lane == cur) myop = (uint32_t)opw;
+                    if ((stopper >> cur) & 1u) break;
+                    opw += __shfl_sync(FULL, adv, cur);
+                    cur = __shfl_sync(FULL, nxt, cur);
+                }
+                // ---- the visited lanes check themselves (reference order: :74 capacity, :75 fit, :128 offset, match capacity)
+                const bool mine = (real >> lane) & 1u;
+                uint32_t verdict = ST_OK;
+                if (mine && !slow && q < n) {
+                    if ((err & 0xFFu) && !(err & 0x300u)) verdict = err;                       // length bytes ran out
+                    else if ((uint64_t)myop + lit > block_max) verdict = ST_OUTPUT_TOO_SMALL;   // :74
+                    else if (err) verdict = err & 0xFFu;
+                    else if (!last && (uint64_t)myop + lit + ml > block_max) verdict = ST_OUTPUT_TOO_SMALL;
+                }
+                const uint32_t bad = __ballot_sync(FULL, verdict != ST_OK);
+                const uint32_t slowm = __ballot_sync(FULL, mine && (slow || q >= n));
+                // tokens in front of the first bad / slow one are good
+                const uint32_t cut = bad | slowm;
+                const uint32_t good = cut ? (real & ((cut & (0u - cut)) - 1u)) : real;
+                if ((good >> lane) & 1u) {
+                    rec[ns + __popc(good & lt)] = JdSeq{myop, litp, lit, last ? 0u : ml, last ? 0u : offset, 0u, 0u, 0u};
+                    if (!last) {
+                        const int64_t src_rel = (int64_t)myop + lit - offset;                 // :142
+                        if (src_rel < 0) atomicMax(&reach[b], (uint32_t)(-src_rel));
+                    }
+                }
+                ns += __popc(good);
+                bool ended = false;
+                if (good) {
+                    const int hi = 31 - __clz(good);
+                    op = (uint64_t)__shfl_sync(FULL, myop, hi) + __shfl_sync(FULL, adv, hi);
+                    ip += __shfl_sync(FULL, nxt, hi);
+                    ended = __shfl_sync(FULL, (int)last, hi) != 0;
+                }
+                if (bad && (!slowm || (bad & (0u - bad)) < (slowm & (0u - slowm)))) {
+                    st = __shfl_sync(FULL, verdict, __ffs(bad) - 1);
+                    break;
+                }
+                if (ended) break;
+                if (slowm && ip < n) {
+                    if (!jd_scan_one(in, n, block_max, rec, ns, ip, op, rch, st, lane)) break;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { nseq[b] = ns; out_len[b] = (uint32_t)op; atomicMax(&reach[b], rch); status[b] = (uint8_t)st; }
+    }
+}
+
+// base[b] = decoded bytes before block b (base[nblocks] = total); a block that reads further back than its history
+// (dictionary, plus the earlier output when linked) gets the reference's "Dictionary Offset Out of Bounds" (:150-152).
+__global__ void __launch_bounds__(32)
+k_jd_bases(const uint32_t *__restrict__ out_len, const uint32_t *__restrict__ reach, uint32_t nblocks, uint32_t dict_len, int linked,
+           uint64_t cap_total, uint64_t *base, uint8_t *status) {
+    if (threadIdx.x) return;
+    uint64_t acc = 0;
+    for (uint32_t b = 0; b < nblocks; ++b) {
+        base[b] = acc;
+        if (status[b] == ST_OK) {
+            const uint64_t hist = (uint64_t)dict_len + (linked ? acc : 0ull);
+            if (reach[b] > hist) status[b] = ST_DICT_OOB;
+            else if (acc + out_len[b] > cap_total) status[b] = ST_OUTPUT_TOO_SMALL;
+        }
+        acc += out_len[b];
+    }
+    base[nblocks] = acc;
+}
+
+// One unit = blocks [b0, b1).  P is indexed from the unit's first output byte.
+__global__ void __launch_bounds__(256)
+k_jd_fill(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, const JdSeq *__restrict__ seqs,
+          const uint64_t *__restrict__ seq_base, const uint32_t *__restrict__ nseq, const uint64_t *__restrict__ base, uint32_t b0,
+          uint32_t ctas_per_block, const uint8_t *out /* final bytes before the unit */, const uint8_t *__restrict__ dict,
+          uint32_t dict_len, int linked, int32_t *P, uint32_t *unresolved) {
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t b = b0 + blockIdx.x / ctas_per_block;
+    const uint32_t gw = (blockIdx.x % ctas_per_block) * 8u + warp, nw = ctas_per_block * 8u;
+    const uint8_t *in = src + src_off[b];
+    const JdSeq *rec = seqs + seq_base[b];
+    const uint64_t ustart = base[b0], bstart = base[b];
+    const uint32_t ns = nseq[b];
+    uint32_t pending = 0;
+    for (uint32_t si = gw; si < ns; si += nw) {
+        const JdSeq q = rec[si];
+        const uint32_t total = q.lit + q.ml;
+        for (uint32_t j = lane; j < total; j += 32) {
+            const uint64_t x = bstart + q.op + j;                // global output position
+            int32_t v;
+            if (j < q.lit) {
+                v = ~(int32_t)in[q.ip + j];
+            } else {
+                const int64_t sg = (int64_t)x - q.off;           // global source position
+                const int64_t sb = sg - (int64_t)bstart;         // relative to the block's start
+                if (sg >= (int64_t)ustart && (linked || sb >= 0)) {
+                    v = (int32_t)(sg - (int64_t)ustart);         // inside the unit: resolve by doubling
+                    ++pending;
+                } else if (linked ? sg >= 0 : sb >= 0) {
+                    v = ~(int32_t)out[sg];                       // earlier unit: final already
+                } else {
+                    // dictionary: directly before output position 0 (linked) / before every block (independent)
+                    v = ~(int32_t)dict[(int64_t)dict_len + (linked ? sg : sb)];
+                }
+            }
+            P[x - ustart] = v;
+        }
+    }
+    pending = __reduce_add_sync(FULL, pending);
+    if (lane == 0 && pending) atomicAdd(unresolved, pending);
+}
+
+__global__ void __launch_bounds__(256)
+k_jd_round(int32_t *P, const uint64_t *__restrict__ base, uint32_t b0, uint32_t b1, const uint32_t *todo, uint32_t *next_todo) {
+    if (*todo == 0) return;                                      // everything resolved in an earlier round
+    const uint64_t len = base[b1] - base[b0];
+    uint32_t pending = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int32_t v = P[i];
+        if (v >= 0) {
+            const int32_t w = P[v];                              // v < i: an earlier byte of the unit
+            P[i] = w;
+            pending += w >= 0;
+        }
+    }
+    pending = __reduce_add_sync(FULL, pending);
+    if (lane_id() == 0 && pending) atomicAdd(next_todo, pending);
+}
+
+__global__ void __launch_bounds__(256)
+k_jd_emit(const int32_t *__restrict__ P, const uint64_t *__restrict__ base, uint32_t b0, uint32_t b1, uint8_t *out) {
+    const uint64_t ustart = base[b0], len = base[b1] - ustart;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x)
+        out[ustart + i] = (uint8_t)~P[i];
+}
+
 // ------------------------------------------------------------------ xxHash32 (src/xxhash32/xxhash32.js:21-97)
 constexpr uint32_t P32_1 = 2654435761u, P32_2 = 2246822519u, P32_3 = 3266489917u, P32_4 = 668265263u, P32_5 = 374761393u;
 __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
