@@ -7,3 +7,14 @@ want=sys.argv[2:] or ['gpu__time_duration.sum','launch__registers_per_thread','l
 for i,h in enumerate(hdr):
     if h in want or ('warp_issue_stalled' in h and h.endswith('per_warp_active.pct')) or (len(sys.argv)>2 and any(w in h for w in sys.argv[2:])):
         print('%-90s %-14s %s'%(h,units[i],vals[i]))
+
+d={h:v for h,v in zip(hdr,vals)}
+items=[]
+for h,v in d.items():
+    if h.startswith('smsp__pcsamp_warps_issue_stalled_') and not h.endswith('_not_issued'):
+        try: items.append((float(v),h))
+        except Exception: pass
+tot=sum(x for x,_ in items) or 1.0
+print('warp stall sampling (share of samples):')
+for x,h in sorted(items,reverse=True)[:8]:
+    print('  %-60s %5.1f%%'%(h.replace('smsp__pcsamp_warps_issue_stalled_',''),100*x/tot))
