@@ -284,38 +284,92 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
     return DLZ4_OK;
 }
 
-// Jump decoder (k_jd_*): token scan of every block, then pointer doubling inside units of <= 8 MiB of consecutive blocks.
+// Jump decoder (k_jd_*): token scan of every block, then pointer doubling inside units of <= 16 MiB of consecutive blocks.
 // Used for linked-block frames and for frames of few large blocks, where one warp per dependent stream would crawl.
 // On return *total = decoded bytes and status_h[i] = per-block status (first non-zero one is the frame's error).
-int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, const uint64_t *d_soff, const uint32_t *d_slen, const uint8_t *d_stored,
+int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, uint64_t frame_span, const uint64_t *d_soff, const uint32_t *d_slen, const uint8_t *d_stored,
                     const std::vector<uint32_t> &slen, uint32_t n, uint32_t B, uint8_t *d_out, uint64_t cap_total, const uint8_t *d_dict,
                     uint32_t dwin, bool linked, uint32_t *d_olen, uint8_t *d_status, std::vector<uint8_t> &status_h, uint64_t *total,
                     cudaStream_t st) {
     std::vector<uint64_t> seq_base(n + 1, 0);
     for (uint32_t i = 0; i < n; ++i) seq_base[i + 1] = seq_base[i] + slen[i] / 3 + B / 2048 + 8;
-    const uint32_t per_unit = std::max<uint32_t>(1u, (8u << 20) / B);
+    uint32_t unit_bytes = 16u << 20;
+    if (const char *e = getenv("DLZ4_JD_UNIT_MIB")) unit_bytes = (uint32_t)std::max(1, atoi(e)) << 20;
+    const uint32_t per_unit = std::max<uint32_t>(1u, unit_bytes / B);
     const uint32_t nunits = (n + per_unit - 1) / per_unit;
     int rounds = 1;
-    while ((1ull << rounds) < (uint64_t)per_unit * B) ++rounds;          // chain depth <= unit bytes, halved per round
+    while ((1ull << (2 * rounds)) < (uint64_t)per_unit * B) ++rounds;    // chain depth <= unit bytes, quartered per round (kJdHops = 4)
+    ++rounds;
     size_t off = 0;
     auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_seq = carve((size_t)seq_base[n] * sizeof(JdSeq)), o_sb = carve((size_t)(n + 1) * 8), o_ns = carve((size_t)n * 4);
     const size_t o_reach = carve((size_t)n * 4), o_base = carve((size_t)(n + 1) * 8), o_P = carve((size_t)per_unit * B * 4);
     const size_t o_todo = carve((size_t)nunits * (rounds + 2) * 4);
+    const size_t ntiles = ((size_t)per_unit * B + kJdTile - 1) / kJdTile, o_tile = carve(ntiles);
+    // chunked (parallel) token scan for blocks > 64 KiB: per-byte next/advance, per-byte chunk exits, run and slow-token lists
+    const bool chunked = B > 65536 && !getenv("DLZ4_JD_SERIAL_SCAN");
+    uint64_t fspan = 0;
+    uint32_t max_slen = 0;
+    std::vector<uint64_t> list_base(n + 1, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        max_slen = std::max(max_slen, slen[i]);
+        list_base[i + 1] = list_base[i] + slen[i] / kJdpChunk + slen[i] / 64 + 8;
+    }
+    size_t o_nx = 0, o_adv = 0, o_ex = 0, o_lb = 0, o_runs = 0, o_slows = 0, o_nr = 0, o_nsl = 0, o_fb = 0;
+    if (chunked) {
+        fspan = frame_span;
+        o_nx = carve((size_t)fspan * 2); o_adv = carve((size_t)fspan * 2); o_ex = carve((size_t)fspan * sizeof(JdpExit));
+        o_lb = carve((size_t)(n + 1) * 8); o_runs = carve((size_t)list_base[n] * sizeof(JdpRun));
+        o_slows = carve((size_t)list_base[n] * sizeof(JdpSlow)); o_nr = carve((size_t)n * 4); o_nsl = carve((size_t)n * 4); o_fb = carve(n);
+    }
     CKS(reserve(ctx, ctx->aux, off));
     uint8_t *A = (uint8_t *)ctx->aux.p;
     JdSeq *d_seq = (JdSeq *)(A + o_seq);
     uint64_t *d_sb = (uint64_t *)(A + o_sb), *d_base = (uint64_t *)(A + o_base);
     uint32_t *d_ns = (uint32_t *)(A + o_ns), *d_reach = (uint32_t *)(A + o_reach), *d_todo = (uint32_t *)(A + o_todo);
     int32_t *d_P = (int32_t *)(A + o_P);
+    uint8_t *d_tile = A + o_tile;
     CK(cudaMemcpyAsync(d_sb, seq_base.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d_todo, 0, (size_t)nunits * (rounds + 2) * 4, st));
     CK(cudaMemsetAsync(d_reach, 0, (size_t)n * 4, st));
     CK(cudaMemsetAsync(ctx->d_counter, 0, 4, st));
-    k_jd_scan<<<(int)std::min<uint64_t>((n + 3) / 4, (uint64_t)ctx->sm_count * 8), 128, 0, st>>>(d_frame, d_soff, d_slen, d_stored, n, B, d_seq, d_sb, d_ns,
-                                                                                                 d_olen, d_reach, d_status, ctx->d_counter);
+    const int scan_grid = (int)std::min<uint64_t>((n + 3) / 4, (uint64_t)ctx->sm_count * 8);
+    if (chunked) {
+        uint16_t *d_nx = (uint16_t *)(A + o_nx), *d_adv = (uint16_t *)(A + o_adv);
+        JdpExit *d_ex = (JdpExit *)(A + o_ex);
+        uint64_t *d_lb = (uint64_t *)(A + o_lb);
+        JdpRun *d_runs = (JdpRun *)(A + o_runs);
+        JdpSlow *d_slows = (JdpSlow *)(A + o_slows);
+        uint32_t *d_nr = (uint32_t *)(A + o_nr), *d_nsl = (uint32_t *)(A + o_nsl);
+        uint8_t *d_fb = A + o_fb;
+        CK(cudaMemcpyAsync(d_lb, list_base.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        k_jdp_next<<<dim3((max_slen + 255) / 256, n), 256, 0, st>>>(d_frame, d_soff, d_slen, d_stored, d_nx, d_adv);
+        k_jdp_exit<<<dim3((max_slen + kJdpChunk - 1) / kJdpChunk, n), 256, 0, st>>>(d_soff, d_slen, d_stored, d_nx, d_adv, d_ex);
+        k_jdp_hop<<<(n + 7) / 8, 256, 0, st>>>(d_frame, d_soff, d_slen, d_stored, n, B, d_ex, d_runs, d_slows, d_lb, d_nr, d_nsl, d_ns, d_olen,
+                                                d_reach, d_status, d_fb);
+        k_jdp_emit<<<dim3(64, n), 256, 0, st>>>(d_frame, d_soff, d_slen, d_nx, d_adv, d_runs, d_slows, d_lb, d_nr, d_nsl, d_seq, d_sb, d_reach);
+        // blocks the chunked scan refused (malformed input, overflow): the serial scan decides their status
+        k_jd_scan<<<scan_grid, 128, 0, st>>>(d_frame, d_soff, d_slen, d_stored, n, B, d_seq, d_sb, d_ns, d_olen, d_reach, d_status,
+                                             ctx->d_counter, d_fb);
+        ctx->launches += 5;
+        if (getenv("DLZ4_DEBUG")) {
+            std::vector<uint32_t> nr(n), nsl(n); std::vector<uint8_t> fb(n);
+            CK(cudaMemcpyAsync(nr.data(), d_nr, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(nsl.data(), d_nsl, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(fb.data(), d_fb, n, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            uint64_t a = 0, b2 = 0, c = 0; uint32_t ma = 0, mb = 0;
+            for (uint32_t i = 0; i < n; ++i) { a += nr[i]; b2 += nsl[i]; c += fb[i]; ma = std::max(ma, nr[i]); mb = std::max(mb, nsl[i]); }
+            fprintf(stderr, "dlz4: chunked scan: %u blocks, runs %llu (max %u per block), slow tokens %llu (max %u), fallback blocks %llu\n", n,
+                    (unsigned long long)a, ma, (unsigned long long)b2, mb, (unsigned long long)c);
+        }
+    } else {
+        k_jd_scan<<<scan_grid, 128, 0, st>>>(d_frame, d_soff, d_slen, d_stored, n, B, d_seq, d_sb, d_ns, d_olen, d_reach, d_status,
+                                             ctx->d_counter, nullptr);
+        ctx->launches++;
+    }
     k_jd_bases<<<1, 32, 0, st>>>(d_olen, d_reach, n, dwin, linked ? 1 : 0, cap_total, d_base, d_status);
-    ctx->launches += 2;
+    ctx->launches++;
     CK(cudaGetLastError());
     status_h.assign(n, 0);
     CK(cudaMemcpyAsync(status_h.data(), d_status, n, cudaMemcpyDeviceToHost, st));
@@ -329,7 +383,8 @@ int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, const uint64_t *d_sof
         uint32_t *todo = d_todo + (size_t)u * (rounds + 2);
         const uint32_t cpb = std::max<uint32_t>(1u, 2048u / (b1 - b0));
         k_jd_fill<<<(b1 - b0) * cpb, 256, 0, st>>>(d_frame, d_soff, d_seq, d_sb, d_ns, d_base, b0, cpb, d_out, d_dict, dwin, linked ? 1 : 0, d_P, todo);
-        for (int r = 0; r < rounds; ++r) k_jd_round<<<wide, 256, 0, st>>>(d_P, d_base, b0, b1, todo + r, todo + r + 1);
+        CK(cudaMemsetAsync(d_tile, 1, ntiles, st));
+        for (int r = 0; r < rounds; ++r) k_jd_round<<<wide, 256, 0, st>>>(d_P, d_base, b0, b1, todo + r, todo + r + 1, d_tile);
         k_jd_emit<<<wide, 256, 0, st>>>(d_P, d_base, b0, b1, d_out);
         ctx->launches += 2 + rounds;
     }
@@ -1209,7 +1264,7 @@ int dlz4_frame_decompress(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_le
         const bool jump = frame_len >= ctx->jump_min_bytes && (!info.block_independence || (B > 65536 && n < 1024));
         if (jump) {
             // linked blocks (block k reads block k-1's output) or few large blocks: token scan + pointer doubling
-            CKS(decompress_jump(ctx, d_frame, d_soff, d_slen, d_stored, slen, n, B, d_out, cap_total, dwin ? d_dict : nullptr, (uint32_t)dwin,
+            CKS(decompress_jump(ctx, d_frame, fpad, d_soff, d_slen, d_stored, slen, n, B, d_out, cap_total, dwin ? d_dict : nullptr, (uint32_t)dwin,
                                 !info.block_independence, d_olen, d_status, status, &total, st));
             for (uint32_t i = 0; i < n && !first_status; ++i) first_status = status[i];
         } else if (!info.block_independence) {

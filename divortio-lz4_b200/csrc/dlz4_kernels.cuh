@@ -1186,13 +1186,14 @@ k_decompress_chain(const uint8_t *__restrict__ src, const uint64_t *__restrict__
 // stream or a copy of an EARLIER output byte, so decoding is pointer chasing and pointer chasing parallelises by doubling:
 //   k_jd_scan     one warp per block walks the tokens only (no copies) and writes one record per sequence;
 //   k_jd_bases    exclusive scan of the decoded block lengths, history / capacity checks in the reference's error order;
-//   per unit of <= 8 MiB of consecutive blocks (its 4-byte-per-byte pointer array stays in L2):
+//   per unit of <= 16 MiB of consecutive blocks (its 4-byte-per-byte pointer array stays in L2):
 //     k_jd_fill   P[x] = ~literal, or ~out[q] when the source q lies before the unit (already final), or q itself;
-//     k_jd_round  P[x] = P[P[x]] for unresolved x, repeated until none is left (chain depth halves per round);
+//     k_jd_round  P[x] = P[P[P[P[x]]]] for unresolved x, repeated until none is left (chain depth quarters per round);
 //     k_jd_emit   out[x] = ~P[x].
 // Units run in stream order, so a unit's sources in earlier units are final bytes.  Nothing here depends on how the
 // frame was parsed: the result is the byte-exact LZ4 decode whatever the dependency structure.
 struct JdSeq { uint32_t op, ip, lit, ml, off, pad0, pad1, pad2; };    // block-relative output / input positions
+constexpr int kJdHops = 4;                                             // pointer links followed per element per round
 constexpr uint32_t kJdChunk = 4096;                                    // long literal runs / matches are recorded in chunks
 
 __device__ __forceinline__ void jd_emit_rec(JdSeq *rec, uint32_t &ns, uint32_t op, uint32_t ip, uint32_t lit, uint32_t ml, uint32_t off,
@@ -1263,12 +1264,16 @@ __device__ __forceinline__ bool jd_scan_one(const uint8_t *__restrict__ in, uint
 __global__ void __launch_bounds__(128)
 k_jd_scan(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ src_len,
           const uint8_t *__restrict__ stored, uint32_t nblocks, uint32_t block_max, JdSeq *seqs, const uint64_t *__restrict__ seq_base,
-          uint32_t *nseq, uint32_t *out_len, uint32_t *reach, uint8_t *status, uint32_t *counter) {
+          uint32_t *nseq, uint32_t *out_len, uint32_t *reach, uint8_t *status, uint32_t *counter,
+          const uint8_t *__restrict__ only /* nullable: scan only blocks with only[b] != 0 (fallback of the chunked scan) */) {
     const uint32_t lane = lane_id();
     const uint32_t lt = (1u << lane) - 1u;
     for (;;) {
         const uint32_t b = next_block(counter, lane);
         if (b >= nblocks) break;
+        if (only && !only[b]) continue;
+        if (only && lane == 0) reach[b] = 0;
+        __syncwarp();
         const uint8_t *in = src + src_off[b];
         const uint32_t n = src_len[b];
         JdSeq *rec = seqs + seq_base[b];
@@ -1377,6 +1382,271 @@ k_jd_scan(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
     }
 }
 
+// ---- chunked token scan (blocks > 64 KiB): the token chain of ONE block in parallel.
+//   k_jdp_next   one thread per compressed byte i sizes the sequence that would start there: nx[i] = bytes to the next token
+//                (0: not sizeable here -- long length runs, the last sequence, anything malformed), adv[i] = lit + match length;
+//   k_jdp_exit   per 2048-byte chunk, pointer doubling in shared memory: from every i, where does the chain leave the chunk
+//                (or which unsizeable token stops it), how many tokens and output bytes on the way;
+//   k_jdp_hop    one thread per block hops chunk to chunk along the real chain (one 16-byte load per chunk), sizes the
+//                unsizeable tokens serially, and lists runs (entry, first record index, output offset) and slow tokens;
+//   k_jdp_emit   one warp per run walks its tokens (nx links, two shuffles per token) and writes the records; one warp per
+//                slow token writes its chunked records.
+// Anything irregular (malformed input, capacity overflow, list overflow) flags the block for the serial scan above, which
+// reproduces the reference's error order; the chunked scan only ever handles well-formed blocks.
+constexpr uint32_t kJdpChunk = 2048;
+constexpr uint32_t kJdpSlowBit = 0x80000000u;
+struct JdpExit { uint32_t ex, cnt, adv, pad; };                 // ex: position where the chain leaves the chunk | kJdpSlowBit
+struct JdpRun { uint32_t pos, ns, op, pad; };
+struct JdpSlow { uint32_t op, litp, lit, ml, off, ns, pad0, pad1; };
+
+__device__ __forceinline__ uint32_t jd_rec_count(uint32_t lit, uint32_t ml) {      // records jd_emit_rec writes
+    uint32_t c = 1;
+    if (lit > kJdChunk) c += (lit - 1) / kJdChunk;
+    if (ml > kJdChunk) c += (ml - 1) / kJdChunk;
+    return c;
+}
+
+__global__ void __launch_bounds__(256)
+k_jdp_next(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ src_len,
+           const uint8_t *__restrict__ stored, uint16_t *nx, uint16_t *adv) {
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = src_len[b];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || stored[b]) return;
+    const uint64_t g = src_off[b];
+    const uint8_t *in = src + g;
+    const uint32_t token = in[i];
+    uint32_t p = i + 1, lit = token >> 4, ml = 0;
+    bool ok = true;
+    if (lit == 15u) {
+        uint32_t v = 255u;
+        for (int k = 0; k < 16 && v == 255u; ++k) {
+            if (p >= n) { ok = false; v = 0; break; }
+            v = in[p++]; lit += v;
+        }
+        if (v == 255u) ok = false;
+    }
+    const uint64_t endlit = (uint64_t)p + lit;
+    if (ok && endlit + 2 <= n) {                                 // endlit >= n: last sequence or malformed -> serial
+        const uint32_t offset = (uint32_t)in[endlit] | ((uint32_t)in[endlit + 1] << 8);
+        p = (uint32_t)endlit + 2;
+        ml = token & 15u;
+        if (offset == 0) ok = false;
+        else if (ml == 15u) {
+            uint32_t v = 255u;
+            for (int k = 0; k < 16 && v == 255u; ++k) {
+                if (p >= n) { ok = false; v = 0; break; }
+                v = in[p++]; ml += v;
+            }
+            if (v == 255u) ok = false;
+        }
+        ml += 4;
+    } else ok = false;
+    if (lit > kJdChunk || ml > kJdChunk || p - i > 0xFFFFu) ok = false;
+    nx[g + i] = ok ? (uint16_t)(p - i) : (uint16_t)0;
+    adv[g + i] = ok ? (uint16_t)(lit + ml) : (uint16_t)0;
+}
+
+__global__ void __launch_bounds__(256)
+k_jdp_exit(const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ src_len, const uint8_t *__restrict__ stored,
+           const uint16_t *__restrict__ nx, const uint16_t *__restrict__ adv, JdpExit *exits) {
+    __shared__ uint16_t tgt[kJdpChunk];
+    __shared__ uint32_t ex[kJdpChunk], cn[kJdpChunk], av[kJdpChunk];
+    const uint32_t b = blockIdx.y, n = src_len[b];
+    const uint32_t c0 = blockIdx.x * kJdpChunk;
+    if (c0 >= n || stored[b]) return;
+    const uint64_t g = src_off[b];
+    const uint32_t cend = c0 + kJdpChunk < n ? c0 + kJdpChunk : n;
+    constexpr int PER = kJdpChunk / 256;
+    for (int k = 0; k < PER; ++k) {
+        const uint32_t i = threadIdx.x + k * 256, a = c0 + i;
+        uint16_t t = 0xFFFFu; uint32_t e = 0, c = 0, v = 0;
+        if (a < cend) {
+            const uint32_t j = nx[g + a];
+            if (j == 0) e = a | kJdpSlowBit;
+            else {
+                c = 1; v = adv[g + a];
+                if (a + j >= cend) e = a + j; else t = (uint16_t)(i + j);
+            }
+        }
+        tgt[i] = t; ex[i] = e; cn[i] = c; av[i] = v;
+    }
+    __syncthreads();
+    for (int round = 0; round < 11; ++round) {                   // a hop is >= 3 bytes: <= 683 hops per chunk
+        uint16_t t2[PER]; uint32_t e2[PER], c2[PER], v2[PER];
+        for (int k = 0; k < PER; ++k) {
+            const uint32_t i = threadIdx.x + k * 256;
+            const uint16_t t = tgt[i];
+            t2[k] = t; e2[k] = ex[i]; c2[k] = cn[i]; v2[k] = av[i];
+            if (t != 0xFFFFu) { t2[k] = tgt[t]; e2[k] = ex[t]; c2[k] += cn[t]; v2[k] += av[t]; }
+        }
+        __syncthreads();
+        for (int k = 0; k < PER; ++k) {
+            const uint32_t i = threadIdx.x + k * 256;
+            tgt[i] = t2[k]; ex[i] = e2[k]; cn[i] = c2[k]; av[i] = v2[k];
+        }
+        __syncthreads();
+    }
+    for (int k = 0; k < PER; ++k) {
+        const uint32_t i = threadIdx.x + k * 256, a = c0 + i;
+        if (a < cend) exits[g + a] = JdpExit{ex[i], cn[i], av[i], 0u};
+    }
+}
+
+// Sum of a length run (bytes of 255 closed by one smaller byte), 32 bytes per step.  Returns false when the input ends first.
+__device__ __forceinline__ bool jd_length_run(const uint8_t *__restrict__ in, uint32_t &ip, uint32_t n, uint32_t &acc, uint32_t lane) {
+    for (;;) {
+        const uint32_t q = ip + lane;
+        const uint32_t v = q < n ? (uint32_t)in[q] : 0x100u;
+        const uint32_t stop = __ballot_sync(FULL, v != 255u);
+        if (!stop) { acc += 255u * 32u; ip += 32u; continue; }
+        const int l = __ffs(stop) - 1;
+        const uint32_t vv = __shfl_sync(FULL, v, l);
+        if (vv == 0x100u) return false;
+        acc += 255u * (uint32_t)l + vv;
+        ip += (uint32_t)l + 1u;
+        return true;
+    }
+}
+
+// One warp per block (uniform control flow; lane 0 writes).
+__global__ void __launch_bounds__(256)
+k_jdp_hop(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ src_len,
+          const uint8_t *__restrict__ stored, uint32_t nblocks, uint32_t block_max, const JdpExit *__restrict__ exits,
+          JdpRun *runs, JdpSlow *slows, const uint64_t *__restrict__ list_base, uint32_t *nruns, uint32_t *nslow,
+          uint32_t *nseq, uint32_t *out_len, uint32_t *reach, uint8_t *status, uint8_t *fallback) {
+    const uint32_t lane = lane_id();
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= nblocks) return;
+    const uint32_t n = src_len[b];
+    const uint64_t g = src_off[b];
+    const uint8_t *in = src + g;
+    JdpRun *R = runs + list_base[b];
+    JdpSlow *S = slows + list_base[b];
+    const uint32_t cap = (uint32_t)(list_base[b + 1] - list_base[b]);
+    uint32_t nr = 0, nsl = 0, ns = 0, pos = 0, rch = 0;
+    uint64_t op = 0;
+    bool fb = false;
+    if (stored[b]) {
+        if (lane == 0) S[0] = JdpSlow{0u, 0u, n, 0u, 0u, 0u, 0u, 0u};
+        nsl = 1;
+        ns = jd_rec_count(n, 0); op = n;
+        if (n > block_max) fb = true;
+    } else {
+        while (pos < n) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(exits + g + pos));
+            const JdpExit E{raw.x, raw.y, raw.z, 0u};
+            if (E.cnt) {
+                if (nr >= cap) { fb = true; break; }
+                if (lane == 0) R[nr] = JdpRun{pos, ns, (uint32_t)op, 0u};
+                ++nr;
+                ns += E.cnt; op += E.adv;
+                if (op > block_max) { fb = true; break; }
+            }
+            if (!(E.ex & kJdpSlowBit)) { pos = E.ex; continue; }
+            // a token the per-byte pass could not size: serial form (any error -> the serial scan decides the status)
+            uint32_t ip = E.ex & ~kJdpSlowBit;
+            const uint32_t token = in[ip++];
+            uint32_t lit = token >> 4;
+            if (lit == 15u && !jd_length_run(in, ip, n, lit, lane)) { fb = true; break; }
+            if (op + lit > block_max || (uint64_t)ip + lit > n) { fb = true; break; }
+            const uint32_t litp = ip;
+            ip += lit;
+            uint32_t ml = 0, offset = 0;
+            const bool last = ip >= n;
+            if (!last) {
+                if (ip + 2 > n) { fb = true; break; }
+                offset = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8);
+                ip += 2;
+                if (offset == 0) { fb = true; break; }
+                ml = token & 15u;
+                if (ml == 15u && !jd_length_run(in, ip, n, ml, lane)) { fb = true; break; }
+                ml += 4;
+                if (op + lit + ml > block_max) { fb = true; break; }
+                const int64_t src_rel = (int64_t)op + lit - offset;
+                if (src_rel < 0 && (uint32_t)(-src_rel) > rch) rch = (uint32_t)(-src_rel);
+            }
+            if (nsl >= cap) { fb = true; break; }
+            if (lane == 0) S[nsl] = JdpSlow{(uint32_t)op, litp, lit, ml, offset, ns, 0u, 0u};
+            ++nsl;
+            ns += jd_rec_count(lit, ml);
+            op += lit + ml;
+            if (last) break;
+            pos = ip;
+        }
+    }
+    if (lane == 0) {
+        nruns[b] = fb ? 0u : nr; nslow[b] = fb ? 0u : nsl;
+        nseq[b] = ns; out_len[b] = (uint32_t)op; reach[b] = rch; status[b] = ST_OK; fallback[b] = fb ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_jdp_emit(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ src_len,
+           const uint16_t *__restrict__ nx, const uint16_t *__restrict__ adv, const JdpRun *__restrict__ runs,
+           const JdpSlow *__restrict__ slows, const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ nruns,
+           const uint32_t *__restrict__ nslow, JdSeq *seqs, const uint64_t *__restrict__ seq_base, uint32_t *reach) {
+    const uint32_t lane = lane_id(), b = blockIdx.y;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+    const uint32_t n = src_len[b];
+    const uint64_t g = src_off[b];
+    const uint8_t *in = src + g;
+    JdSeq *rec = seqs + seq_base[b];
+    const uint32_t nr = nruns[b], nsl = nslow[b];
+    uint32_t rch = 0;
+    for (uint32_t w = gw; w < nr + nsl; w += nw) {
+        if (w >= nr) {                                           // slow token: chunked records
+            const JdpSlow q = slows[list_base[b] + (w - nr)];
+            uint32_t ns = q.ns;
+            jd_emit_rec(rec, ns, q.op, q.litp, q.lit, q.ml, q.off, lane);
+            continue;
+        }
+        const JdpRun r = runs[list_base[b] + w];
+        const uint32_t cend = ((r.pos / kJdpChunk) + 1) * kJdpChunk < n ? ((r.pos / kJdpChunk) + 1) * kJdpChunk : n;
+        uint32_t ip = r.pos, ns = r.ns, op = r.op;
+        bool done = false;
+        while (!done) {
+            const uint32_t q = ip + lane;
+            const uint32_t j = q < cend ? (uint32_t)nx[g + q] : 0u;     // 0 also behind the chunk: the run ends there
+            const uint32_t a = q < cend ? (uint32_t)adv[g + q] : 0u;
+            uint32_t cur = 0, real = 0, myop = 0, opw = op, last_hop = 0;
+            while (cur < 32u) {
+                const uint32_t jj = __shfl_sync(FULL, j, cur);
+                if (jj == 0) { done = true; break; }             // unsizeable token or end of the chunk: k_jdp_hop continues
+                real |= 1u << cur;
+                if (lane == cur) myop = opw;
+                opw += __shfl_sync(FULL, a, cur);
+                last_hop = cur + jj;
+                cur = last_hop;
+            }
+            if ((real >> lane) & 1u) {                           // visited lanes = real tokens: parse and write the record
+                const uint32_t token = in[q];
+                uint32_t p = q + 1, lit = token >> 4;
+                if (lit == 15u) { uint32_t v; do { v = in[p++]; lit += v; } while (v == 255u); }
+                const uint32_t litp = p;
+                p += lit;
+                const uint32_t offset = (uint32_t)in[p] | ((uint32_t)in[p + 1] << 8);
+                p += 2;
+                uint32_t ml = token & 15u;
+                if (ml == 15u) { uint32_t v; do { v = in[p++]; ml += v; } while (v == 255u); }
+                ml += 4;
+                rec[ns + __popc(real & lt)] = JdSeq{myop, litp, lit, ml, offset, 0u, 0u, 0u};
+                const int64_t src_rel = (int64_t)myop + lit - offset;
+                if (src_rel < 0 && (uint32_t)(-src_rel) > rch) rch = (uint32_t)(-src_rel);
+            }
+            ns += __popc(real);
+            op = opw;
+            if (!done) {
+                ip += last_hop;
+                if (ip >= cend) done = true;
+            }
+        }
+    }
+    rch = __reduce_max_sync(FULL, rch);
+    if (lane == 0 && rch) atomicMax(&reach[b], rch);
+}
+
 // base[b] = decoded bytes before block b (base[nblocks] = total); a block that reads further back than its history
 // (dictionary, plus the earlier output when linked) gets the reference's "Dictionary Offset Out of Bounds" (:150-152).
 __global__ void __launch_bounds__(32)
@@ -1438,21 +1708,40 @@ k_jd_fill(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
     if (lane == 0 && pending) atomicAdd(unresolved, pending);
 }
 
+// Tiles of 4096 elements that had nothing unresolved in the previous round are skipped (tile_todo, reset to 1 per unit).
+constexpr uint32_t kJdTile = 4096;
 __global__ void __launch_bounds__(256)
-k_jd_round(int32_t *P, const uint64_t *__restrict__ base, uint32_t b0, uint32_t b1, const uint32_t *todo, uint32_t *next_todo) {
+k_jd_round(int32_t *P, const uint64_t *__restrict__ base, uint32_t b0, uint32_t b1, const uint32_t *todo, uint32_t *next_todo,
+           uint8_t *tile_todo) {
     if (*todo == 0) return;                                      // everything resolved in an earlier round
     const uint64_t len = base[b1] - base[b0];
-    uint32_t pending = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
-        const int32_t v = P[i];
-        if (v >= 0) {
-            const int32_t w = P[v];                              // v < i: an earlier byte of the unit
-            P[i] = w;
-            pending += w >= 0;
+    const uint32_t ntiles = (uint32_t)((len + kJdTile - 1) / kJdTile);
+    uint32_t pending_total = 0;
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        if (!tile_todo[t]) continue;                             // uniform per CTA
+        uint32_t pending = 0;
+        const uint64_t t0 = (uint64_t)t * kJdTile;
+#pragma unroll 4
+        for (uint32_t k = threadIdx.x; k < kJdTile; k += 256) {
+            const uint64_t i = t0 + k;
+            if (i >= len) break;
+            int32_t v = P[i];
+            if (v >= 0) {
+                // up to kJdHops links per round (v < i: an earlier byte of the unit).  Every link read spans >= 4^round original
+                // hops, whether it is this round's value or the last one's, so log4(unit bytes) rounds resolve any chain.
+#pragma unroll
+                for (int h = 0; h < kJdHops && v >= 0; ++h) v = P[v];
+                P[i] = v;
+                pending += v >= 0;
+            }
         }
+        const int any = __syncthreads_or((int)pending);
+        if (threadIdx.x == 0) tile_todo[t] = any ? 1 : 0;
+        pending_total += pending;
+        __syncthreads();
     }
-    pending = __reduce_add_sync(FULL, pending);
-    if (lane_id() == 0 && pending) atomicAdd(next_todo, pending);
+    pending_total = __reduce_add_sync(FULL, pending_total);
+    if (lane_id() == 0 && pending_total) atomicAdd(next_todo, pending_total);
 }
 
 __global__ void __launch_bounds__(256)

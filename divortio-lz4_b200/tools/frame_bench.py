@@ -1,6 +1,6 @@
 """Frame API (compressBuffer / decompressBuffer) through the C ABI with pinned host buffers: wall time of the call, device
 time of its kernel section, segment statistics of the segment-parallel engine, and the CPU oracle (one thread) beside it.
-Usage: python divortio-lz4_b200/tools/frame_bench.py [kind=log|mixed] [MiB] [--no-cpu]"""
+Usage: python divortio-lz4_b200/tools/frame_bench.py [kind=log|mixed] [MiB] [--no-cpu] [--only=CASE] [--once]"""
 import ctypes as C
 import os
 import sys
@@ -16,6 +16,8 @@ from divortio_lz4_b200.api import FrameInfo, FrameOpts  # noqa: E402
 kind = sys.argv[1] if len(sys.argv) > 1 else "log"
 mib = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 cpu = "--no-cpu" not in sys.argv
+only = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--only=")]
+reps = 1 if "--once" in sys.argv else 3
 n = mib << 20
 ctx = dl.Context(0)
 L = dl.lib()
@@ -32,13 +34,16 @@ cap = int(L.dlz4_frame_bound(n))
 p_f, h_f = pinned(cap)
 p_o, h_o = pinned(n)
 print("%s %d MiB, pinned host buffers; GB/s of uncompressed bytes" % (kind, mib))
-for bs, indep, cc, bc in ((4194304, False, False, False), (4194304, True, False, False), (65536, False, False, False),
-                          (65536, True, False, False), (4194304, True, True, True), (4194304, False, True, False)):
+cases = ((4194304, False, False, False), (4194304, True, False, False), (65536, False, False, False),
+         (65536, True, False, False), (4194304, True, True, True), (4194304, False, True, False))
+for ci, (bs, indep, cc, bc) in enumerate(cases):
+    if only and ci not in only:
+        continue
     opts = FrameOpts(bs, int(indep), int(cc), 1, int(bc))
     flen = C.c_uint64(0)
     best_c = best_d = 1e9
     kc = kd = 0.0
-    for rep in range(3):
+    for rep in range(reps):
         t0 = time.perf_counter()
         ctx.check(L.dlz4_frame_compress(ctx.handle, p_in, n, None, 0, C.byref(opts), p_f, cap, C.byref(flen)))
         t1 = time.perf_counter()
