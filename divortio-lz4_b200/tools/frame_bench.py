@@ -1,6 +1,7 @@
 """Frame API (compressBuffer / decompressBuffer) through the C ABI with pinned host buffers: wall time of the call, device
-time of its kernel section, segment statistics of the segment-parallel engine, and the CPU oracle (one thread) beside it.
-Usage: python divortio-lz4_b200/tools/frame_bench.py [kind=log|mixed] [MiB] [--no-cpu] [--only=CASE] [--once]"""
+time of its kernel section and the segment statistics of the segment-parallel engine.  (The CPU baseline lives in bench.py;
+product tools never touch oracle/.)
+Usage: python divortio-lz4_b200/tools/frame_bench.py [kind=log|mixed] [MiB] [--only=CASE] [--once]"""
 import ctypes as C
 import os
 import sys
@@ -15,7 +16,6 @@ from divortio_lz4_b200.api import FrameInfo, FrameOpts  # noqa: E402
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "log"
 mib = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-cpu = "--no-cpu" not in sys.argv
 only = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--only=")]
 reps = 1 if "--once" in sys.argv else 3
 n = mib << 20
@@ -61,13 +61,4 @@ for ci, (bs, indep, cc, bc) in enumerate(cases):
             " | decompress %6.2f GB/s (call %6.1f ms, kernels %6.1f ms)" %
             (bs, "independent" if indep else "linked", cc, bc, n / flen.value, n / best_c / 1e9, best_c * 1e3, kc, stats[0], stats[1], stats[2],
              n / best_d / 1e9, best_d * 1e3, kd))
-    if cpu:
-        import oracle
-        sub = h_in[:min(n, 64 << 20)]
-        t0 = time.perf_counter()
-        f = oracle.compress_buffer(sub, None, bs, indep, cc, True, None, bc)
-        t1 = time.perf_counter()
-        oracle.decompress_buffer(f)
-        t2 = time.perf_counter()
-        line += " | CPU oracle 1 thread: compress %.2f, decompress %.2f GB/s" % (sub.size / (t1 - t0) / 1e9, sub.size / (t2 - t1) / 1e9)
     print(line, flush=True)
