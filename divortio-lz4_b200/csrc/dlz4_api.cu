@@ -277,8 +277,10 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
             ctx->seg_rounds++;
         }
     }
-    k_seg_assemble<<<(int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(d_buf, bstride, d_sf, d_sc, d_poff, d_plen, n, d_comp,
-                                                                                             d_coff, d_clen);
+    {
+        const uint32_t gx = (uint32_t)std::min<uint64_t>(n, 65535), gy = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(64, (uint64_t)ctx->sm_count * 8 / gx));
+        k_seg_assemble<<<dim3(gx, gy), 256, 0, st>>>(d_buf, bstride, d_sf, d_sc, d_poff, d_plen, n, d_comp, d_coff, d_clen);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     return DLZ4_OK;
@@ -290,7 +292,7 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
 int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, uint64_t frame_span, const uint64_t *d_soff, const uint32_t *d_slen, const uint8_t *d_stored,
                     const std::vector<uint32_t> &slen, uint32_t n, uint32_t B, uint8_t *d_out, uint64_t cap_total, const uint8_t *d_dict,
                     uint32_t dwin, bool linked, uint32_t *d_olen, uint8_t *d_status, std::vector<uint8_t> &status_h, uint64_t *total,
-                    cudaStream_t st) {
+                    cudaStream_t st, uint8_t *host_out, uint64_t host_cap, bool *copied_out) {
     std::vector<uint64_t> seq_base(n + 1, 0);
     for (uint32_t i = 0; i < n; ++i) seq_base[i + 1] = seq_base[i] + slen[i] / 3 + B / 2048 + 8;
     uint32_t unit_bytes = 16u << 20;
@@ -372,11 +374,16 @@ int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, uint64_t frame_span, 
     ctx->launches++;
     CK(cudaGetLastError());
     status_h.assign(n, 0);
+    std::vector<uint64_t> base_h(n + 1);
     CK(cudaMemcpyAsync(status_h.data(), d_status, n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(total, d_base + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(base_h.data(), d_base, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    *total = base_h[n];
     for (uint32_t i = 0; i < n; ++i)
         if (status_h[i]) return DLZ4_OK;                                  // the caller maps the first status to the error
+    // a unit's bytes are final once its k_jd_emit ran: ship them while the later units resolve
+    const bool ship = host_out && *total <= host_cap && nunits <= 128;
+    if (copied_out) *copied_out = ship;
     const int wide = ctx->sm_count * 8;
     for (uint32_t u = 0; u < nunits; ++u) {
         const uint32_t b0 = u * per_unit, b1 = std::min<uint32_t>(n, b0 + per_unit);
@@ -387,7 +394,13 @@ int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, uint64_t frame_span, 
         for (int r = 0; r < rounds; ++r) k_jd_round<<<wide, 256, 0, st>>>(d_P, d_base, b0, b1, todo + r, todo + r + 1, d_tile);
         k_jd_emit<<<wide, 256, 0, st>>>(d_P, d_base, b0, b1, d_out);
         ctx->launches += 2 + rounds;
+        if (ship && base_h[b1] > base_h[b0]) {
+            CK(cudaEventRecord(ctx->evp[u], st));
+            CK(cudaStreamWaitEvent(ctx->copy_out, ctx->evp[u], 0));
+            CK(cudaMemcpyAsync(host_out + base_h[b0], d_out + base_h[b0], base_h[b1] - base_h[b0], cudaMemcpyDeviceToHost, ctx->copy_out));
+        }
     }
+
     CK(cudaGetLastError());
     return DLZ4_OK;
 }
@@ -1260,12 +1273,13 @@ int dlz4_frame_decompress(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_le
     CK(cudaEventRecord(ctx->ev0, st));
     uint64_t total = 0;
     int first_status = 0;
+    bool shipped = false;                                                // the jump decoder copies finished units out as it goes
     if (n) {
         const bool jump = frame_len >= ctx->jump_min_bytes && (!info.block_independence || (B > 65536 && n < 1024));
         if (jump) {
             // linked blocks (block k reads block k-1's output) or few large blocks: token scan + pointer doubling
             CKS(decompress_jump(ctx, d_frame, fpad, d_soff, d_slen, d_stored, slen, n, B, d_out, cap_total, dwin ? d_dict : nullptr, (uint32_t)dwin,
-                                !info.block_independence, d_olen, d_status, status, &total, st));
+                                !info.block_independence, d_olen, d_status, status, &total, st, output, output_cap, &shipped));
             for (uint32_t i = 0; i < n && !first_status; ++i) first_status = status[i];
         } else if (!info.block_independence) {
             // short linked frame: serial chain (one warp)
@@ -1315,6 +1329,7 @@ int dlz4_frame_decompress(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_le
         }
     }
     CK(cudaEventRecord(ctx->ev1, st));
+    if (shipped) CK(cudaStreamSynchronize(ctx->copy_out));               // no copy into the caller's buffer survives this call
     if (first_status) { CK(cudaStreamSynchronize(st)); return first_status; }
 
     if ((flags & 2u) && info.has_block_checksum) {
@@ -1332,7 +1347,7 @@ int dlz4_frame_decompress(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_le
     }
     *output_len = total;
     if (total > output_cap) return DLZ4_E_OUTPUT_TOO_SMALL;
-    if (total) CK(cudaMemcpyAsync(output, d_out, total, cudaMemcpyDeviceToHost, st));
+    if (total && !shipped) CK(cudaMemcpyAsync(output, d_out, total, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     return DLZ4_OK;

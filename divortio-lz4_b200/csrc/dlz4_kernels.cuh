@@ -882,10 +882,12 @@ k_seg_verify(const SegJob *__restrict__ jobs, uint32_t njobs, const int32_t *__r
 }
 
 // Concatenates the pieces of every block (slots [slot_first[b], +slot_count[b]), in order) into dst + dst_off[b].
+// gridDim.y CTAs share a block: CTA y copies the 4 KiB stripes y, y + gridDim.y, ... of the block's compressed stream.
 __global__ void __launch_bounds__(256)
 k_seg_assemble(const uint8_t *__restrict__ blockbuf, uint64_t blockbuf_stride, const uint32_t *__restrict__ slot_first,
                const uint32_t *__restrict__ slot_count, const uint32_t *__restrict__ piece_off, const uint32_t *__restrict__ piece_len,
                uint32_t nblocks, uint8_t *__restrict__ dst, const uint64_t *__restrict__ dst_off, uint32_t *__restrict__ comp_len) {
+    constexpr uint32_t kStripe = 4096;
     for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
         const uint8_t *src = blockbuf + (uint64_t)b * blockbuf_stride;
         uint8_t *d = dst + dst_off[b];
@@ -893,10 +895,15 @@ k_seg_assemble(const uint8_t *__restrict__ blockbuf, uint64_t blockbuf_stride, c
         for (uint32_t k = 0; k < slot_count[b]; ++k) {
             const uint32_t sl = slot_first[b] + k, n = piece_len[sl];
             const uint8_t *s = src + piece_off[sl];
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) d[pos + i] = s[i];
+            // stripes are counted along the assembled stream so that the CTAs of a block stay balanced
+            for (uint32_t st0 = ((pos / kStripe + gridDim.y - 1 - blockIdx.y) / gridDim.y * gridDim.y + blockIdx.y) * kStripe; st0 < pos + n;
+                 st0 += gridDim.y * kStripe) {
+                const uint32_t lo = st0 > pos ? st0 : pos, hi = st0 + kStripe < pos + n ? st0 + kStripe : pos + n;
+                for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) d[i] = s[i - pos];
+            }
             pos += n;
         }
-        if (threadIdx.x == 0) comp_len[b] = pos;
+        if (threadIdx.x == 0 && blockIdx.y == 0) comp_len[b] = pos;
     }
 }
 
