@@ -1033,94 +1033,202 @@ __device__ uint32_t decompress_block_warp(const uint8_t *__restrict__ in, const 
     return (uint32_t)(op - out_pos);
 }
 
-// decompressBlock, leaner formulation (the one the kernels use): 32-bit indices relative to the block's own output
-// start `ob`, `hist` = bytes of earlier output directly before `ob` that may serve as history (frame mode; at most
-// 65536 matter because offsets are 16-bit), and literals + match of a sequence written in ONE merged pass whenever the
-// match source lies entirely before the bytes of that pass (offset >= min(lit + matchLen, 32), the common case on text):
-// lane j < lit takes in[...], lane j >= lit takes out[... - offset]; 32 bytes per round, coalesced.
-// Error checks happen in the reference's order (blockDecompress.js:74,75,128,151) so the first error reported is the same.
+// One sequence at in[ip], uniform across the warp (the loop body of blockDecompress.js:55-271).  Returns false when the block
+// ends here (last sequence or error, `st` set).
+__device__ __forceinline__ bool dec_one_sequence(const uint8_t *__restrict__ in, const uint32_t n, uint8_t *const ob, const uint32_t cap,
+                                                 const uint32_t hist, const uint8_t *__restrict__ dict, const uint32_t dict_len,
+                                                 uint32_t &ip, uint32_t &op, uint32_t &st, const uint32_t lane) {
+    const uint32_t token = in[ip++];                             // :58
+    uint32_t lit = token >> 4;                                   // :61
+    if (lit == 15u) {                                            // :62-68
+        uint32_t b;
+        do {
+            if (ip >= n) { st = ST_MALFORMED; return false; }
+            b = in[ip++]; lit += b;
+        } while (b == 255u);
+    }
+    if ((uint64_t)op + lit > cap) { st = ST_OUTPUT_TOO_SMALL; return false; }      // :74
+    if ((uint64_t)ip + lit > n) { st = ST_MALFORMED; return false; }              // :75
+    const uint32_t litp = ip;
+    ip += lit;
+    if (ip >= n) {                                               // :123 last sequence: literals only
+        if (lit) warp_copy(ob + op, in + litp, lit, lane);
+        op += lit;
+        return false;
+    }
+    if (ip + 2 > n) { if (lit) warp_copy(ob + op, in + litp, lit, lane); st = ST_MALFORMED; return false; }
+    const uint32_t offset = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8);   // :126
+    ip += 2;
+    if (offset == 0) { st = ST_OFFSET_ZERO; return false; }      // :128
+    uint32_t ml = token & 15u;                                   // :131
+    if (ml == 15u) {                                             // :132-138
+        uint32_t b;
+        do {
+            if (ip >= n) { st = ST_MALFORMED; return false; }
+            b = in[ip++]; ml += b;
+        } while (b == 255u);
+    }
+    ml += 4;                                                     // :139
+    const int64_t src_rel = (int64_t)op + lit - offset;          // :142, relative to ob
+    if (src_rel < -(int64_t)hist) {
+        // :145-200 the match starts in the dictionary (ob - hist is output index 0)
+        if (lit) warp_copy(ob + op, in + litp, lit, lane);
+        op += lit;
+        const int64_t cs = src_rel + hist;                       // < 0
+        int64_t from_dict = -cs;
+        if (from_dict > ml) from_dict = ml;
+        const int64_t di = (int64_t)dict_len + cs;
+        if (di < 0 || di + from_dict > dict_len) { st = ST_DICT_OOB; return false; }   // :150-152
+        if ((uint64_t)op + ml > cap) { st = ST_OUTPUT_TOO_SMALL; return false; }
+        warp_copy(ob + op, dict + di, (uint32_t)from_dict, lane);
+        op += (uint32_t)from_dict;
+        const uint32_t rem = ml - (uint32_t)from_dict;
+        __syncwarp();
+        if (rem) warp_match_copy(ob + op, offset, rem, lane);
+        op += rem;
+        __syncwarp();
+        return true;
+    }
+    const uint32_t total = lit + ml;
+    if ((uint64_t)op + total > cap) {                            // literals fit (checked above), the match does not
+        st = ST_OUTPUT_TOO_SMALL;
+        return false;
+    }
+    if (offset >= (total < 32u ? total : 32u)) {
+        // merged pass: every source byte of a round was written before that round
+        uint8_t *const d = ob + op;
+        const uint8_t *const ls = in + litp;
+        const uint8_t *const ms = d - offset;                    // ms[j] is the match source of output byte j (j >= lit)
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t j = base + lane;
+            if (j < total) d[j] = j < lit ? ls[j] : ms[j];
+            __syncwarp();
+        }
+    } else {
+        if (lit) warp_copy(ob + op, in + litp, lit, lane);
+        __syncwarp();
+        warp_match_copy(ob + op + lit, offset, ml, lane);
+        __syncwarp();
+    }
+    op += total;
+    return true;
+}
+
+// decompressBlock, the formulation the kernels use: 32-bit indices relative to the block's own output start `ob`, `hist` =
+// bytes of earlier output directly before `ob` that may serve as history (frame mode; at most 65536 matter because offsets are
+// 16-bit), literals + match of a sequence written in ONE merged pass whenever the match source lies entirely before the bytes
+// of that pass (offset >= min(lit + matchLen, 32), the common case on text).
+// The token chain is serial (a token's position follows from the previous sequence's lengths): three dependent loads per
+// sequence.  So the warp speculates: lane l sizes the sequence that WOULD start at byte ip + l of the window, the warp hops from
+// lane 0 along the `next` links (two shuffles per real token) and the visited lanes -- the real tokens -- check themselves in
+// the reference's order (:74, :75, :128, ...).  Their copies then run in order, one sequence per step.  Tokens the window
+// cannot size (length runs of more than 3 bytes, dictionary sources, anything malformed) take dec_one_sequence, which is also
+// what decides every error, so the first error reported is the reference's.
 __device__ uint32_t decompress_block_warp_v2(const uint8_t *__restrict__ in, const uint32_t n, uint8_t *const ob,
                                              const uint32_t cap, const uint32_t hist, const uint8_t *__restrict__ dict,
                                              const uint32_t dict_len, uint32_t *status) {
     const uint32_t lane = lane_id();
     uint32_t ip = 0, op = 0;
     uint32_t st = ST_OK;
-    while (ip < n) {                                             // :55
-        const uint32_t token = in[ip++];                         // :58
-        uint32_t lit = token >> 4;                               // :61
-        if (lit == 15u) {                                        // :62-68
-            uint32_t b;
-            do {
-                if (ip >= n) { st = ST_MALFORMED; break; }
-                b = in[ip++]; lit += b;
-            } while (b == 255u);
-            if (st) break;
+    while (ip < n) {
+        // ---- every lane sizes "its" sequence
+        const uint32_t q = ip + lane;
+        uint32_t lit = 0, ml = 0, offset = 1, litp = 0, nxt = 1;
+        bool stop = true, last = false;                          // stop: the serial form decides (or the block ends)
+        if (q < n) {
+            const uint32_t token = in[q];
+            uint32_t p = q + 1;
+            lit = token >> 4;
+            bool ok = true;
+            if (lit == 15u) {                                    // at most 3 length bytes speculatively
+                uint32_t v = 255u;
+                for (int k = 0; k < 3 && v == 255u; ++k) {
+                    if (p >= n) { ok = false; v = 0; break; }
+                    v = in[p++]; lit += v;
+                }
+                if (v == 255u) ok = false;
+            }
+            litp = p;
+            const uint64_t endlit = (uint64_t)p + lit;
+            if (ok && endlit + 2 <= n) {
+                offset = (uint32_t)in[endlit] | ((uint32_t)in[endlit + 1] << 8);
+                p = (uint32_t)endlit + 2;
+                ml = token & 15u;
+                if (offset == 0) ok = false;
+                else if (ml == 15u) {
+                    uint32_t v = 255u;
+                    for (int k = 0; k < 3 && v == 255u; ++k) {
+                        if (p >= n) { ok = false; v = 0; break; }
+                        v = in[p++]; ml += v;
+                    }
+                    if (v == 255u) ok = false;
+                }
+                ml += 4;
+                nxt = p - ip;
+            } else ok = false;                                   // last sequence, or malformed: serial form
+            stop = !ok;
         }
-        if ((uint64_t)op + lit > cap) { st = ST_OUTPUT_TOO_SMALL; break; }      // :74
-        if ((uint64_t)ip + lit > n) { st = ST_MALFORMED; break; }              // :75
-        const uint32_t litp = ip;
-        ip += lit;
-        if (ip >= n) {                                           // :123 last sequence: literals only
-            if (lit) warp_copy(ob + op, in + litp, lit, lane);
-            op += lit;
-            break;
+        // ---- hop along the real tokens
+        uint32_t cur = 0, real = 0, myop = 0, opw = op;
+        const uint32_t adv = lit + ml;
+        const uint32_t stopper = __ballot_sync(FULL, stop);
+        while (cur < 32u) {
+            if ((stopper >> cur) & 1u) break;
+            real |= 1u << cur;
+            if (lane == cur) myop = opw;
+            opw += __shfl_sync(FULL, adv, cur);
+            cur = __shfl_sync(FULL, nxt, cur);
         }
-        if (ip + 2 > n) { if (lit) warp_copy(ob + op, in + litp, lit, lane); st = ST_MALFORMED; break; }
-        const uint32_t offset = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8);   // :126
-        ip += 2;
-        if (offset == 0) { st = ST_OFFSET_ZERO; break; }         // :128
-        uint32_t ml = token & 15u;                               // :131
-        if (ml == 15u) {                                         // :132-138
-            uint32_t b;
-            do {
-                if (ip >= n) { st = ST_MALFORMED; break; }
-                b = in[ip++]; ml += b;
-            } while (b == 255u);
-            if (st) break;
+        // ---- the visited lanes check capacity and history themselves; the first one that fails goes to the serial form
+        bool fine = (real >> lane) & 1u;
+        if (fine) {
+            if ((uint64_t)myop + lit + ml > cap) fine = false;                                 // :74 / match capacity
+            else if ((int64_t)myop + lit - offset < -(int64_t)hist) fine = false;               // dictionary source
         }
-        ml += 4;                                                 // :139
-        const int64_t src_rel = (int64_t)op + lit - offset;      // :142, relative to ob
-        if (src_rel < -(int64_t)hist) {
-            // :145-200 the match starts in the dictionary (ob - hist is output index 0)
-            if (lit) warp_copy(ob + op, in + litp, lit, lane);
-            op += lit;
-            const int64_t cs = src_rel + hist;                   // < 0
-            int64_t from_dict = -cs;
-            if (from_dict > ml) from_dict = ml;
-            const int64_t di = (int64_t)dict_len + cs;
-            if (di < 0 || di + from_dict > dict_len) { st = ST_DICT_OOB; break; }   // :150-152
-            if ((uint64_t)op + ml > cap) { st = ST_OUTPUT_TOO_SMALL; break; }
-            warp_copy(ob + op, dict + di, (uint32_t)from_dict, lane);
-            op += (uint32_t)from_dict;
-            const uint32_t rem = ml - (uint32_t)from_dict;
-            __syncwarp();
-            if (rem) warp_match_copy(ob + op, offset, rem, lane);
-            op += rem;
-            __syncwarp();
-            continue;
-        }
-        const uint32_t total = lit + ml;
-        if ((uint64_t)op + total > cap) {                        // literals fit (checked above), the match does not
-            st = ST_OUTPUT_TOO_SMALL;
-            break;
-        }
-        if (offset >= (total < 32u ? total : 32u)) {
-            // merged pass: every source byte of a round was written before that round
-            uint8_t *const d = ob + op;
-            const uint8_t *const ls = in + litp;
-            const uint8_t *const ms = d - offset;                // ms[j] is the match source of output byte j (j >= lit)
-            for (uint32_t base = 0; base < total; base += 32) {
-                const uint32_t j = base + lane;
-                if (j < total) d[j] = j < lit ? ls[j] : ms[j];
+        const uint32_t notfine = real & ~__ballot_sync(FULL, fine);
+        const uint32_t good = notfine ? (real & ((notfine & (0u - notfine)) - 1u)) : real;
+        // ---- copies, in order
+        const uint32_t pack = lit | (ml << 16);                  // both < 1024 here
+        for (uint32_t m = good; m; m &= m - 1u) {
+            const int l = __ffs(m) - 1;
+            const uint32_t pk = __shfl_sync(FULL, pack, l), off_ = __shfl_sync(FULL, offset, l);
+            const uint32_t lp = __shfl_sync(FULL, litp, l), o_ = __shfl_sync(FULL, myop, l);
+            const uint32_t lit_ = pk & 0xFFFFu, total = lit_ + (pk >> 16);
+            uint8_t *const d = ob + o_;
+            if (off_ >= (total < 32u ? total : 32u)) {
+                // lane j's source: literal j of the sequence, or the match byte `offset` behind its own output byte
+                const uint8_t *sp = lane < lit_ ? in + (lp + lane) : d + ((int32_t)lane - (int32_t)off_);
+                uint8_t *dp = d + lane;
+                if (total <= 32u) {                              // the common case: one round, no loop
+                    if (lane < total) *dp = *sp;
+                } else {
+#pragma unroll 1
+                    for (uint32_t base = 0; base < total; base += 32) {          // uniform trip count: every round ends in a barrier
+                        const uint32_t j = base + lane;
+                        if (j < total) *dp = *sp;
+                        dp += 32;
+                        sp = j + 32 < lit_ ? in + (lp + j + 32) : d + ((int32_t)(j + 32) - (int32_t)off_);
+                        __syncwarp();
+                    }
+                }
+                __syncwarp();
+            } else {
+                if (lit_) warp_copy(d, in + lp, lit_, lane);
+                __syncwarp();
+                warp_match_copy(d + lit_, off_, total - lit_, lane);
                 __syncwarp();
             }
-        } else {
-            if (lit) warp_copy(ob + op, in + litp, lit, lane);
-            __syncwarp();
-            warp_match_copy(ob + op + lit, offset, ml, lane);
-            __syncwarp();
         }
-        op += total;
+        if (good) {
+            const int hi = 31 - __clz(good);
+            op = __shfl_sync(FULL, myop, hi) + __shfl_sync(FULL, adv, hi);
+            ip += __shfl_sync(FULL, nxt, hi);
+        }
+        if (good != real || cur < 32u) {
+            // the next token is one the window could not take (or the walk stopped at one): serial form
+            if (ip >= n) break;
+            if (!dec_one_sequence(in, n, ob, cap, hist, dict, dict_len, ip, op, st, lane)) break;
+        }
     }
     *status = st;
     return op;
