@@ -117,12 +117,18 @@ int block_id_for(uint64_t bytes) {          // bufferCompress.js:77-82
 const uint32_t kBlockMax[8] = {0, 0, 0, 0, 65536, 262144, 1048576, 4194304};
 
 // ---- launch helpers ----------------------------------------------------------------------------------
+int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int64_t total, int64_t B, uint32_t n, bool linked,
+                       const int32_t *init_table, uint8_t *d_comp, const uint64_t *d_coff, uint32_t *d_clen, cudaStream_t st);
+
 int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len, uint32_t n,
                     uint32_t max_len, const uint8_t *prefix, uint32_t prefix_len, const int32_t *init_table, uint8_t *dst,
                     const uint64_t *dst_off, uint32_t *comp_len, cudaStream_t st, uint32_t *counter = nullptr, bool dense = false) {
     if (n == 0) return DLZ4_OK;
     if (!counter) counter = ctx->d_counter;
     CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+    // a prefix without an initial table is never referenced: every table entry was inserted by the block itself
+    // (blockCompress.js:54-55), so the bytes are those of the block compressed alone
+    if (init_table == nullptr) { prefix = nullptr; prefix_len = 0; }
     if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr && ctx->hybrid) {
         // one table region per work-queue counter: kernels of different pipeline lanes run concurrently
         const size_t region = (size_t)(counter - ctx->d_counter) % kGtabRegions;
@@ -138,6 +144,23 @@ int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, 
         k_compress_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * (kHashEntries * 2 + kRingBytes), st>>>(
             src, src_off, src_len, n, dst, dst_off, comp_len, counter);
     } else {
+        if (max_len > 65536 && prefix_len == 0 && init_table == nullptr && n <= 65536) {
+            // blocks > 64 KiB: if they tile one contiguous range uniformly (the usual batch), cut them into segments
+            // (k_compress_segments) instead of one 3-per-SM chain per block.  The descriptors live on the device: read them back.
+            std::vector<uint64_t> off(n);
+            std::vector<uint32_t> len(n);
+            CK(cudaMemcpyAsync(off.data(), src_off, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(len.data(), src_len, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const uint64_t B = len[0];
+            bool uniform = B > 65536 && (B & (B - 1)) == 0 && off[0] + (uint64_t)n * B < 0x7FFFFFF0ull;
+            for (uint32_t i = 0; uniform && i < n; ++i)
+                uniform = off[i] == off[0] + (uint64_t)i * B && (len[i] == B || (i + 1 == n && len[i] <= B && len[i] > 0));
+            if (uniform) {
+                const int64_t total = (int64_t)(n - 1) * (int64_t)B + len[n - 1];
+                return compress_segmented(ctx, src, (int64_t)off[0], total, (int64_t)B, n, false, nullptr, dst, dst_off, comp_len, st);
+            }
+        }
         const int grid = (int)std::min<uint64_t>((n + kWarpsGeneric32 - 1) / kWarpsGeneric32, (uint64_t)ctx->sm_count);
         k_compress_generic32<kWarpsGeneric32><<<grid, kWarpsGeneric32 * 32, kWarpsGeneric32 * (kHashEntries * 4 + kRingBytes), st>>>(
             src, src_off, src_len, n, prefix, prefix_len, init_table, dst, dst_off, comp_len, counter);

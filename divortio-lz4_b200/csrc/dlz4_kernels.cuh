@@ -121,6 +121,18 @@ struct TabG16 {
     __device__ __forceinline__ int32_t get(uint32_t h) const { return start + (int32_t)__ldcg(t + h); }
     __device__ __forceinline__ void put(uint32_t h, int32_t p) { __stcg(t + h, (uint16_t)(p - start)); }
 };
+// Blocks of <= 4096 bytes (config 4: 4 KiB messages): zeroing a 32 KiB table per 4 KiB block costs more than the block.
+// An entry is (epoch:4 | position:12) and counts only when its epoch is the current block's; the table is cleared once every
+// 15 blocks.  Exact: an entry of another epoch is an entry the reference's fresh table does not have.
+template <bool kGlobal>
+struct Tab12e {
+    uint16_t *t; int32_t start; uint32_t epoch;
+    __device__ __forceinline__ uint32_t ld(uint32_t h) const { return kGlobal ? (uint32_t)__ldcg(t + h) : (uint32_t)t[h]; }
+    __device__ __forceinline__ void st(uint32_t h, uint32_t v) { if (kGlobal) __stcg(t + h, (uint16_t)v); else t[h] = (uint16_t)v; }
+    __device__ __forceinline__ int32_t dec(uint32_t v) const { return (v >> 12) == epoch ? start + (int32_t)(v & 4095u) : -1; }
+    __device__ __forceinline__ int32_t get(uint32_t h) const { return dec(ld(h)); }
+    __device__ __forceinline__ void put(uint32_t h, int32_t p) { st(h, (epoch << 12) | (uint32_t)(p - start)); }
+};
 // The reference's own representation: Int32, value = position + 1, <= 0 empty (blockCompress.js:54-55).
 struct Tab32 {
     int32_t *t;
@@ -251,6 +263,10 @@ __device__ __forceinline__ uint32_t tab_raw(const TabG16 &T, uint32_t h) { retur
 __device__ __forceinline__ void tab_set_raw(TabG16 &T, uint32_t h, uint32_t v) { __stcg(T.t + h, (uint16_t)v); }
 __device__ __forceinline__ uint32_t tab_enc(const TabG16 &T, int32_t p) { return (uint32_t)(p - T.start) & 0xFFFFu; }
 __device__ __forceinline__ int32_t tab_dec(const TabG16 &T, uint32_t raw) { return T.start + (int32_t)raw; }
+template <bool G> __device__ __forceinline__ uint32_t tab_raw(const Tab12e<G> &T, uint32_t h) { return T.ld(h); }
+template <bool G> __device__ __forceinline__ void tab_set_raw(Tab12e<G> &T, uint32_t h, uint32_t v) { T.st(h, v); }
+template <bool G> __device__ __forceinline__ uint32_t tab_enc(const Tab12e<G> &T, int32_t p) { return (T.epoch << 12) | (uint32_t)(p - T.start); }
+template <bool G> __device__ __forceinline__ int32_t tab_dec(const Tab12e<G> &T, uint32_t raw) { return T.dec(raw); }
 __device__ __forceinline__ uint32_t tab_raw(const TabG32 &T, uint32_t h) { return (uint32_t)__ldcg(T.t + h); }
 __device__ __forceinline__ void tab_set_raw(TabG32 &T, uint32_t h, uint32_t v) { __stcg(T.t + h, (int32_t)v); }
 __device__ __forceinline__ uint32_t tab_enc(const TabG32 &, int32_t p) { return (uint32_t)(p + 1); }
@@ -676,21 +692,28 @@ k_compress_fresh16h(const uint8_t *__restrict__ src, const uint64_t *__restrict_
     const bool in_smem = warp == 0;
     uint16_t *tab = in_smem ? reinterpret_cast<uint16_t *>(smem)
                             : gtabs + ((size_t)blockIdx.x * kHyGlWarps + (warp - 1)) * kHashEntries;
+    uint32_t epoch = 15;                           // small-block epoch (Tab12e); 15 forces a clear before the first use
     for (;;) {
         const uint32_t b = next_block(counter, lane);
         if (b >= nblocks) break;
         const uint32_t len = src_len[b];
         if (len > 65536u) { if (lane == 0) comp_len[b] = 0xFFFFFFFFu; continue; }
         uint4 *t4 = reinterpret_cast<uint4 *>(tab);
-        uint32_t c;
-        if (in_smem) {
-            for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+        const bool small = len <= 4096u;
+        if (!small || ++epoch > 15u) {
+            if (in_smem) { for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0); }
+            else { for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) __stcg(t4 + i, make_uint4(0, 0, 0, 0)); }
             __syncwarp();
+            epoch = small ? 1u : 15u;              // a 16-bit-position block leaves arbitrary epochs behind: clear again next time
+        }
+        uint32_t c;
+        if (small) {
+            if (in_smem) { Tab12e<false> T{tab, 0, epoch}; c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], ring); }
+            else { Tab12e<true> T{tab, 0, epoch}; c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], ring); }
+        } else if (in_smem) {
             Tab16 T{tab, 0};
             c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], ring);
         } else {
-            for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) __stcg(t4 + i, make_uint4(0, 0, 0, 0));
-            __syncwarp();
             TabG16 T{tab, 0};
             c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], ring);
         }
