@@ -139,6 +139,14 @@ int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, 
         k_compress_fresh16h<<<grid, kHyWarps * 32, kHySmemBytes, st>>>(
             src, src_off, src_len, n, dst, dst_off, comp_len, counter,
             ctx->d_gtabs + region * (size_t)ctx->hy_grid * kHyGlWarps * kHashEntries, active);
+    } else if (max_len <= 4096 && prefix_len > 0 && init_table != nullptr && ctx->hybrid && prefix_len < 0x7FFF0000u) {
+        // small blocks behind a shared prefix, all from the same initial table: read-only base table + per-warp overlay
+        const size_t region = (size_t)(counter - ctx->d_counter) % kGtabRegions;
+        const int grid = (int)std::min<uint64_t>(dense ? (n + kHyWarps - 1) / kHyWarps : n, (uint64_t)ctx->hy_grid);
+        const uint32_t active = dense ? (uint32_t)kHyWarps : (uint32_t)std::min<uint64_t>((n + grid - 1) / grid, (uint64_t)kHyWarps);
+        k_compress_overlay<<<grid, kHyWarps * 32, kHySmemBytes, st>>>(
+            src, src_off, src_len, n, prefix, prefix_len, init_table, dst, dst_off, comp_len, counter,
+            ctx->d_gtabs + region * (size_t)ctx->hy_grid * kHyGlWarps * kHashEntries, active);
     } else if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr) {
         const int grid = (int)std::min<uint64_t>((n + kWarpsFresh16 - 1) / kWarpsFresh16, (uint64_t)ctx->sm_count);
         k_compress_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * (kHashEntries * 2 + kRingBytes), st>>>(
@@ -478,6 +486,7 @@ int dlz4_init(int device, dlz4_ctx **out) {
     ctx->hy_grid = ctx->sm_count * kHyCtasPerSm;
     CK(cudaMalloc(&ctx->d_gtabs, (size_t)kGtabRegions * ctx->hy_grid * kHyGlWarps * kHashEntries * 2));
     CK(cudaFuncSetAttribute(k_compress_fresh16h, cudaFuncAttributeMaxDynamicSharedMemorySize, kHySmemBytes));
+    CK(cudaFuncSetAttribute(k_compress_overlay, cudaFuncAttributeMaxDynamicSharedMemorySize, kHySmemBytes));
     CK(cudaFuncSetAttribute(k_compress_generic32<kWarpsGeneric32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kWarpsGeneric32 * (kHashEntries * 4 + kRingBytes)));
     CK(cudaFuncSetAttribute(k_compress_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kHashEntries * 4 + kRingBytes));

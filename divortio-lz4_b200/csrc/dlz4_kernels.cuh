@@ -133,6 +133,21 @@ struct Tab12e {
     __device__ __forceinline__ int32_t get(uint32_t h) const { return dec(ld(h)); }
     __device__ __forceinline__ void put(uint32_t h, int32_t p) { st(h, (epoch << 12) | (uint32_t)(p - start)); }
 };
+// Small blocks that all start from the SAME initial table (config 4: a table warmed from / primed with a shared dictionary
+// prefix): copying 64 KiB of table per 4 KiB message would cost 16x the message.  The initial table stays read-only in
+// global memory (L1/L2-resident, shared by every warp); a per-warp 16-bit overlay holds the block's own inserts as
+// (epoch:4 | position - start:12) and wins whenever its epoch is current.  Values are the reference's: position + 1, <= 0 empty.
+template <bool kGlobal>
+struct TabOv {
+    uint16_t *ov; const int32_t *base; int32_t start; uint32_t epoch;
+    __device__ __forceinline__ uint32_t raw(uint32_t h) const {
+        const uint32_t v = kGlobal ? (uint32_t)__ldcg(ov + h) : (uint32_t)ov[h];
+        return (v >> 12) == epoch ? (uint32_t)(start + (int32_t)(v & 4095u) + 1) : (uint32_t)__ldg(base + h);
+    }
+    __device__ __forceinline__ void st(uint32_t h, uint32_t v) { if (kGlobal) __stcg(ov + h, (uint16_t)v); else ov[h] = (uint16_t)v; }
+    __device__ __forceinline__ int32_t get(uint32_t h) const { return (int32_t)raw(h) - 1; }
+    __device__ __forceinline__ void put(uint32_t h, int32_t p) { st(h, (epoch << 12) | (uint32_t)(p - start)); }
+};
 // The reference's own representation: Int32, value = position + 1, <= 0 empty (blockCompress.js:54-55).
 struct Tab32 {
     int32_t *t;
@@ -267,6 +282,10 @@ template <bool G> __device__ __forceinline__ uint32_t tab_raw(const Tab12e<G> &T
 template <bool G> __device__ __forceinline__ void tab_set_raw(Tab12e<G> &T, uint32_t h, uint32_t v) { T.st(h, v); }
 template <bool G> __device__ __forceinline__ uint32_t tab_enc(const Tab12e<G> &T, int32_t p) { return (T.epoch << 12) | (uint32_t)(p - T.start); }
 template <bool G> __device__ __forceinline__ int32_t tab_dec(const Tab12e<G> &T, uint32_t raw) { return T.dec(raw); }
+template <bool G> __device__ __forceinline__ uint32_t tab_raw(const TabOv<G> &T, uint32_t h) { return T.raw(h); }
+template <bool G> __device__ __forceinline__ void tab_set_raw(TabOv<G> &T, uint32_t h, uint32_t v) { T.st(h, v); }
+template <bool G> __device__ __forceinline__ uint32_t tab_enc(const TabOv<G> &T, int32_t p) { return (T.epoch << 12) | (uint32_t)(p - T.start); }
+template <bool G> __device__ __forceinline__ int32_t tab_dec(const TabOv<G> &, uint32_t raw) { return (int32_t)raw - 1; }
 __device__ __forceinline__ uint32_t tab_raw(const TabG32 &T, uint32_t h) { return (uint32_t)__ldcg(T.t + h); }
 __device__ __forceinline__ void tab_set_raw(TabG32 &T, uint32_t h, uint32_t v) { __stcg(T.t + h, (int32_t)v); }
 __device__ __forceinline__ uint32_t tab_enc(const TabG32 &, int32_t p) { return (uint32_t)(p + 1); }
@@ -327,10 +346,13 @@ struct SpanState {
 //                          has no such sequence it is finished as above.
 // kEmit == false runs the identical parse without writing output (warm-up of a speculative segment).
 constexpr uint32_t kSpanStopped = 0xFFFFFFFFu;
-template <class Tab, bool kEmit>
+// kSplit: the source is `pre[0, plen)` ++ block, stored apart (shared dictionary prefix of config 4); `base` is then the
+// block's pointer minus plen, valid for indices >= plen only.
+template <class Tab, bool kEmit, bool kSplit = false>
 __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const int32_t start, const int32_t len, Tab &T,
                                        uint8_t *const out, uint32_t *const ring /* kRingBytes of shared memory */,
-                                       SpanState &st, const int32_t limit) {
+                                       SpanState &st, const int32_t limit, const uint8_t *__restrict__ pre = nullptr,
+                                       const int32_t plen = 0) {
     const uint32_t lane = lane_id();
     const uint32_t lt = (1u << lane) - 1u;
     const int32_t sEnd = start + len;
@@ -340,7 +362,17 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
     uint32_t smc = st.smc;
     uint32_t D = st.D;
     uint32_t pend = st.pend;
-    SrcFlat S{base};
+    struct SrcSel {                              // unaligned 4-byte loads at virtual index v (match extension, batch step)
+        const uint8_t *base, *pre; int32_t plen;
+        __device__ __forceinline__ uint32_t ld32(int32_t v) const {
+            if (!kSplit || v >= plen) return ld32u(base + v);
+            if (v + 4 <= plen) return ld32u(pre + v);
+            uint32_t r = 0;
+            for (int k = 0; k < 4; ++k) r |= (uint32_t)(v + k < plen ? pre[v + k] : base[v + k]) << (8 * k);
+            return r;
+        }
+        __device__ __forceinline__ const uint8_t *lit_ptr(int32_t v) const { return base + v; }
+    } S{base, pre, plen};
 
     // forward ring: the 128-byte lines around the window live in a 3-line shared-memory ring filled by cp.async one line
     // ahead of use (no registers, no scoreboard dependency between the prefetch and the window's own loads)
@@ -394,9 +426,13 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
             // candidate bytes cand .. cand+35 as three aligned 16-byte loads (3 L1 wavefronts per lane instead of 9)
             uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;
             uint32_t cs = 0;
-            if (ok) {                       // cand + 35 < p + 35 <= w + 66 < sEnd, and the 16-byte granules holding them
-                cs = (uint32_t)((reinterpret_cast<uintptr_t>(base) + (uint32_t)cand) & 15u);
-                const uint4 *cq = reinterpret_cast<const uint4 *>(base + (cand - (int32_t)cs));
+            // split source: a candidate whose 48-byte read would leave the prefix (or start before it) sends the window to
+            // the batch step, which reads byte-exact across the seam
+            const bool seam = kSplit && ok && cand < plen && (cand + 48 > plen || cand < 16);
+            if (ok && !seam) {              // cand + 35 < p + 35 <= w + 66 < sEnd, and the 16-byte granules holding them
+                const uint8_t *cb = (kSplit && cand < plen) ? pre + cand : base + cand;
+                cs = (uint32_t)(reinterpret_cast<uintptr_t>(cb) & 15u);
+                const uint4 *cq = reinterpret_cast<const uint4 *>(cb - cs);
                 q0 = __ldg(cq); q1 = __ldg(cq + 1);
                 if (cs + 36u > 32u) q2 = __ldg(cq + 2);
             }
@@ -404,7 +440,7 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
             // two lanes of the window in one slot?  Then a later lane's candidate depends on the parse -> batch step.
             // Nothing is inserted yet, so the table is still the exact pre-window state either way.
             const uint32_t mine = tab_enc(T, p);
-            const uint32_t conflict = __ballot_sync(FULL, __match_any_sync(FULL, h) != (1u << lane));
+            const uint32_t conflict = __ballot_sync(FULL, __match_any_sync(FULL, h) != (1u << lane) || seam);
             PT_MARK(3)
             if (conflict) {
                 PT_COUNT(10, 1)
@@ -716,6 +752,49 @@ k_compress_fresh16h(const uint8_t *__restrict__ src, const uint64_t *__restrict_
         } else {
             TabG16 T{tab, 0};
             c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], ring);
+        }
+        if (lane == 0) comp_len[b] = c;
+        __syncwarp();
+    }
+}
+
+// Blocks of <= 4096 bytes behind a shared prefix, all starting from the same initial table (TabOv).  Same CTA shape as
+// k_compress_fresh16h: warp 0 keeps its overlay in shared memory, warps 1..6 in L2-resident global scratch.
+__global__ void __launch_bounds__(kHyWarps * 32, kHyCtasPerSm)
+k_compress_overlay(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ src_len,
+                   uint32_t nblocks, const uint8_t *__restrict__ prefix, uint32_t prefix_len, const int32_t *__restrict__ init_table,
+                   uint8_t *__restrict__ dst, const uint64_t *__restrict__ dst_off, uint32_t *__restrict__ comp_len, uint32_t *counter,
+                   uint16_t *gtabs, uint32_t active_warps) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    if (warp >= active_warps) return;
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + kHashEntries * 2 + warp * kRingBytes);
+    const bool in_smem = warp == 0;
+    uint16_t *tab = in_smem ? reinterpret_cast<uint16_t *>(smem)
+                            : gtabs + ((size_t)blockIdx.x * kHyGlWarps + (warp - 1)) * kHashEntries;
+    const int32_t plen = (int32_t)prefix_len;
+    uint32_t epoch = 15;
+    for (;;) {
+        const uint32_t b = next_block(counter, lane);
+        if (b >= nblocks) break;
+        const uint32_t len = src_len[b];
+        if (len > 4096u) { if (lane == 0) comp_len[b] = 0xFFFFFFFFu; continue; }
+        if (++epoch > 15u) {
+            uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+            if (in_smem) { for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0); }
+            else { for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) __stcg(t4 + i, make_uint4(0, 0, 0, 0)); }
+            __syncwarp();
+            epoch = 1;
+        }
+        const uint8_t *vbase = src + src_off[b] - plen;           // virtual index plen = first byte of the message
+        SpanState st{plen, plen, 67u, 0u, 0u, -1};
+        uint32_t c;
+        if (in_smem) {
+            TabOv<false> T{tab, init_table, plen, epoch};
+            c = compress_span_warp<TabOv<false>, true, true>(vbase, plen, (int32_t)len, T, dst + dst_off[b], ring, st, INT_MAX, prefix, plen);
+        } else {
+            TabOv<true> T{tab, init_table, plen, epoch};
+            c = compress_span_warp<TabOv<true>, true, true>(vbase, plen, (int32_t)len, T, dst + dst_off[b], ring, st, INT_MAX, prefix, plen);
         }
         if (lane == 0) comp_len[b] = c;
         __syncwarp();

@@ -93,3 +93,8 @@ import ctypes as C  # noqa: E402
 blocks_case("config4: JSON 4 KiB msgs, no prefix", msgs, 4096)
 blocks_case("config4: + 64 KiB prefix, warm=none", msgs, 4096, prefix=dic)
 blocks_case("config4: + 64 KiB prefix, warm=jenkins", msgs, 4096, prefix=dic, warm=dl.WARM_JENKINS)
+# warm=primed: the table the kernel itself leaves behind after compressing the dictionary (raw API, table is in/out)
+tab = np.zeros(16384, dtype=np.int32)
+scratch = np.zeros(dl.compress_bound(dic.size), dtype=np.uint8)
+dl.compressBlock(dic, scratch, 0, dic.size, tab, 0, ctx=ctx)
+blocks_case("config4: + 64 KiB prefix, warm=primed", msgs, 4096, prefix=dic, warm=dl.WARM_TABLE, table=tab)

@@ -115,6 +115,32 @@ def test_compress_with_shared_prefix_three_table_modes(dl):
     assert sizes["primed"] < sizes["none"]                # only the kernel's own hash makes the prefix useful
 
 
+def test_overlay_tables_ragged_messages_odd_prefixes(dl):
+    """Small blocks behind a shared prefix with a warmed / primed table (k_compress_overlay): ragged lengths, prefixes of odd
+    lengths and alignments, enough messages for every warp to wrap its 4-bit epoch several times."""
+    from divortio_lz4_b200 import corpus
+    rng = np.random.RandomState(77)
+    nmsg = 9000
+    raw = corpus.jsonmsgs(9, 0, nmsg)
+    ln = rng.randint(0, 4097, size=nmsg).astype(np.uint32)
+    ln[:8] = [0, 1, 12, 13, 66, 67, 4095, 4096]
+    off = np.arange(nmsg, dtype=np.uint64) * 4096
+    for plen in (65536, 65535, 4097, 1000, 37):
+        dic = corpus.jsonmsgs(45, 0, 17).tobytes()[3:3 + plen]
+        dic = np.frombuffer(dic, dtype=np.uint8).copy()
+        work = np.concatenate([dic, np.zeros(8, dtype=np.uint8)])
+        primed = oracle.new_table()
+        oracle.compress_block(dic, 0, dic.size, primed)
+        for mode, (warm, init, otab) in {"jenkins": (dl.WARM_JENKINS, None, oracle.warm_table_jenkins(work, dic.size)),
+                                         "primed": (dl.WARM_TABLE, primed, primed)}.items():
+            dst, doff, clen = dl.compress_blocks(raw, off, ln, prefix=dic, warm=warm, init_table=init)
+            odst, odoff, oclen = oracle.compress_blocks_prefix(dic, otab, raw, off, ln)
+            assert np.array_equal(clen, oclen), (plen, mode)
+            bad = [i for i in range(nmsg) if not np.array_equal(dst[int(doff[i]):int(doff[i]) + int(clen[i])],
+                                                                 odst[int(odoff[i]):int(odoff[i]) + int(oclen[i])])]
+            assert not bad, (plen, mode, bad[:5])
+
+
 def test_decompress_edge_corpora(dl):
     corp = edge_corpora()
     names = list(corp)
