@@ -247,6 +247,37 @@ def run_b200(args):
         e2e = {"t": te / esteps, "h2d": n + cbytes + nblk * (20 + 20), "d2h": cbytes + n + nblk * (4 + 5)}
         L.dlz4_pinned_free(pin_c)
         L.dlz4_pinned_free(pin_o)
+    # ---- reported separately: the reference's DEFAULT frame (linked 4 MiB blocks, BASELINE configs[0] shape: 64 MiB log text)
+    # through the frame C ABI with pinned host buffers -- segment-parallel compressor and jump decoder
+    frames = None
+    if rank == 0 and not args.no_e2e:
+        from divortio_lz4_b200.api import FrameOpts
+        fn = min(n, 64 << 20)
+        pin_l = L.dlz4_pinned_alloc(fn + 64)
+        hl = np.ctypeslib.as_array(C.cast(pin_l, C.POINTER(C.c_uint8)), shape=(fn + 64,))
+        corpus.log(1, fn, out=hl)
+        fcap = int(L.dlz4_frame_bound(fn))
+        pin_f = L.dlz4_pinned_alloc(fcap + 64)
+        pin_b = L.dlz4_pinned_alloc(fn + 64)
+        opts = FrameOpts(4194304, 0, 0, 1, 0)
+        flen, blen = C.c_uint64(0), C.c_uint64(0)
+        tcs, tds = [], []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ctx.check(L.dlz4_frame_compress(ctx.handle, pin_l, fn, None, 0, C.byref(opts), pin_f, fcap, C.byref(flen)))
+            t1 = time.perf_counter()
+            ctx.check(L.dlz4_frame_decompress(ctx.handle, pin_f, flen.value, None, 0, 1, pin_b, fn, C.byref(blen)))
+            t2 = time.perf_counter()
+            tcs.append(t1 - t0)
+            tds.append(t2 - t1)
+        back = np.ctypeslib.as_array(C.cast(pin_b, C.POINTER(C.c_uint8)), shape=(fn,))
+        assert blen.value == fn and np.array_equal(back, hl[:fn]), "linked frame round trip mismatch"
+        segs, reruns, rounds = ctx.segment_stats
+        frames = {"workload": "LOG(seed=1) %d MiB, one linked-block frame (blockIndependence=false, 4 MiB blocks), host to host" % (fn >> 20),
+                  "compress_gbs": round(fn / min(tcs) / 1e9, 3), "decompress_gbs": round(fn / min(tds) / 1e9, 3),
+                  "ratio": round(fn / flen.value, 4), "segments": segs, "segments_rerun": reruns, "rerun_rounds": rounds}
+        for ptr in (pin_l, pin_f, pin_b):
+            L.dlz4_pinned_free(ptr)
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
@@ -292,7 +323,8 @@ def run_b200(args):
                          "algorithmic_bytes_per_launch": n + csize},
             "detail": {"compress_gbs": round(args.steps * total / tc / 1e9, 3), "decompress_gbs": round(args.steps * total / td / 1e9, 3),
                        "decompress_hbm_frac": round(((n + csize) / (td / args.steps) / 1e9) / peak, 5),
-                       "ratio": round(total / csize_all, 4), "wall_s_timed_region": round(t_wall, 4), "verified_roundtrip": True},
+                       "ratio": round(total / csize_all, 4), "wall_s_timed_region": round(t_wall, 4), "verified_roundtrip": True,
+                       "linked_frame": frames},
         }
         if not args.no_cpu_baseline and world >= 1:
             sample = min(n, args.cpu_sample_bytes)
