@@ -508,14 +508,15 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
                     }
                     const uint32_t lit = (uint32_t)(hl - a_rel);
                     const uint32_t code = (uint32_t)(mlh - 4);
-                    const uint32_t litx = lit >= 15u ? 1u + (lit - 15u) / 255u : 0u;
-                    const uint32_t mlx = code >= 15u ? 1u + (code - 15u) / 255u : 0u;
+                    uint32_t litx = 0, mlx = code >= 15u;            // a match inside the window is <= 32 bytes: one length byte at most
+                    if (lit >= 15u) litx = 1u + (lit - 15u) / 255u;  // uniform and rare (3 % of sequences on text)
+                    if (code >= 15u + 255u) mlx = 1u + (code - 15u) / 255u;     // long match (continued above)
                     if (lane == (uint32_t)hl) { myD = D; myLit = lit; myMl = (uint32_t)mlh; }
                     D += 3u + litx + lit + mlx;
                     heads |= 1u << hl;
                     a_rel = hl + mlh;
                     cur = (uint32_t)a_rel;
-                    inside |= (cur < 32u ? ((1u << cur) - 1u) : FULL) & ~((2u << hl) - 1u);
+                    inside |= (cur < 32u ? (1u << cur) : 0u) - (2u << hl);      // bits hl+1 .. cur-1 (to the top when the match leaves the window)
                     smc_cur = 67;
                 }
                 PT_MARK(5)
