@@ -25,7 +25,7 @@ __all__ = [
     "LZ4", "LZ4Error", "Context", "default_context", "compressBlock", "decompressBlock", "compressBuffer",
     "decompressBuffer", "xxHash32", "compress_blocks", "decompress_blocks", "xxh32_batch", "compress_bound",
     "frame_bound", "shard_range", "ensureBuffer", "lib", "LIB_PATH", "WARM_NONE", "WARM_JENKINS", "WARM_TABLE",
-    "HIST_RAW", "HIST_FRAME", "frame_info",
+    "HIST_RAW", "HIST_FRAME", "frame_info", "decompressFrames", "XXHash32", "chain_compress",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -35,6 +35,9 @@ WARM_NONE, WARM_JENKINS, WARM_TABLE = 0, 1, 2
 HIST_RAW, HIST_FRAME = 0, 1
 E_CUDA = 30
 E_BAD_VERSION = 6
+E_DICT_OOB = 4
+E_BAD_MAGIC = 5
+E_CONTENT_CHECKSUM = 7
 
 
 class LZ4Error(Exception):
@@ -49,7 +52,12 @@ class FrameInfo(C.Structure):
     _fields_ = [("content_size", C.c_uint64), ("max_decoded", C.c_uint64), ("nblocks", C.c_uint32),
                 ("block_max_size", C.c_uint32), ("flg", C.c_uint8), ("bd", C.c_uint8), ("has_content_size", C.c_uint8),
                 ("has_content_checksum", C.c_uint8), ("has_block_checksum", C.c_uint8), ("has_dict_id", C.c_uint8),
-                ("block_independence", C.c_uint8), ("pad", C.c_uint8), ("dict_id", C.c_uint32), ("version", C.c_int32)]
+                ("block_independence", C.c_uint8), ("pad", C.c_uint8), ("dict_id", C.c_uint32), ("version", C.c_int32),
+                ("frame_bytes", C.c_uint64)]
+
+
+class Xxh32State(C.Structure):
+    _fields_ = [("v", C.c_uint32 * 4), ("total", C.c_uint64), ("mem", C.c_uint8 * 16), ("memsize", C.c_uint32), ("seed", C.c_uint32)]
 
 
 class FrameOpts(C.Structure):
@@ -97,6 +105,13 @@ def lib():
         "dlz4_frame_info": (C.c_int, [vp, u64, C.POINTER(FrameInfo)]),
         "dlz4_frame_decompress": (C.c_int, [vp, vp, u64, vp, u64, u32, vp, u64, C.POINTER(u64)]),
         "dlz4_frame_pack_dev": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, u32, C.c_int, vp, vp, vp]),
+        "dlz4_frame_decompress_ex": (C.c_int, [vp, vp, u64, vp, u64, u32, vp, u64, C.POINTER(u64), vp]),
+        "dlz4_frames_decompress": (C.c_int, [vp, vp, u64, vp, u64, u32, vp, u64, C.POINTER(u64), C.POINTER(u32)]),
+        "dlz4_frames_info": (C.c_int, [vp, u64, C.POINTER(u64), C.POINTER(u32)]),
+        "dlz4_xxh32_reset": (None, [C.POINTER(Xxh32State), u32]),
+        "dlz4_xxh32_update": (C.c_int, [vp, C.POINTER(Xxh32State), vp, u64]),
+        "dlz4_xxh32_digest": (u32, [C.POINTER(Xxh32State)]),
+        "dlz4_chain_compress": (C.c_int, [vp, vp, u64, i32, i32, i32, vp, vp, u64, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -111,7 +126,8 @@ EXPORTED_SYMBOLS = [
     "dlz4_pinned_alloc", "dlz4_pinned_free", "dlz4_compress_bound", "dlz4_frame_bound", "dlz4_shard_range",
     "dlz4_compress_blocks_dev", "dlz4_compress_blocks", "dlz4_decompress_blocks_dev", "dlz4_decompress_blocks",
     "dlz4_compress_block", "dlz4_decompress_block", "dlz4_xxh32_batch_dev", "dlz4_xxh32_stream_dev", "dlz4_xxh32",
-    "dlz4_xxh32_batch", "dlz4_frame_compress", "dlz4_frame_info", "dlz4_frame_decompress", "dlz4_frame_pack_dev",
+    "dlz4_xxh32_batch", "dlz4_frame_compress", "dlz4_frame_info", "dlz4_frame_decompress", "dlz4_frame_pack_dev", "dlz4_frames_decompress", "dlz4_frames_info", "dlz4_frame_decompress_ex", "dlz4_xxh32_reset", "dlz4_xxh32_update", "dlz4_xxh32_digest",
+    "dlz4_chain_compress",
 ]
 
 
@@ -372,6 +388,60 @@ def decompressBuffer(input, dictionary=None, verifyChecksum=True, verifyBlockChe
                                      _ptr(out), int(info.max_decoded), C.byref(n))
     ctx.check(st)
     return out[:int(n.value)].tobytes()
+
+
+def decompressFrames(input, dictionary=None, verifyChecksum=True, verifyBlockChecksums=False, ctx=None):
+    """Every LZ4 frame of a buffer of concatenated frames, skippable frames skipped (the reference's
+    decompressBuffer stops at the first EndMark, its stream decoder loops: src/shared/lz4Decode.js:262-266).
+    Returns (bytes, number of frames)."""
+    ctx = ctx or default_context()
+    f = ensureBuffer(input)
+    total, count = C.c_uint64(0), C.c_uint32(0)
+    st = lib().dlz4_frames_info(_ptr(f), f.size, C.byref(total), C.byref(count))
+    ctx.check(st)
+    d = ensureBuffer(dictionary) if dictionary is not None and len(dictionary) > 0 else None
+    out = np.empty(int(total.value) + 16, dtype=np.uint8)
+    n = C.c_uint64()
+    flags = (1 if verifyChecksum else 0) | (2 if verifyBlockChecksums else 0)
+    st = lib().dlz4_frames_decompress(ctx.handle, _ptr(f), f.size, _ptr(d), d.size if d is not None else 0, flags,
+                                      _ptr(out), int(total.value), C.byref(n), C.byref(count))
+    ctx.check(st)
+    return out[:int(n.value)].tobytes(), int(count.value)
+
+
+class XXHash32(object):
+    """The reference's stateful hasher (src/xxhash32/xxhash32Stateful.js): update(bytes) ... digest()."""
+
+    def __init__(self, seed=0, ctx=None):
+        self._ctx = ctx or default_context()
+        self._s = Xxh32State()
+        lib().dlz4_xxh32_reset(C.byref(self._s), seed & 0xFFFFFFFF)
+
+    def update(self, data):
+        b = ensureBuffer(data)
+        if b.size:
+            self._ctx.check(lib().dlz4_xxh32_update(self._ctx.handle, C.byref(self._s), _ptr(b), b.size))
+        return self
+
+    def digest(self):
+        return int(lib().dlz4_xxh32_digest(C.byref(self._s)))
+
+
+def chain_compress(work, start, total, block_size, table, ctx=None):
+    """Every block of work[start, start+total) as one linked chain, `table` (int32[16384]) carried in and out
+    (LZ4Encoder._flushBlock over all full blocks of an add(), lz4Encode.js:215-298).  Returns a list of per-block bytes."""
+    ctx = ctx or default_context()
+    work = ensureBuffer(work)
+    n = (total + block_size - 1) // block_size
+    if n == 0:
+        return []
+    stride = compress_bound(block_size)
+    dst = np.empty(n * stride, dtype=np.uint8)
+    clen = np.zeros(n, dtype=np.uint32)
+    st = lib().dlz4_chain_compress(ctx.handle, _ptr(work), work.size, int(start), int(total), int(block_size), _ptr(table),
+                                   _ptr(dst), stride, _ptr(clen))
+    ctx.check(st)
+    return [dst[k * stride:k * stride + int(clen[k])] for k in range(n)]
 
 
 class _LZ4(object):

@@ -118,7 +118,8 @@ const uint32_t kBlockMax[8] = {0, 0, 0, 0, 65536, 262144, 1048576, 4194304};
 
 // ---- launch helpers ----------------------------------------------------------------------------------
 int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int64_t total, int64_t B, uint32_t n, bool linked,
-                       const int32_t *init_table, uint8_t *d_comp, const uint64_t *d_coff, uint32_t *d_clen, cudaStream_t st);
+                       const int32_t *init_table, uint8_t *d_comp, const uint64_t *d_coff, uint32_t *d_clen, cudaStream_t st,
+                       int32_t *final_table = nullptr);
 
 int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len, uint32_t n,
                     uint32_t max_len, const uint8_t *prefix, uint32_t prefix_len, const int32_t *init_table, uint8_t *dst,
@@ -185,8 +186,10 @@ int launch_decompress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off
     if (n == 0) return DLZ4_OK;
     if (!counter) counter = ctx->d_counter;
     CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
-    const int grid = (int)std::min<uint64_t>((n + kWarpsDecode - 1) / kWarpsDecode, (uint64_t)ctx->sm_count * 8);
-    k_decompress_blocks<kWarpsDecode><<<grid, kWarpsDecode * 32, 0, st>>>(src, src_off, src_len, n, dst, dst_off, dst_cap, dict,
+    // frame history: a block may read what the blocks before it wrote, so ONE warp takes them in queue order (the parallel
+    // route for linked data is the frame call's jump decoder)
+    const int grid = hist_frame ? 1 : (int)std::min<uint64_t>((n + kWarpsDecode - 1) / kWarpsDecode, (uint64_t)ctx->sm_count * 8);
+    k_decompress_blocks<kWarpsDecode><<<grid, hist_frame ? 32 : kWarpsDecode * 32, 0, st>>>(src, src_off, src_len, n, dst, dst_off, dst_cap, dict,
                                                                            dict_len, hist_frame, stored, out_len, status, counter);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -204,7 +207,7 @@ int launch_xxh32_batch(dlz4_ctx *ctx, const uint8_t *base, const uint64_t *off, 
 }
 
 int launch_xxh32_stream(dlz4_ctx *ctx, const uint8_t *data, uint64_t len, uint32_t seed, uint32_t *out, cudaStream_t st) {
-    k_xxh32_stream<<<1, 32, 0, st>>>(data, len, seed, out);
+    k_xxh32_stream<<<1, 32, 0, st>>>(data, len, seed, out, nullptr, nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
     return DLZ4_OK;
@@ -214,7 +217,8 @@ int launch_xxh32_stream(dlz4_ctx *ctx, const uint8_t *data, uint64_t len, uint32
 // size B that tile [start, start + total) of the working buffer; linked: one chain carrying the table (init_table = its
 // initial state), otherwise every block is its own chain with a fresh table.  Output: d_comp + d_coff[b], d_clen[b].
 int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int64_t total, int64_t B, uint32_t n, bool linked,
-                       const int32_t *init_table, uint8_t *d_comp, const uint64_t *d_coff, uint32_t *d_clen, cudaStream_t st) {
+                       const int32_t *init_table, uint8_t *d_comp, const uint64_t *d_coff, uint32_t *d_clen, cudaStream_t st,
+                       int32_t *final_table /* nullable, device int32[16384]: the chain's table after its last block (linked only) */) {
     if (n == 0) return DLZ4_OK;
     // segment size: about 2048 segments over the call, at least 128 KiB; warm-up 512 KiB (tools/resync_stats.c)
     int64_t S = 128 << 10;
@@ -308,6 +312,8 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
             ctx->seg_rounds++;
         }
     }
+    if (final_table && linked)      // the last segment's table buffer is the chain's end state (verified above)
+        CK(cudaMemcpyAsync(final_table, d_tab + (size_t)(nj - 1) * kHashEntries, kHashEntries * 4, cudaMemcpyDeviceToDevice, st));
     {
         const uint32_t gx = (uint32_t)std::min<uint64_t>(n, 65535), gy = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(64, (uint64_t)ctx->sm_count * 8 / gx));
         k_seg_assemble<<<dim3(gx, gy), 256, 0, st>>>(d_buf, bstride, d_sf, d_sc, d_poff, d_plen, n, d_comp, d_coff, d_clen);
@@ -1250,11 +1256,54 @@ int dlz4_frame_info(const uint8_t *frame, uint64_t frame_len, dlz4_frame_info_t 
     uint64_t bound = 0;
     for (const BlockRef &b : blocks) bound += b.stored ? b.len : std::min<uint64_t>((uint64_t)b.len * 255, info->block_max_size);
     info->max_decoded = info->content_size ? info->content_size : bound;
+    info->frame_bytes = end + (info->has_content_checksum ? 4 : 0);
+    if (info->frame_bytes > frame_len) return DLZ4_E_MALFORMED;
     return DLZ4_OK;
+}
+
+}  // extern "C"
+// Walks concatenated / skippable frames (LZ4 frame spec); fn(frame pointer, info) is called per LZ4 frame.
+template <class Fn>
+static int for_each_frame(const uint8_t *data, uint64_t len, Fn fn) {
+    uint64_t pos = 0;
+    while (pos < len) {
+        if (pos + 4 > len) return DLZ4_E_BAD_MAGIC;
+        const uint32_t magic = rd32(data + pos);
+        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {                       // skippable frame
+            if (pos + 8 > len) return DLZ4_E_MALFORMED;
+            const uint64_t sz = rd32(data + pos + 4);
+            if (pos + 8 + sz > len) return DLZ4_E_MALFORMED;
+            pos += 8 + sz;
+            continue;
+        }
+        dlz4_frame_info_t info;
+        int s = dlz4_frame_info(data + pos, len - pos, &info);
+        if (s) return s;
+        s = fn(data + pos, info);
+        if (s) return s;
+        pos += info.frame_bytes;
+    }
+    return DLZ4_OK;
+}
+extern "C" {
+
+int dlz4_frames_info(const uint8_t *data, uint64_t data_len, uint64_t *max_decoded, uint32_t *frames) {
+    if (!data || !max_decoded) return DLZ4_E_INVALID_ARG;
+    uint64_t total = 0;
+    uint32_t count = 0;
+    const int s = for_each_frame(data, data_len, [&](const uint8_t *, const dlz4_frame_info_t &info) { total += info.max_decoded; ++count; return DLZ4_OK; });
+    *max_decoded = total;
+    if (frames) *frames = count;
+    return s;
 }
 
 int dlz4_frame_decompress(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_len, const uint8_t *dictionary, uint64_t dict_len,
                           uint32_t flags, uint8_t *output, uint64_t output_cap, uint64_t *output_len) {
+    return dlz4_frame_decompress_ex(ctx, frame, frame_len, dictionary, dict_len, flags, output, output_cap, output_len, nullptr);
+}
+
+int dlz4_frame_decompress_ex(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_len, const uint8_t *dictionary, uint64_t dict_len,
+                             uint32_t flags, uint8_t *output, uint64_t output_cap, uint64_t *output_len, uint32_t *block_out_len) {
     if (!ctx || !frame || !output_len) return DLZ4_E_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -1381,10 +1430,116 @@ int dlz4_frame_decompress(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_le
     }
     *output_len = total;
     if (total > output_cap) return DLZ4_E_OUTPUT_TOO_SMALL;
+    if (block_out_len && n) CK(cudaMemcpyAsync(block_out_len, d_olen, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (total && !shipped) CK(cudaMemcpyAsync(output, d_out, total, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     return DLZ4_OK;
+}
+
+// ---- stateful xxh32 (the reference's XXHash32 class: update / digest, src/xxhash32/xxhash32Stateful.js) ---------------
+void dlz4_xxh32_reset(dlz4_xxh32_state *s, uint32_t seed) {
+    if (!s) return;
+    memset(s, 0, sizeof *s);
+    s->seed = seed;
+    s->v[0] = seed + 2654435761u + 2246822519u; s->v[1] = seed + 2246822519u; s->v[2] = seed; s->v[3] = seed - 2654435761u;
+}
+
+int dlz4_xxh32_update(dlz4_ctx *ctx, dlz4_xxh32_state *s, const uint8_t *data, uint64_t len) {
+    if (!ctx || !s || (len && !data)) return DLZ4_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    s->total += len;
+    if (s->memsize + len < 16) {                                        // not a stripe yet
+        memcpy(s->mem + s->memsize, data, (size_t)len);
+        s->memsize += (uint32_t)len;
+        return DLZ4_OK;
+    }
+    // stripes = pending tail ++ data, cut at a multiple of 16; the rest becomes the new tail
+    const uint64_t avail = s->memsize + len, body = avail & ~15ull, from_data = body - s->memsize;
+    CKS(reserve(ctx, ctx->work, body + 64));
+    uint8_t *d = (uint8_t *)ctx->work.p;
+    if (s->memsize) CK(cudaMemcpyAsync(d, s->mem, s->memsize, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + s->memsize, data, from_data, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_hash + 4, s->v, 16, cudaMemcpyHostToDevice, st));
+    k_xxh32_stream<<<1, 32, 0, st>>>(d, body, s->seed, nullptr, ctx->d_hash + 4, ctx->d_hash + 8);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(s->v, ctx->d_hash + 8, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    s->memsize = (uint32_t)(avail - body);
+    memcpy(s->mem, data + from_data, s->memsize);
+    return DLZ4_OK;
+}
+
+uint32_t dlz4_xxh32_digest(const dlz4_xxh32_state *s) {
+    // the accumulators come from the GPU; what is left is the merge and <= 15 tail bytes (xxhash32.js:59-97), like the header byte
+    auto rl = [](uint32_t x, int r) { return (x << r) | (x >> (32 - r)); };
+    uint32_t h = s->total >= 16 ? rl(s->v[0], 1) + rl(s->v[1], 7) + rl(s->v[2], 12) + rl(s->v[3], 18) : s->seed + 374761393u;
+    h += (uint32_t)s->total;
+    const uint8_t *p = s->mem, *end = s->mem + s->memsize;
+    while (p + 4 <= end) { h = rl(h + rd32(p) * 3266489917u, 17) * 668265263u; p += 4; }
+    while (p < end) { h = rl(h + (*p) * 374761393u, 11) * 2654435761u; ++p; }
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    return h;
+}
+
+// ---- one linked chain with the table in/out (LZ4Encoder._flushBlock over every full block of an add(), lz4Encode.js:215-298) ----
+int dlz4_chain_compress(dlz4_ctx *ctx, const uint8_t *work, uint64_t work_len, int32_t start, int32_t total, int32_t block_size,
+                        int32_t *table, uint8_t *dst, uint64_t dst_stride, uint32_t *comp_len) {
+    if (!ctx || !work || !table || !dst || !comp_len || start < 0 || total < 0 || block_size <= 0) return DLZ4_E_INVALID_ARG;
+    if ((uint64_t)start + (uint64_t)total > work_len || work_len >= 0x7FFFFFF0ull) return DLZ4_E_INVALID_ARG;
+    if (total == 0) return DLZ4_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = (uint32_t)(((int64_t)total + block_size - 1) / block_size);
+    const uint64_t stride = (dlz4_compress_bound((uint64_t)block_size) + 15) & ~15ull;
+    if (dst_stride < dlz4_compress_bound((uint64_t)std::min(block_size, total))) return DLZ4_E_OUTPUT_TOO_SMALL;
+    CKS(reserve(ctx, ctx->work, work_len + 64));
+    CKS(reserve(ctx, ctx->comp, (uint64_t)n * stride + 64));
+    CKS(reserve(ctx, ctx->meta, (size_t)n * (8 + 8 + 4 + 4) + 64));
+    uint8_t *d_work = (uint8_t *)ctx->work.p, *d_comp = (uint8_t *)ctx->comp.p;
+    uint64_t *d_soff = (uint64_t *)ctx->meta.p, *d_coff = d_soff + n;
+    uint32_t *d_slen = (uint32_t *)(d_coff + n), *d_clen = d_slen + n;
+    CK(cudaMemcpyAsync(d_work, work, work_len, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_table, table, kHashEntries * 4, cudaMemcpyHostToDevice, st));
+    k_uniform_blocks<<<(n + 255) / 256, 256, 0, st>>>((uint64_t)start, (uint64_t)total, (uint32_t)block_size, n, d_soff, d_slen, d_coff, stride);
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev0, st));
+    if ((uint64_t)total >= ctx->seg_min_bytes)
+        CKS(compress_segmented(ctx, d_work, start, total, block_size, n, true, ctx->d_table, d_comp, d_coff, d_clen, st, ctx->d_table));
+    else
+        CKS(launch_chain(ctx, d_work, start, total, block_size, n, ctx->d_table, d_comp, stride, d_clen, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaMemcpyAsync(comp_len, d_clen, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(table, ctx->d_table, kHashEntries * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint64_t take = std::min<uint64_t>(comp_len[k], dst_stride);       // undersized room truncates like a typed array
+        if (take) CK(cudaMemcpyAsync(dst + (uint64_t)k * dst_stride, d_comp + (uint64_t)k * stride, take, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return DLZ4_OK;
+}
+
+int dlz4_frames_decompress(dlz4_ctx *ctx, const uint8_t *data, uint64_t data_len, const uint8_t *dictionary, uint64_t dict_len,
+                           uint32_t flags, uint8_t *output, uint64_t output_cap, uint64_t *output_len, uint32_t *frames) {
+    if (!ctx || !data || !output_len) return DLZ4_E_INVALID_ARG;
+    uint64_t written = 0;
+    uint32_t count = 0;
+    const int s = for_each_frame(data, data_len, [&](const uint8_t *f, const dlz4_frame_info_t &info) {
+        uint64_t got = 0;
+        const int r = dlz4_frame_decompress(ctx, f, info.frame_bytes, dictionary, dict_len, flags, output ? output + written : nullptr,
+                                            output_cap - written, &got);
+        if (r) return r;
+        written += got;
+        ++count;
+        return (int)DLZ4_OK;
+    });
+    *output_len = written;
+    if (frames) *frames = count;
+    return s;
 }
 
 }  // extern "C"

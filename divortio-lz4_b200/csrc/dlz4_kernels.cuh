@@ -2038,11 +2038,14 @@ k_xxh32_batch(const uint8_t *__restrict__ base, const uint64_t *__restrict__ off
 // One hash over one long buffer: a single quad is the whole parallelism the algorithm has.  The other 28
 // lanes of the warp stage the stream through shared memory so the four chain lanes never wait on HBM.
 __global__ void __launch_bounds__(32)
-k_xxh32_stream(const uint8_t *__restrict__ data, uint64_t len, uint32_t seed, uint32_t *out) {
+k_xxh32_stream(const uint8_t *__restrict__ data, uint64_t len, uint32_t seed, uint32_t *out,
+               const uint32_t *__restrict__ acc_in /* nullable: resume from 4 accumulators */,
+               uint32_t *acc_out /* nullable: stop after the stripes and store the accumulators (stateful update) */) {
     __shared__ __align__(16) uint32_t buf[2][1024];              // 2 x 4 KiB = 2 x 256 stripes
     const uint32_t lane = lane_id();
     const uint64_t nstripes = len >> 4;
     uint32_t v = lane == 0 ? seed + P32_1 + P32_2 : lane == 1 ? seed + P32_2 : lane == 2 ? seed : seed - P32_1;
+    if (acc_in && lane < 4) v = acc_in[lane];
     const bool aligned = (reinterpret_cast<uintptr_t>(data) & 15u) == 0;
     uint64_t s = 0;
     if (aligned) {
@@ -2075,6 +2078,10 @@ k_xxh32_stream(const uint8_t *__restrict__ data, uint64_t len, uint32_t seed, ui
     if (lane < 4) {
         const uint8_t *q = data + 4 * lane;
         for (; s < nstripes; ++s) v = xxh_round(v, ld32u(q + 16 * s));
+    }
+    if (acc_out) {                                               // stateful update: the caller keeps the tail and the total length
+        if (lane < 4) acc_out[lane] = v;
+        return;
     }
     const uint32_t v1 = __shfl_sync(FULL, v, 0), v2 = __shfl_sync(FULL, v, 1), v3 = __shfl_sync(FULL, v, 2), v4 = __shfl_sync(FULL, v, 3);
     if (lane == 0) {

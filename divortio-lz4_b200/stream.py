@@ -1,0 +1,274 @@
+"""Host-side mirror of the reference's streaming codec: `LZ4Encoder` (src/shared/lz4Encode.js:95-332) and
+`LZ4Decoder` (src/shared/lz4Decode.js:52-306), same constructor arguments, same methods, same chunk-by-chunk results -- with the
+GPU block path beneath them.  What changes is the batching: an `add()` that completes several blocks compresses them in ONE call
+(independent blocks: one batch; linked blocks: one chain through the segment-parallel engine, hash table carried in and out),
+and an `update()` decodes every complete block it holds in one frame call (jump decoder for linked data).  The emitted pieces
+are byte-identical to flushing block by block.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import api
+
+MAX_WINDOW_SIZE = 65536
+BLOCK_MAX_SIZES = {4: 65536, 5: 262144, 6: 1048576, 7: 4194304}
+
+
+def _block_id(nbytes):                       # lz4Encode.js:337-343
+    if not nbytes or nbytes <= 65536:
+        return 4
+    if nbytes <= 262144:
+        return 5
+    if nbytes <= 1048576:
+        return 6
+    return 7
+
+
+def _u32(v):
+    return int(v & 0xFFFFFFFF).to_bytes(4, "little")
+
+
+def _jenkins_slots(buf):
+    """lz4Encode.js:155-167: table[JENKINS(seq_i)] = i + 1 for ascending i (the last writer of a slot wins)."""
+    n = buf.size
+    table = np.zeros(16384, dtype=np.int32)
+    if n < 4:
+        return table
+    b = buf.astype(np.uint32)
+    h = b[:n - 3] | (b[1:n - 2] << 8) | (b[2:n - 1] << 16) | (b[3:] << 24)
+    with np.errstate(over="ignore"):
+        h = h + np.uint32(2127912214) + (h << np.uint32(12))
+        h = h ^ np.uint32(3345072700) ^ (h >> np.uint32(19))
+        h = h + np.uint32(374761393) + (h << np.uint32(5))
+        h = (h + np.uint32(3550635116)) ^ (h << np.uint32(9))
+        h = h + np.uint32(4251993797) + (h << np.uint32(3))
+        h = h ^ np.uint32(3042594569) ^ (h >> np.uint32(16))
+    slot = (h >> np.uint32(18)) & np.uint32(16383)
+    table[slot] = np.arange(1, n - 2, dtype=np.int32)          # ascending assignment: the highest i per slot stays
+    return table
+
+
+def create_frame_header(block_independence, content_checksum, bd_id, dict_id, ctx=None):
+    """lz4Encode.js:61-94 (no content size in stream frames; a dictId of 0 counts as absent, `if (dictId)`)."""
+    flg = 1 << 6
+    if block_independence:
+        flg |= 0x20
+    if content_checksum:
+        flg |= 0x04
+    if dict_id:
+        flg |= 0x01
+    body = bytes([flg, (bd_id & 7) << 4]) + (_u32(dict_id) if dict_id else b"")
+    hc = (api.xxHash32(body, 0, ctx=ctx) >> 8) & 0xFF
+    return _u32(0x184D2204) + body + bytes([hc])
+
+
+class LZ4Encoder(object):
+    """new LZ4Encoder(maxBlockSize=4194304, blockIndependence=false, contentChecksum=false, dictionary=null)"""
+
+    def __init__(self, maxBlockSize=4194304, blockIndependence=False, contentChecksum=False, dictionary=None, ctx=None):
+        self._ctx = ctx or api.default_context()
+        self.blockIndependence = bool(blockIndependence)
+        self.contentChecksum = bool(contentChecksum)
+        self.blockSize = BLOCK_MAX_SIZES.get(_block_id(maxBlockSize), 4194304)
+        self.bdId = _block_id(self.blockSize)
+        self.buffer = np.zeros(0, dtype=np.uint8)
+        self.hasWrittenHeader = False
+        self.isClosed = False
+        self.hashTable = np.zeros(16384, dtype=np.int32)
+        self.dictSize = 0
+        self.hasher = api.XXHash32(0, ctx=self._ctx) if self.contentChecksum else None
+        self.dictId = None
+        if dictionary is not None and len(dictionary) > 0:
+            d = api.ensureBuffer(dictionary)
+            self.dictId = api.xxHash32(d, 0, ctx=self._ctx)
+            window = d[max(0, d.size - MAX_WINDOW_SIZE):]                    # _initDictionary, :140-168
+            self.buffer = window.copy()
+            self.dictSize = int(window.size)
+            self.hashTable = _jenkins_slots(self.buffer)
+
+    # ---- add / finish ---------------------------------------------------------------------------------------------
+    def add(self, chunk):
+        if self.isClosed:
+            raise RuntimeError("Stream is closed")
+        data = api.ensureBuffer(chunk)
+        if data.size == 0:
+            return []
+        if self.hasher:
+            self.hasher.update(data)
+        self.buffer = np.concatenate([self.buffer, data])
+        results = []
+        if not self.hasWrittenHeader:
+            results.append(create_frame_header(self.blockIndependence, self.contentChecksum, self.bdId, self.dictId, self._ctx))
+            self.hasWrittenHeader = True
+        full = (self.buffer.size - self.dictSize) // self.blockSize             # `while (buffer.length >= dictSize + blockSize)`
+        if full:
+            results.extend(self._flush_blocks(full * self.blockSize))
+        return results
+
+    def finish(self):
+        if self.isClosed:
+            return []
+        self.isClosed = True
+        frames = []
+        if not self.hasWrittenHeader:
+            frames.append(create_frame_header(self.blockIndependence, self.contentChecksum, self.bdId, self.dictId, self._ctx))
+        rest = self.buffer.size - self.dictSize
+        if rest > 0:
+            frames.extend(self._flush_blocks(rest))                              # full blocks, then the final short one
+        frames.append(_u32(0))
+        if self.hasher:
+            frames.append(_u32(self.hasher.digest()))
+        return frames
+
+    # ---- _flushBlock over `total` pending bytes at once (:215-298) -------------------------------------------------
+    def _flush_blocks(self, total):
+        bs = self.blockSize
+        start = self.dictSize
+        n = (total + bs - 1) // bs
+        lens = [min(bs, total - k * bs) for k in range(n)]
+        if self.blockIndependence:
+            # table cleared before every block (:240-242): fresh independent blocks, the dictionary prefix is never referenced
+            off = (np.arange(n, dtype=np.uint64) * bs) + np.uint64(start)
+            ln = np.array(lens, dtype=np.uint32)
+            dst, doff, clen = api.compress_blocks(self.buffer, off, ln, ctx=self._ctx)
+            comp = [dst[int(doff[k]):int(doff[k]) + int(clen[k])] for k in range(n)]
+            self.hashTable[:] = 0                                                # what the last block's fill(0) + parse leaves is not
+            self._table_stale = True                                             # observable: the next flush clears it again
+        else:
+            comp = api.chain_compress(self.buffer, start, total, bs, self.hashTable, ctx=self._ctx)
+        out = []
+        for k in range(n):
+            raw = self.buffer[start + k * bs:start + k * bs + lens[k]]
+            c = comp[k]
+            if 0 < c.size < lens[k]:                                             # :263-273 stored-block rule
+                out.append(_u32(c.size) + c.tobytes())
+            else:
+                out.append(_u32(lens[k] | 0x80000000) + raw.tobytes())
+        consumed_end = start + total
+        if not self.blockIndependence:
+            keep = min(consumed_end, MAX_WINDOW_SIZE)                             # :276-296 slide the window, rebase the table
+            shift = consumed_end - keep
+            self.buffer = self.buffer[shift:].copy()
+            self.dictSize = keep
+            t = self.hashTable
+            self.hashTable = np.where(t > shift, t - shift, 0).astype(np.int32)
+        else:
+            self.buffer = self.buffer[consumed_end:].copy()
+            self.dictSize = 0
+        return out
+
+
+class LZ4Decoder(object):
+    """new LZ4Decoder(dictionary=null, verifyChecksum=true); update(chunk) -> list of decoded chunks (one per block)."""
+
+    def __init__(self, dictionary=None, verifyChecksum=True, ctx=None):
+        self._ctx = ctx or api.default_context()
+        self.dictionary = api.ensureBuffer(dictionary) if dictionary is not None and len(dictionary) > 0 else None
+        self.verifyChecksum = bool(verifyChecksum)
+        self.state = "magic"
+        self.buffer = b""
+        self.hasher = None
+        self.window = np.zeros(0, dtype=np.uint8)
+        if self.dictionary is not None:
+            self.window = self.dictionary[max(0, self.dictionary.size - MAX_WINDOW_SIZE):].copy()   # _initWindow
+        self.blockIndependence = True
+        self.hasBlockChecksum = self.hasContentChecksum = self.hasContentSize = self.hasDictId = False
+        self._bd = 0x70
+
+    def update(self, chunk):
+        self.buffer += bytes(api.ensureBuffer(chunk).tobytes())
+        output = []
+        while True:
+            if self.state == "magic":                                            # lz4Decode.js:118-131
+                if len(self.buffer) < 4:
+                    break
+                if int.from_bytes(self.buffer[:4], "little") != 0x184D2204:
+                    raise api.LZ4Error(api.E_BAD_MAGIC, "LZ4: Invalid Magic Number")
+                self.buffer = self.buffer[4:]
+                self.state = "header"
+                self.hasher = api.XXHash32(0, ctx=self._ctx) if self.verifyChecksum else None
+            if self.state == "header":                                           # :134-178
+                if len(self.buffer) < 2:
+                    break
+                flg = self.buffer[0]
+                self.blockIndependence = bool(flg & 0x20)
+                self.hasBlockChecksum = bool(flg & 0x10)
+                self.hasContentSize = bool(flg & 0x08)
+                self.hasContentChecksum = bool(flg & 0x04)
+                self.hasDictId = bool(flg & 0x01)
+                need = 2 + (8 if self.hasContentSize else 0) + (4 if self.hasDictId else 0) + 1
+                if len(self.buffer) < need:
+                    break
+                self._bd = self.buffer[1]
+                if self.hasDictId:
+                    cur = 2 + (8 if self.hasContentSize else 0)
+                    expected = int.from_bytes(self.buffer[cur:cur + 4], "little")
+                    if self.dictionary is None:
+                        raise api.LZ4Error(api.E_DICT_OOB, "LZ4: Archive requires a Dictionary, but none was provided.")
+                    actual = api.xxHash32(self.dictionary, 0, ctx=self._ctx)
+                    if actual != expected:
+                        raise api.LZ4Error(api.E_DICT_OOB, "LZ4: Dictionary ID Mismatch. Header: 0x%x, Provided: 0x%x" % (expected, actual))
+                self.buffer = self.buffer[need:]
+                self.state = "blocks"
+            if self.state == "blocks":                                           # :181-243, every complete block at once
+                blocks, pos, end_mark = [], 0, False
+                while True:
+                    if len(self.buffer) - pos < 4:
+                        break
+                    val = int.from_bytes(self.buffer[pos:pos + 4], "little")
+                    if val == 0:
+                        pos += 4
+                        end_mark = True
+                        break
+                    size = val & 0x7FFFFFFF
+                    need = size + (4 if self.hasBlockChecksum else 0)
+                    if len(self.buffer) - pos - 4 < need:
+                        break
+                    blocks.append((val, self.buffer[pos + 4:pos + 4 + size]))
+                    pos += 4 + need
+                if blocks:
+                    output.extend(self._decode(blocks))
+                self.buffer = self.buffer[pos:]
+                if not end_mark:
+                    break
+                self.state = "checksum"
+            if self.state == "checksum":                                         # :246-266
+                if self.hasContentChecksum:
+                    if len(self.buffer) < 4:
+                        break
+                    if self.verifyChecksum and self.hasher:
+                        if int.from_bytes(self.buffer[:4], "little") != self.hasher.digest():
+                            raise api.LZ4Error(api.E_CONTENT_CHECKSUM, "LZ4: Content Checksum Error")
+                    self.buffer = self.buffer[4:]
+                self.state = "magic"
+                self.hasher = None
+                if len(self.buffer) == 0:
+                    break
+        return output
+
+    def _decode(self, blocks):
+        """All blocks of one update() as a synthetic frame: linked blocks see window ++ earlier output (:215-222,:240)."""
+        flg = (1 << 6) | (0x20 if self.blockIndependence else 0)
+        body = bytes([flg, self._bd])
+        hdr = _u32(0x184D2204) + body + bytes([(api.xxHash32(body, 0, ctx=self._ctx) >> 8) & 0xFF])
+        frame = hdr + b"".join(_u32(v) + d for v, d in blocks) + _u32(0)
+        f = np.frombuffer(frame, dtype=np.uint8)
+        bmax = BLOCK_MAX_SIZES.get((self._bd >> 4) & 7, 4194304)
+        out = np.empty(len(blocks) * bmax + 16, dtype=np.uint8)
+        n = C.c_uint64(0)
+        olen = np.zeros(len(blocks), dtype=np.uint32)
+        hist = self.window if (not self.blockIndependence and self.window.size) else None
+        st = api.lib().dlz4_frame_decompress_ex(self._ctx.handle, api._ptr(f), f.size, api._ptr(hist), hist.size if hist is not None else 0, 0,
+                                                api._ptr(out), out.size - 16, C.byref(n), api._ptr(olen))
+        self._ctx.check(st)
+        chunks, p = [], 0
+        for k in range(len(blocks)):
+            chunks.append(out[p:p + int(olen[k])].tobytes())
+            p += int(olen[k])
+        decoded = out[:p]
+        if self.hasher and p:
+            self.hasher.update(decoded)
+        if not self.blockIndependence and p:                                     # _updateWindow, :278-304: the last 64 KiB
+            self.window = np.concatenate([self.window, decoded])[-MAX_WINDOW_SIZE:].copy()
+        return chunks

@@ -172,11 +172,51 @@ typedef struct dlz4_frame_info_t {
     uint8_t  flg, bd, has_content_size, has_content_checksum, has_block_checksum, has_dict_id, block_independence, pad;
     uint32_t dict_id;
     int32_t  version;
+    uint64_t frame_bytes;         /* bytes of this frame: header .. EndMark [content checksum] */
 } dlz4_frame_info_t;
 int dlz4_frame_info(const uint8_t *frame, uint64_t frame_len, dlz4_frame_info_t *info);
 int dlz4_frame_decompress(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_len, const uint8_t *dictionary,
                           uint64_t dict_len, uint32_t flags, uint8_t *output, uint64_t output_cap,
                           uint64_t *output_len);
+
+/* a buffer of several concatenated frames (what `cat a.lz4 b.lz4` or the lz4 CLI with several inputs produces) with
+ * skippable frames (magic 0x184D2A50..5F, u32 size, payload) between them.  bufferDecompress.js:51-220 stops at the first
+ * EndMark; the reference's stream decoder loops over frames (src/shared/lz4Decode.js:262-266).  Decodes every LZ4 frame in
+ * order into `output` (same flags as dlz4_frame_decompress), skips skippable frames, and reports how many frames it decoded.
+ * Trailing bytes that are not a frame are DLZ4_E_BAD_MAGIC.
+ */
+int dlz4_frames_decompress(dlz4_ctx *ctx, const uint8_t *data, uint64_t data_len, const uint8_t *dictionary, uint64_t dict_len,
+                           uint32_t flags, uint8_t *output, uint64_t output_cap, uint64_t *output_len, uint32_t *frames);
+/* Sum of the decoded-size bounds of all LZ4 frames in `data` (to size `output`), and their count. */
+int dlz4_frames_info(const uint8_t *data, uint64_t data_len, uint64_t *max_decoded, uint32_t *frames);
+
+/* SURVEY 8 f1 (streaming codec, src/shared/lz4Encode.js / lz4Decode.js) -- the two pieces the stream classes need below them.
+ *
+ * Stateful xxh32 (the reference's XXHash32 class, update()/digest()): the stripe loop runs on the GPU with the four
+ * accumulators carried in `v`; the host keeps the < 16-byte tail and finishes the digest (merge + tail + avalanche).
+ */
+typedef struct dlz4_xxh32_state {
+    uint32_t v[4];
+    uint64_t total;
+    uint8_t  mem[16];
+    uint32_t memsize;
+    uint32_t seed;
+} dlz4_xxh32_state;
+void dlz4_xxh32_reset(dlz4_xxh32_state *s, uint32_t seed);
+int dlz4_xxh32_update(dlz4_ctx *ctx, dlz4_xxh32_state *s, const uint8_t *data, uint64_t len);
+uint32_t dlz4_xxh32_digest(const dlz4_xxh32_state *s);
+/* LZ4Encoder._flushBlock for every full block of an add() at once (lz4Encode.js:215-298, linked mode): blocks of
+ * block_size tile work[start, start + total), history is work[0, start), `table` (int32[16384], position + 1 in `work`) is
+ * the carried state, read and written.  Block k's bytes go to dst + k * dst_stride, its size to comp_len[k].  Long runs take
+ * the segment-parallel engine; the table returned is the serial loop's. */
+int dlz4_chain_compress(dlz4_ctx *ctx, const uint8_t *work, uint64_t work_len, int32_t start, int32_t total, int32_t block_size,
+                        int32_t *table, uint8_t *dst, uint64_t dst_stride, uint32_t *comp_len);
+
+/* dlz4_frame_decompress that also reports every block's decoded length (block_out_len[nblocks], nullable): the stream
+ * decoder hands out one chunk per block like LZ4Decoder.update (lz4Decode.js:206-245). */
+int dlz4_frame_decompress_ex(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_len, const uint8_t *dictionary,
+                             uint64_t dict_len, uint32_t flags, uint8_t *output, uint64_t output_cap, uint64_t *output_len,
+                             uint32_t *block_out_len);
 
 /* Device-resident frame assembly used by the sharded path: given the per-block compressed
  * lengths and the worst-case-strided scratch produced by dlz4_compress_blocks_dev, writes

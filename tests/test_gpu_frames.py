@@ -138,3 +138,32 @@ def test_gpu_frames_decode_in_liblz4(dl):
         for indep in (False, True):
             f = _gpu_frame(dl, data, None, bs, indep, True, True, True)
             assert lz4f.decompress_frame(f, len(data)) == data
+
+
+def test_concatenated_and_skippable_frames(dl):
+    """`cat a.lz4 b.lz4`, skippable frames between them (LZ4 frame spec); decompressBuffer itself keeps the reference's
+    one-frame behaviour (bufferDecompress.js stops at the first EndMark)."""
+    import struct
+    from divortio_lz4_b200 import corpus
+    a = corpus.log(61, 300000).tobytes()
+    b = corpus.mixed(62, 700001).tobytes()
+    c = b""
+    fa = oracle.compress_buffer(a, None, 65536, True, True, True)
+    fb = oracle.compress_buffer(b, None, 4194304, False, True, False)          # linked, no content size -> jump decoder
+    fc = oracle.compress_buffer(c)
+    skip = struct.pack("<II", 0x184D2A53, 11) + b"hello world"
+    cat = skip + fa + skip + skip + fb + fc + skip
+    out, count = dl.decompressFrames(cat, None, True)
+    assert count == 3 and out == a + b + c
+    assert dl.decompressBuffer(fa + fb) == a                                     # reference behaviour: first frame only
+    import lz4f
+    if lz4f.available():
+        cat2 = lz4f.compress_frame(a, 4, True, True, False, True) + lz4f.compress_frame(b, 7, False, True, True, False)
+        out2, count2 = dl.decompressFrames(cat2, None, True, True)
+        assert count2 == 2 and out2 == a + b
+    with pytest.raises(dl.LZ4Error, match="Invalid Magic"):
+        dl.decompressFrames(fa + b"\x01\x02\x03\x04\x05")
+    bad = bytearray(fa + fb)
+    bad[-1] ^= 0x55                                                              # second frame's content checksum
+    with pytest.raises(dl.LZ4Error, match="Content Checksum"):
+        dl.decompressFrames(bytes(bad))
