@@ -445,12 +445,22 @@ def chain_compress(work, start, total, block_size, table, ctx=None):
 
 
 class _LZ4(object):
-    """The reference's facade object (src/lz4.js:27-66), hot-path members only."""
+    """The reference's facade object (src/lz4.js:27-66): block / buffer members, the stream classes and the worker offload."""
     compressRaw = staticmethod(compressBlock)
     decompressRaw = staticmethod(decompressBlock)
     compress = staticmethod(compressBuffer)
     decompress = staticmethod(decompressBuffer)
     xxHash32 = staticmethod(xxHash32)
+
+    @staticmethod
+    def compressWorker(data, options=None):                    # src/lz4.js:54
+        from .worker import LZ4Worker
+        return LZ4Worker.compress(data, options)
+
+    @staticmethod
+    def decompressWorker(data, options=None):                  # src/lz4.js:55
+        from .worker import LZ4Worker
+        return LZ4Worker.decompress(data, options)
 
 
 LZ4 = _LZ4()

@@ -108,3 +108,20 @@ def test_stateful_xxh32_matches_one_shot(st):
     assert dl.XXHash32(0).update(b"Hello World").digest() == 0xB1FD16EE         # :20
     ref = bytes((i * 31 + 17) & 0xFF for i in range(1024))                     # xxhash32Stateful.test.mjs:29-46
     assert dl.XXHash32(7).update(ref[:100]).update(ref[100:]).digest() == oracle.xxh32(ref, 7)
+
+
+def test_worker_offload_returns_futures_with_the_sync_results(st):
+    """LZ4.compressWorker / decompressWorker (src/webWorker/workerClient.js:114-152) -- one off-thread worker."""
+    import divortio_lz4_b200 as dl
+    data = _data("log", 2 * 1024 * 1024 + 9)
+    futs = [dl.LZ4.compressWorker(data, {"maxBlockSize": bs, "blockIndependence": ind, "contentChecksum": True})
+            for bs, ind in ((65536, True), (4194304, False), (262144, True))]
+    want = [oracle.compress_buffer(data, None, bs, ind, True) for bs, ind in ((65536, True), (4194304, False), (262144, True))]
+    assert dl.compressBuffer(data, None, 65536, True, True) == want[0]        # the caller's own context stays usable meanwhile
+    got = [f.result(timeout=120) for f in futs]
+    assert got == want
+    backs = [dl.LZ4.decompressWorker(g, {"verifyChecksum": True}) for g in got]
+    assert all(b.result(timeout=120) == data for b in backs)
+    bad = bytearray(got[0]); bad[-1] ^= 1
+    with pytest.raises(dl.LZ4Error, match="Content Checksum Error"):
+        dl.LZ4.decompressWorker(bytes(bad)).result(timeout=120)
