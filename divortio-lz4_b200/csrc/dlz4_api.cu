@@ -278,9 +278,9 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
     uint32_t *counter = ctx->d_counter + 8;
     auto launch = [&](const uint32_t *list, uint32_t count) -> int {
         CK(cudaMemsetAsync(counter, 0, 4, st));
-        const int grid = (int)std::min<uint64_t>(count, (uint64_t)ctx->sm_count * 4);
+        const int grid = (int)std::min<uint64_t>(count, (uint64_t)ctx->sm_count * kSegCtasPerSm);
         const uint32_t active = (uint32_t)std::min<uint64_t>((count + grid - 1) / grid, (uint64_t)kSegWarps);
-        k_compress_segments<<<grid, kSegWarps * 32, kSegWarps * kRingBytes, st>>>(d_work, d_jobs, list, count, (int32_t)B, init_table, d_tab, d_snap,
+        k_compress_segments<<<grid, kSegWarps * 32, kSegSmemBytes, st>>>(d_work, d_jobs, list, count, (int32_t)B, init_table, d_tab, d_snap,
                                                                                   d_ss, d_es, d_buf, bstride, d_poff, d_plen, counter, active);
         ctx->launches++;
         CK(cudaGetLastError());
@@ -493,6 +493,7 @@ int dlz4_init(int device, dlz4_ctx **out) {
     CK(cudaMalloc(&ctx->d_gtabs, (size_t)kGtabRegions * ctx->hy_grid * kHyGlWarps * kHashEntries * 2));
     CK(cudaFuncSetAttribute(k_compress_fresh16h, cudaFuncAttributeMaxDynamicSharedMemorySize, kHySmemBytes));
     CK(cudaFuncSetAttribute(k_compress_overlay, cudaFuncAttributeMaxDynamicSharedMemorySize, kHySmemBytes));
+    CK(cudaFuncSetAttribute(k_compress_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, kSegSmemBytes));
     CK(cudaFuncSetAttribute(k_compress_generic32<kWarpsGeneric32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kWarpsGeneric32 * (kHashEntries * 4 + kRingBytes)));
     CK(cudaFuncSetAttribute(k_compress_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kHashEntries * 4 + kRingBytes));

@@ -867,8 +867,8 @@ struct SegState { int32_t s, head; };    // next probe position (== anchor, sear
 // sequences over n >= 4 source bytes takes at most n + n/255 bytes)
 __device__ __host__ __forceinline__ uint64_t seg_piece_offset(uint64_t x) { return x + (x >> 3); }
 
-template <bool kEmit>
-__device__ __forceinline__ void seg_run(const uint8_t *__restrict__ base, const SegJob &J, int32_t block_size, TabG32 &T,
+template <class Tab, bool kEmit>
+__device__ __forceinline__ void seg_run(const uint8_t *__restrict__ base, const SegJob &J, int32_t block_size, Tab &T,
                                         uint32_t *ring, SegState &S, int32_t limit, uint8_t *blockbuf, uint64_t blockbuf_stride,
                                         uint32_t *piece_off, uint32_t *piece_len, int32_t stop_fresh_at) {
     // Runs blocks from state S until a span stops at `limit` (S = hand-over state) or a fresh block start >= stop_fresh_at
@@ -889,18 +889,73 @@ __device__ __forceinline__ void seg_run(const uint8_t *__restrict__ base, const 
             const uint32_t slot = J.first_slot + (uint32_t)(bi - bfirst);
             const uint32_t off = (uint32_t)seg_piece_offset((uint64_t)(S.s - bstart));
             uint8_t *out = blockbuf + (uint64_t)(J.first_block + (uint32_t)(bi - bfirst)) * blockbuf_stride + off;
-            r = compress_span_warp<TabG32, true>(base, bstart, blen, T, out, ring, st, limit);
+            r = compress_span_warp<Tab, true>(base, bstart, blen, T, out, ring, st, limit);
             if (lane == 0) { piece_off[slot] = off; piece_len[slot] = r == kSpanStopped ? st.D : r; }
         } else {
-            r = compress_span_warp<TabG32, false>(base, bstart, blen, T, nullptr, ring, st, limit);
+            r = compress_span_warp<Tab, false>(base, bstart, blen, T, nullptr, ring, st, limit);
         }
         if (r == kSpanStopped) { S.s = st.sIndex; S.head = st.head; break; }
         S.s = bstart + blen; S.head = -1;                        // block finished: the next one starts fresh (table carried)
     }
 }
 
-constexpr int kSegWarps = 7;
-__global__ void __launch_bounds__(kSegWarps * 32, 4)
+// One segment by one warp.  kSmem: the live table is in shared memory (twice as fast a chain; 3 per SM) and is written to
+// tables[j] at the end, where the verification and a re-run of the successor read it; otherwise tables[j] itself is live.
+template <class Tab, bool kSmem>
+__device__ __forceinline__ void seg_job(const uint8_t *__restrict__ base, const SegJob &J, uint32_t j, int32_t block_size,
+                                        const int32_t *__restrict__ init_table, int32_t *live, int32_t *tables, int32_t *snaps,
+                                        SegState *snap_state, SegState *end_state, uint8_t *blockbuf, uint64_t blockbuf_stride,
+                                        uint32_t *piece_off, uint32_t *piece_len, uint32_t *ring) {
+    const uint32_t lane = lane_id();
+    uint4 *l4 = reinterpret_cast<uint4 *>(live);
+    auto put = [&](uint32_t i, const uint4 &v) { if (kSmem) l4[i] = v; else __stcg(l4 + i, v); };
+    auto get = [&](uint32_t i) -> uint4 { return kSmem ? l4[i] : __ldcg(l4 + i); };
+    constexpr uint32_t kVec = kHashEntries * 4 / 16;
+    Tab T{live};
+    SegState S;
+    if (J.flags & kSegRerun) {
+        // exact start: the predecessor's end state (its table buffer is final, nobody writes it during this launch)
+        const uint4 *p4 = reinterpret_cast<const uint4 *>(tables + (size_t)(j - 1) * kHashEntries);
+        uint4 *s4 = reinterpret_cast<uint4 *>(snaps + (size_t)j * kHashEntries);
+        for (uint32_t i = lane; i < kVec; i += 32) { const uint4 v = __ldcg(p4 + i); put(i, v); __stcg(s4 + i, v); }
+        S = end_state[j - 1];
+        if (lane == 0) snap_state[j] = S;                        // the start is now exact as long as the predecessor's end stands
+        __syncwarp();
+    } else if (J.flags & kSegFirst) {
+        if (init_table && j == 0) {
+            const uint4 *i4 = reinterpret_cast<const uint4 *>(init_table);
+            for (uint32_t i = lane; i < kVec; i += 32) put(i, i4[i]);
+        } else {
+            for (uint32_t i = lane; i < kVec; i += 32) put(i, make_uint4(0, 0, 0, 0));
+        }
+        S.s = J.seg_begin; S.head = -1;
+        __syncwarp();
+    } else {
+        for (uint32_t i = lane; i < kVec; i += 32) put(i, make_uint4(0, 0, 0, 0));
+        __syncwarp();
+        S.s = J.warm_begin; S.head = -1;
+        seg_run<Tab, false>(base, J, block_size, T, ring, S, J.seg_begin, nullptr, 0, nullptr, nullptr, J.seg_begin);
+        __syncwarp();
+        uint4 *s4 = reinterpret_cast<uint4 *>(snaps + (size_t)j * kHashEntries);
+        for (uint32_t i = lane; i < kVec; i += 32) __stcg(s4 + i, get(i));
+        if (lane == 0) snap_state[j] = S;
+    }
+    const bool last = (J.flags & kSegLast) != 0;
+    seg_run<Tab, true>(base, J, block_size, T, ring, S, last ? INT_MAX : J.seg_end, blockbuf, blockbuf_stride, piece_off, piece_len,
+                       last ? INT_MAX : J.seg_end);
+    if (lane == 0) end_state[j] = S;
+    __syncwarp();
+    if (kSmem) {
+        uint4 *t4 = reinterpret_cast<uint4 *>(tables + (size_t)j * kHashEntries);
+        for (uint32_t i = lane; i < kVec; i += 32) __stcg(t4 + i, l4[i]);
+        __syncwarp();
+    }
+}
+
+constexpr int kSegWarps = 7;                       // warp 0: shared-memory table (64 KiB), warps 1..6: tables in L2
+constexpr int kSegCtasPerSm = 3;
+constexpr int kSegSmemBytes = kHashEntries * 4 + kSegWarps * kRingBytes;
+__global__ void __launch_bounds__(kSegWarps * 32, kSegCtasPerSm)
 k_compress_segments(const uint8_t *__restrict__ base, const SegJob *__restrict__ jobs, const uint32_t *__restrict__ job_list,
                     uint32_t njobs, int32_t block_size, const int32_t *__restrict__ init_table /* nullable: chain 0 */,
                     int32_t *tables, int32_t *snaps, SegState *snap_state, SegState *end_state,
@@ -909,7 +964,7 @@ k_compress_segments(const uint8_t *__restrict__ base, const SegJob *__restrict__
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     if (warp >= active_warps) return;
-    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + warp * kRingBytes);
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + kHashEntries * 4 + warp * kRingBytes);
     for (;;) {
         const uint32_t q = next_block(counter, lane);
         if (q >= njobs) break;
@@ -920,42 +975,12 @@ k_compress_segments(const uint8_t *__restrict__ base, const SegJob *__restrict__
             const uint32_t nslots = (uint32_t)((last_pos - J.chain_start) / block_size - (J.seg_begin - J.chain_start) / block_size) + 1u;
             for (uint32_t i = lane; i < nslots; i += 32) piece_len[J.first_slot + i] = 0;
         }
-        int32_t *tab = tables + (size_t)j * kHashEntries;
-        uint4 *t4 = reinterpret_cast<uint4 *>(tab);
-        TabG32 T{tab};
-        SegState S;
-        if (J.flags & kSegRerun) {
-            // exact start: the predecessor's end state (its table buffer is final, nobody writes it during this launch)
-            const uint4 *p4 = reinterpret_cast<const uint4 *>(tables + (size_t)(j - 1) * kHashEntries);
-            uint4 *s4 = reinterpret_cast<uint4 *>(snaps + (size_t)j * kHashEntries);
-            for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) { const uint4 v = __ldcg(p4 + i); __stcg(t4 + i, v); __stcg(s4 + i, v); }
-            S = end_state[j - 1];
-            if (lane == 0) snap_state[j] = S;                    // the start is now exact as long as the predecessor's end stands
-            __syncwarp();
-        } else if (J.flags & kSegFirst) {
-            if (init_table && j == 0) {
-                const uint4 *i4 = reinterpret_cast<const uint4 *>(init_table);
-                for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) __stcg(t4 + i, i4[i]);
-            } else {
-                for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) __stcg(t4 + i, make_uint4(0, 0, 0, 0));
-            }
-            S.s = J.seg_begin; S.head = -1;
-            __syncwarp();
-        } else {
-            for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) __stcg(t4 + i, make_uint4(0, 0, 0, 0));
-            __syncwarp();
-            S.s = J.warm_begin; S.head = -1;
-            seg_run<false>(base, J, block_size, T, ring, S, J.seg_begin, nullptr, 0, nullptr, nullptr, J.seg_begin);
-            __syncwarp();
-            uint4 *s4 = reinterpret_cast<uint4 *>(snaps + (size_t)j * kHashEntries);
-            for (uint32_t i = lane; i < kHashEntries * 4 / 16; i += 32) __stcg(s4 + i, __ldcg(t4 + i));
-            if (lane == 0) snap_state[j] = S;
-        }
-        const bool last = (J.flags & kSegLast) != 0;
-        seg_run<true>(base, J, block_size, T, ring, S, last ? INT_MAX : J.seg_end, blockbuf, blockbuf_stride, piece_off, piece_len,
-                      last ? INT_MAX : J.seg_end);
-        if (lane == 0) end_state[j] = S;
-        __syncwarp();
+        if (warp == 0)
+            seg_job<Tab32, true>(base, J, j, block_size, init_table, reinterpret_cast<int32_t *>(smem), tables, snaps, snap_state, end_state,
+                                 blockbuf, blockbuf_stride, piece_off, piece_len, ring);
+        else
+            seg_job<TabG32, false>(base, J, j, block_size, init_table, tables + (size_t)j * kHashEntries, tables, snaps, snap_state,
+                                   end_state, blockbuf, blockbuf_stride, piece_off, piece_len, ring);
     }
 }
 
