@@ -2092,9 +2092,20 @@ k_xxh32_stream(const uint8_t *__restrict__ data, uint64_t len, uint32_t seed, ui
             }
             __syncwarp();
             if (lane < 4) {
+                // v' = rotl(v + x*P2, 13) * P1 is three dependent operations per stripe.  With a = v + x*P2 and
+                // rotl(a,13) = (a << 13) + (a >> 19):  a' = (a >> 19)*P1 + (a*(P1 << 13) + x'*P2) -- the shift and the
+                // second multiply-add run side by side, two dependent operations per stripe.
                 const uint32_t *w = buf[c & 1] + lane;
+                constexpr uint32_t K1 = P32_1 << 13;
+                uint32_t a = v + w[0] * P32_2;
 #pragma unroll 16
-                for (int t = 0; t < 256; ++t) v = xxh_round(v, w[t * 4]);
+                for (int t = 1; t < 256; ++t) {
+                    const uint32_t y = w[t * 4] * P32_2;
+                    uint32_t c;                                 // fixed association (nvcc would re-order the sum into three links)
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(c) : "r"(a), "r"(K1), "r"(y));
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(a >> 19), "r"(P32_1), "r"(c));
+                }
+                v = rotl32(a, 13) * P32_1;
             }
             __syncwarp();
         }
