@@ -2024,8 +2024,17 @@ __device__ __forceinline__ uint32_t xxh32_quad(const uint8_t *p, uint32_t len, u
                 uint32_t x[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) x[u] = w[(s + u) * 4];
+                // eight stripes with two dependent operations each (see k_xxh32_stream): a' = (a >> 19)*P1 + (a*(P1 << 13) + x'*P2)
+                constexpr uint32_t K1 = P32_1 << 13;
+                uint32_t acc = v + x[0] * P32_2;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v = xxh_round(v, x[u]);
+                for (int u = 1; u < 8; ++u) {
+                    const uint32_t y = x[u] * P32_2;
+                    uint32_t c;
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(c) : "r"(acc), "r"(K1), "r"(y));
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(acc >> 19), "r"(P32_1), "r"(c));
+                }
+                v = rotl32(acc, 13) * P32_1;
             }
             for (; s < nstripes; ++s) v = xxh_round(v, w[s * 4]);
         } else {
