@@ -314,11 +314,11 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "kernel": "k_compress_fresh16h", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(ach / peak, 5),
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload, ncu --set full
-                         # (profiles/r01b_bench_compress_full.txt: 23.44 GB + 3.36 GB).  17x the algorithmic bytes: 28 block
+                         # (profiles/r01c_bench_compress_full.txt: 23.48 GB + 3.36 GB).  17x the algorithmic bytes: 28 block
                          # chains per SM keep 4144 x (64 KiB block + 32 KiB table) = 400 MB in flight, three times the L2,
                          # so candidate reads and table sectors miss to HBM.  The 7-chain kernel it replaced moved
                          # 1.53 GB (1.0x) at half the throughput -- DESIGN.md 4.1 has the trade.
-                         "traffic": 26806567000 if n == (1 << 30) else None,
+                         "traffic": 26842329000 if n == (1 << 30) else None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
                          "algorithmic_bytes_per_launch": n + csize},
             "detail": {"compress_gbs": round(args.steps * total / tc / 1e9, 3), "decompress_gbs": round(args.steps * total / td / 1e9, 3),

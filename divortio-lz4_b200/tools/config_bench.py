@@ -73,18 +73,7 @@ m = min(n, 256 << 20)
 t = timed(lambda: dev.xxh32_stream_dev(ctx, src[:m], one), reps=1)
 print("xxh32_stream (serial chain, one warp), %d MiB    %8.2f GB/s" % (m >> 20, m / t / 1e6))
 
-# frame API end to end (host pointers), config 3 options
-for bs, indep in ((4194304, True), (65536, True), (4194304, False)):
-    sub = host[:min(n, (256 << 20) if indep else (32 << 20))]
-    for cc in (False, True):
-        t0 = time.perf_counter()
-        f = dl.compressBuffer(sub, None, bs, indep, cc, True, None, True, ctx=ctx)
-        t1 = time.perf_counter()
-        back = dl.decompressBuffer(f, None, True, True, ctx=ctx)
-        t2 = time.perf_counter()
-        assert back == sub.tobytes()
-        print("frame API e2e %3d MiB block %7d %s contentChecksum=%d: compress %6.2f GB/s (kernels %.1f ms) | decompress %6.2f GB/s" %
-              (sub.size >> 20, bs, "independent" if indep else "linked     ", cc, sub.size / (t1 - t0) / 1e9, 0.0, sub.size / (t2 - t1) / 1e9), flush=True)
+# (the frame API is timed by tools/frame_bench.py: C ABI with pinned buffers, no Python copies)
 
 # config 4: small messages with a shared dictionary prefix
 msgs = corpus.jsonmsgs(4, 0, nmsg)
