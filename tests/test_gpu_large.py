@@ -113,3 +113,22 @@ def test_config5_shape_decode_reference_and_cli_frames_linked_and_independent(en
         linked.append(lz4f.compress_frame(small.tobytes(), 7, True, True, False, False))
     for f in linked:
         assert dl.decompressBuffer(f) == small.tobytes()
+
+
+def test_reference_default_frame_1gib_linked_blocks_byte_exact(env):
+    """The reference's default options on 1 GiB (blockIndependence=false, 4 MiB blocks): one serial chain in the reference, 2048
+    speculative segments here.  The frame must equal the oracle's byte for byte (checked through length and xxh32 of the whole
+    frame, and through the first difference if they differ), and the jump decoder must return the input."""
+    dl, corpus, dev, torch, ctx = env
+    n = 1 << 30
+    data = corpus.mixed(7, n)
+    f = dl.compressBuffer(data, None, 4194304, False, False, True, ctx=ctx)
+    segs, reruns, rounds = ctx.segment_stats
+    want = oracle.compress_buffer(data, None, 4194304, False, False, True)
+    assert len(f) == len(want)
+    if f != want:
+        a, b = np.frombuffer(f, dtype=np.uint8), np.frombuffer(want, dtype=np.uint8)
+        raise AssertionError("first difference at frame byte %d" % int(np.nonzero(a != b)[0][0]))
+    assert segs == 2048 and reruns <= 64, (segs, reruns, rounds)
+    back = dl.decompressBuffer(f, None, True, False, ctx=ctx)
+    assert len(back) == n and np.array_equal(np.frombuffer(back, dtype=np.uint8), data)
