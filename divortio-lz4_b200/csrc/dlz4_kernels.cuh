@@ -1435,7 +1435,8 @@ k_decompress_chain(const uint8_t *__restrict__ src, const uint64_t *__restrict__
 //     k_jd_emit   out[x] = ~P[x].
 // Units run in stream order, so a unit's sources in earlier units are final bytes.  Nothing here depends on how the
 // frame was parsed: the result is the byte-exact LZ4 decode whatever the dependency structure.
-struct JdSeq { uint32_t op, ip, lit, ml, off, pad0, pad1, pad2; };    // block-relative output / input positions
+struct JdSeq { uint32_t op, ip, lit, ml, off, m0, pad1, pad2; };      // block-relative output / input positions; m0 = first
+                                                                      // output byte of the WHOLE match (chunked records share it)
 constexpr int kJdHops = 4;                                             // pointer links followed per element per round
 constexpr uint32_t kJdChunk = 4096;                                    // long literal runs / matches are recorded in chunks
 
@@ -1447,11 +1448,12 @@ __device__ __forceinline__ void jd_emit_rec(JdSeq *rec, uint32_t &ns, uint32_t o
         ++ns; op += kJdChunk; ip += kJdChunk; lit -= kJdChunk;
     }
     uint32_t first = ml > kJdChunk ? kJdChunk : ml;
-    if (lane == 0) rec[ns] = JdSeq{op, ip, lit, first, off, 0u, 0u, 0u};
+    const uint32_t m0 = op + lit;
+    if (lane == 0) rec[ns] = JdSeq{op, ip, lit, first, off, m0, 0u, 0u};
     ++ns; op += lit + first; ml -= first;
     while (ml) {
         first = ml > kJdChunk ? kJdChunk : ml;
-        if (lane == 0) rec[ns] = JdSeq{op, 0u, 0u, first, off, 0u, 0u, 0u};
+        if (lane == 0) rec[ns] = JdSeq{op, 0u, 0u, first, off, m0, 0u, 0u};
         ++ns; op += first; ml -= first;
     }
 }
@@ -1596,7 +1598,7 @@ k_jd_scan(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
                 const uint32_t cut = bad | slowm;
                 const uint32_t good = cut ? (real & ((cut & (0u - cut)) - 1u)) : real;
                 if ((good >> lane) & 1u) {
-                    rec[ns + __popc(good & lt)] = JdSeq{myop, litp, lit, last ? 0u : ml, last ? 0u : offset, 0u, 0u, 0u};
+                    rec[ns + __popc(good & lt)] = JdSeq{myop, litp, lit, last ? 0u : ml, last ? 0u : offset, myop + lit, 0u, 0u};
                     if (!last) {
                         const int64_t src_rel = (int64_t)myop + lit - offset;                 // :142
                         if (src_rel < 0) atomicMax(&reach[b], (uint32_t)(-src_rel));
@@ -1874,7 +1876,7 @@ k_jdp_emit(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off
                 uint32_t ml = token & 15u;
                 if (ml == 15u) { uint32_t v; do { v = in[p++]; ml += v; } while (v == 255u); }
                 ml += 4;
-                rec[ns + __popc(real & lt)] = JdSeq{myop, litp, lit, ml, offset, 0u, 0u, 0u};
+                rec[ns + __popc(real & lt)] = JdSeq{myop, litp, lit, ml, offset, myop + lit, 0u, 0u};
                 const int64_t src_rel = (int64_t)myop + lit - offset;
                 if (src_rel < 0 && (uint32_t)(-src_rel) > rch) rch = (uint32_t)(-src_rel);
             }
@@ -1932,7 +1934,10 @@ k_jd_fill(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
             if (j < q.lit) {
                 v = ~(int32_t)in[q.ip + j];
             } else {
-                const int64_t sg = (int64_t)x - q.off;           // global source position
+                // a match longer than its offset repeats the `off` bytes in front of it: point every byte straight at them
+                // (a zero run of a whole block is then one link deep instead of a chain as long as the run)
+                const uint32_t dm = q.op + j - q.m0;             // distance into the whole match
+                const int64_t sg = dm < q.off ? (int64_t)x - q.off : (int64_t)bstart + q.m0 - q.off + (dm % q.off);   // global source
                 const int64_t sb = sg - (int64_t)bstart;         // relative to the block's start
                 if (sg >= (int64_t)ustart && (linked || sb >= 0)) {
                     v = (int32_t)(sg - (int64_t)ustart);         // inside the unit: resolve by doubling
