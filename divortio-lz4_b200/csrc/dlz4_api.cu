@@ -1448,14 +1448,14 @@ void dlz4_xxh32_reset(dlz4_xxh32_state *s, uint32_t seed) {
 
 int dlz4_xxh32_update(dlz4_ctx *ctx, dlz4_xxh32_state *s, const uint8_t *data, uint64_t len) {
     if (!ctx || !s || (len && !data)) return DLZ4_E_INVALID_ARG;
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
     s->total += len;
-    if (s->memsize + len < 16) {                                        // not a stripe yet
+    if (s->memsize + len < 16) {                                        // not a stripe yet: host-side buffering only
         memcpy(s->mem + s->memsize, data, (size_t)len);
         s->memsize += (uint32_t)len;
         return DLZ4_OK;
     }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
     // stripes = pending tail ++ data, cut at a multiple of 16; the rest becomes the new tail
     const uint64_t avail = s->memsize + len, body = avail & ~15ull, from_data = body - s->memsize;
     CKS(reserve(ctx, ctx->work, body + 64));

@@ -102,3 +102,46 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in text and "lz4_oracle" not in text and "from oracle" not in text, f
+
+
+def test_frames_info_walks_concatenated_and_skippable_frames_on_the_host():
+    """dlz4_frames_info is host-only (header parse + block walk): counts, bounds and errors without a GPU."""
+    import struct
+    import oracle
+    a, b = b"frame one " * 5000, bytes(range(256)) * 3000
+    fa = oracle.compress_buffer(a, None, 65536, True, True, True)
+    fb = oracle.compress_buffer(b, None, 4194304, False, False, False)          # no content size: bound from the block table
+    skip = struct.pack("<II", 0x184D2A5F, 5) + b"xxxxx"
+    L = api.lib()
+
+    def info(buf):
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        total, count = C.c_uint64(0), C.c_uint32(0)
+        st = L.dlz4_frames_info(arr.ctypes.data, arr.size, C.byref(total), C.byref(count))
+        return st, int(total.value), int(count.value)
+
+    st, total, count = info(skip + fa + skip + fb + skip)
+    assert st == 0 and count == 2 and total >= len(a) + len(b)
+    assert info(fa)[1:] == (len(a), 1)
+    assert info(fa + b"\x00\x01\x02\x03")[0] == api.E_BAD_MAGIC
+    assert info(fa[:-3])[0] != 0                                                  # truncated content checksum / EndMark
+    assert info(struct.pack("<II", 0x184D2A50, 100) + b"short")[0] != 0          # skippable frame longer than the buffer
+    fi = api.FrameInfo()
+    arr = np.frombuffer(fa + fb, dtype=np.uint8)
+    assert L.dlz4_frame_info(arr.ctypes.data, arr.size, C.byref(fi)) == 0 and fi.frame_bytes == len(fa)
+
+
+def test_stateful_xxh32_digest_of_short_inputs_needs_no_device():
+    """Below one 16-byte stripe dlz4_xxh32_update only buffers and dlz4_xxh32_digest finishes on the host (xxhash32.js:67-97)."""
+    import oracle
+    L = api.lib()
+    for seed in (0, 7):
+        for data in (b"", b"a", b"Hello World", b"123456789012345"):
+            s = api.Xxh32State()
+            L.dlz4_xxh32_reset(C.byref(s), seed)
+            for k in range(len(data)):                                            # byte by byte: never reaches a stripe
+                arr = np.frombuffer(data[k:k + 1], dtype=np.uint8)
+                # ctx is only dereferenced when a stripe is ready; a dummy non-null handle is never touched here
+                assert L.dlz4_xxh32_update(C.c_void_p(1), C.byref(s), arr.ctypes.data, 1) == 0
+            assert L.dlz4_xxh32_digest(C.byref(s)) == oracle.xxh32(data, seed)
+    assert L.dlz4_xxh32_digest(C.byref(s)) == oracle.xxh32(b"123456789012345", 7)
