@@ -189,8 +189,12 @@ int launch_decompress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off
     // frame history: a block may read what the blocks before it wrote, so ONE warp takes them in queue order (the parallel
     // route for linked data is the frame call's jump decoder)
     const int grid = hist_frame ? 1 : (int)std::min<uint64_t>((n + kWarpsDecode - 1) / kWarpsDecode, (uint64_t)ctx->sm_count * 8);
-    k_decompress_blocks<kWarpsDecode><<<grid, hist_frame ? 32 : kWarpsDecode * 32, 0, st>>>(src, src_off, src_len, n, dst, dst_off, dst_cap, dict,
-                                                                           dict_len, hist_frame, stored, out_len, status, counter);
+    if (dict_len)
+        k_decompress_blocks<kWarpsDecode, true><<<grid, hist_frame ? 32 : kWarpsDecode * 32, 0, st>>>(src, src_off, src_len, n, dst, dst_off, dst_cap,
+                                                                                                      dict, dict_len, hist_frame, stored, out_len, status, counter);
+    else
+        k_decompress_blocks<kWarpsDecode, false><<<grid, hist_frame ? 32 : kWarpsDecode * 32, 0, st>>>(src, src_off, src_len, n, dst, dst_off, dst_cap,
+                                                                                                       dict, dict_len, hist_frame, stored, out_len, status, counter);
     ctx->launches++;
     CK(cudaGetLastError());
     return DLZ4_OK;

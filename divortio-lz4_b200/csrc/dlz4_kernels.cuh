@@ -1250,8 +1250,9 @@ __device__ __forceinline__ bool dec_one_sequence(const uint8_t *__restrict__ in,
 // sequence.  So the warp speculates: lane l sizes the sequence that WOULD start at byte ip + l of the window, the warp hops from
 // lane 0 along the `next` links (two shuffles per real token) and the visited lanes -- the real tokens -- check themselves in
 // the reference's order (:74, :75, :128, ...).  Their copies then run in order, one sequence per step.  Tokens the window
-// cannot size (length runs of more than 3 bytes, dictionary sources, anything malformed) take dec_one_sequence, which is also
+// cannot size (length runs of more than 3 bytes, sources that straddle the dictionary, anything malformed) take dec_one_sequence, also
 // what decides every error, so the first error reported is the reference's.
+template <bool kDict>                       // kDict: a dictionary exists, matches that lie inside it take the window path too
 __device__ uint32_t decompress_block_warp_v2(const uint8_t *__restrict__ in, const uint32_t n, uint8_t *const ob,
                                              const uint32_t cap, const uint32_t hist, const uint8_t *__restrict__ dict,
                                              const uint32_t dict_len, uint32_t *status) {
@@ -1309,20 +1310,42 @@ __device__ uint32_t decompress_block_warp_v2(const uint8_t *__restrict__ in, con
         }
         // ---- the visited lanes check capacity and history themselves; the first one that fails goes to the serial form
         bool fine = (real >> lane) & 1u;
+        uint32_t dsrc = 0;                                       // 1 + index into `dict` when the whole match lies in the dictionary
         if (fine) {
+            const int64_t srel = (int64_t)myop + lit - offset;   // match source relative to ob (:142)
             if ((uint64_t)myop + lit + ml > cap) fine = false;                                 // :74 / match capacity
-            else if ((int64_t)myop + lit - offset < -(int64_t)hist) fine = false;               // dictionary source
+            else if (srel < -(int64_t)hist) {
+                // :145-200 the source starts in the dictionary (ob - hist is output index 0).  Entirely inside it (config 4:
+                // every message reads the shared dictionary): a plain copy from `dict`.  Crossing into the output or out of
+                // bounds: serial form.
+                const int64_t di = (int64_t)dict_len + srel + hist;
+                if (kDict && di >= 0 && srel + hist + (int64_t)ml <= 0) dsrc = (uint32_t)di + 1u;
+                else fine = false;
+            }
         }
         const uint32_t notfine = real & ~__ballot_sync(FULL, fine);
         const uint32_t good = notfine ? (real & ((notfine & (0u - notfine)) - 1u)) : real;
         // ---- copies, in order
         const uint32_t pack = lit | (ml << 16);                  // both < 1024 here
+        const bool anydict = kDict && __ballot_sync(FULL, dsrc != 0) != 0;
         for (uint32_t m = good; m; m &= m - 1u) {
             const int l = __ffs(m) - 1;
             const uint32_t pk = __shfl_sync(FULL, pack, l), off_ = __shfl_sync(FULL, offset, l);
             const uint32_t lp = __shfl_sync(FULL, litp, l), o_ = __shfl_sync(FULL, myop, l);
             const uint32_t lit_ = pk & 0xFFFFu, total = lit_ + (pk >> 16);
             uint8_t *const d = ob + o_;
+            if (kDict && anydict) {                              // uniform: some sequence of this window reads the dictionary
+                const uint32_t ds = __shfl_sync(FULL, dsrc, l);
+                if (ds) {
+                    const uint8_t *dsp = dict + (ds - 1u) - lit_;                 // dsp[j] = dictionary byte of output byte j >= lit_
+                    for (uint32_t base = 0; base < total; base += 32) {
+                        const uint32_t j = base + lane;
+                        if (j < total) d[j] = j < lit_ ? in[lp + j] : dsp[j];
+                    }
+                    __syncwarp();
+                    continue;
+                }
+            }
             if (off_ >= (total < 32u ? total : 32u)) {
                 // lane j's source: literal j of the sequence, or the match byte `offset` behind its own output byte
                 const uint8_t *sp = lane < lit_ ? in + (lp + lane) : d + ((int32_t)lane - (int32_t)off_);
@@ -1365,7 +1388,7 @@ __device__ uint32_t decompress_block_warp_v2(const uint8_t *__restrict__ in, con
 // Batched decode, one warp per block, blocks handed out by an atomic counter.
 // hist_frame != 0: block i's output array starts at dst[0] (history = dict ++ dst[0..dst_off[i]));
 // otherwise each block's array starts at its own dst_off[i].
-template <int WARPS>
+template <int WARPS, bool kDict>
 __global__ void __launch_bounds__(WARPS * 32)
 k_decompress_blocks(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
                     const uint32_t *__restrict__ src_len, uint32_t nblocks, uint8_t *dst,
@@ -1387,7 +1410,7 @@ k_decompress_blocks(const uint8_t *__restrict__ src, const uint64_t *__restrict_
         } else {
             const uint64_t o = dst_off[b];
             const uint32_t hist = hist_frame ? (uint32_t)(o < 65536ull ? o : 65536ull) : 0u;
-            w = decompress_block_warp_v2(src + src_off[b], src_len[b], dst + o, dst_cap[b], hist, dict, dict_len, &st);
+            w = decompress_block_warp_v2<kDict>(src + src_off[b], src_len[b], dst + o, dst_cap[b], hist, dict, dict_len, &st);
         }
         if (lane == 0) { out_len[b] = w; status[b] = (uint8_t)st; }
     }
@@ -1413,7 +1436,7 @@ k_decompress_chain(const uint8_t *__restrict__ src, const uint64_t *__restrict__
                 __syncwarp();
             } else {
                 const uint64_t room = dst_total - (uint64_t)op;
-                w = decompress_block_warp_v2(src + src_off[b], src_len[b], dst + op, (uint32_t)(room < 0xFFFFFFFFull ? room : 0xFFFFFFFFull),
+                w = decompress_block_warp_v2<true>(src + src_off[b], src_len[b], dst + op, (uint32_t)(room < 0xFFFFFFFFull ? room : 0xFFFFFFFFull),
                                              (uint32_t)(op < 65536 ? op : 65536), dict, dict_len, &st);
             }
         }
