@@ -45,6 +45,7 @@ struct dlz4_ctx {
     uint16_t *d_gtabs = nullptr;        // kGtabRegions x hy_grid x kHyGlWarps tables of 16384 x u16 (one region per stream lane)
     Buf work, comp, seg, out, meta, aux, pin;
     std::string last_error;
+    uint64_t frame_pipe_min_bytes = 32ull << 20;             // independent 64 KiB-block frames at least this long: chunked pipeline
     uint64_t jump_min_bytes = 256ull << 10;                  // frames at least this long may use the jump decoder (DLZ4_JUMP_MIN_KIB)
     uint64_t seg_min_bytes = 256ull << 10;                   // frames at least this long use the segment-parallel engine (DLZ4_SEG_MIN_KIB)
     uint32_t seg_jobs = 0, seg_reruns = 0, seg_rounds = 0;   // last segment-parallel call: segments, re-run segments, rounds
@@ -619,15 +620,20 @@ int dlz4_compress_blocks_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *
 // Blocks must be ascending and non-overlapping in `src`; output is packed (block i directly after block i-1).
 static const uint32_t kMaxChunks = 56;
 
+// frame_mode: the packed stream is the body of an LZ4 frame -- [u32 size | stored bit][payload][u32 xxh32]* with the
+// stored-block rule of bufferCompress.js:221-231 -- instead of bare compressed blocks; *total_out = its length.
 static int compress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_bytes, const uint64_t *src_off,
                                   const uint32_t *src_len, uint32_t n, uint32_t max_len, uint8_t *dst, uint64_t dst_bytes,
-                                  uint32_t *comp_len) {
+                                  uint32_t *comp_len, int frame_mode = 0, int block_checksum = 0, uint64_t *total_out = nullptr) {
     const uint64_t stride = (dlz4_compress_bound(max_len) + 15) & ~15ull;
     const uint64_t src_pad = (src_bytes + 15) & ~(uint64_t)15;
     CKS(reserve(ctx, ctx->work, src_pad + 16));
     CKS(reserve(ctx, ctx->comp, (uint64_t)n * stride + 64));
-    CKS(reserve(ctx, ctx->seg, (uint64_t)n * stride + 64));
+    CKS(reserve(ctx, ctx->seg, (uint64_t)n * (stride + 16) + 64));
     CKS(reserve(ctx, ctx->meta, (size_t)n * (8 + 8 + 4 + 4) + ((size_t)n + 64) * 8 + 256));
+    CKS(reserve(ctx, ctx->aux, (size_t)n * 12 + 256));                   // frame mode: payload offsets / lengths for the block checksums
+    uint64_t *d_doff = (uint64_t *)ctx->aux.p;
+    uint32_t *d_dlen = (uint32_t *)(d_doff + n);
     CKS(reserve_pinned(ctx, ctx->pin, 64 * 8 + (size_t)n * 4));      // chunk totals + comp_len staging (pageable D2H would block)
     uint8_t *d_src = (uint8_t *)ctx->work.p, *d_comp = (uint8_t *)ctx->comp.p, *d_pack = (uint8_t *)ctx->seg.p;
     uint64_t *d_soff = (uint64_t *)ctx->meta.p, *d_coff = d_soff + n, *d_pos = d_coff + n;     // d_pos: per chunk n_c + 1 entries
@@ -664,7 +670,7 @@ static int compress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t sr
         CK(cudaEventSynchronize(ctx->evp[64 + c]));
         const uint64_t tot = h_tot[c];
         if (host_pos + tot > dst_bytes) return DLZ4_E_OUTPUT_TOO_SMALL;
-        if (tot) CK(cudaMemcpyAsync(dst + host_pos, d_pack + (uint64_t)cb[c] * stride, tot, cudaMemcpyDeviceToHost, so));
+        if (tot) CK(cudaMemcpyAsync(dst + host_pos, d_pack + (uint64_t)cb[c] * (stride + 16), tot, cudaMemcpyDeviceToHost, so));
         host_pos += tot;
         return DLZ4_OK;
     };
@@ -685,13 +691,16 @@ static int compress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t sr
         CKS(launch_compress(ctx, d_src, d_soff + b0, d_slen + b0, m, max_len, nullptr, 0, nullptr, d_comp, d_coff + b0, d_clen + b0, sk,
                             ctx->d_counter + 1 + (c % nl), nc > 1));
         uint64_t *pos = d_pos + b0 + c;                                   // m + 1 entries
-        k_frame_layout<<<1, 1024, 0, sk>>>(d_slen + b0, d_clen + b0, m, 0, pos, nullptr, nullptr, 1);
+        uint8_t *pack_c = d_pack + (uint64_t)b0 * (stride + 16);
+        k_frame_layout<<<1, 1024, 0, sk>>>(d_slen + b0, d_clen + b0, m, block_checksum, pos, frame_mode ? d_doff + b0 : nullptr,
+                                           frame_mode ? d_dlen + b0 : nullptr, frame_mode ? 0 : 1);
         k_frame_gather<<<(int)std::min<uint64_t>(m, (uint64_t)ctx->sm_count * 8), 256, 0, sk>>>(
-            d_src, d_soff + b0, d_slen + b0, d_comp, d_coff + b0, d_clen + b0, m, pos, d_pack + (uint64_t)b0 * stride, 1);
+            d_src, d_soff + b0, d_slen + b0, d_comp, d_coff + b0, d_clen + b0, m, pos, pack_c, frame_mode ? 0 : 1);
         ctx->launches += 2;
         CK(cudaGetLastError());
+        if (frame_mode && block_checksum) CKS(launch_xxh32_batch(ctx, pack_c, d_doff + b0, d_dlen + b0, m, 0, nullptr, pack_c, sk));
         CK(cudaMemcpyAsync((void *)(h_tot + c), pos + m, 8, cudaMemcpyDeviceToHost, sk));
-        CK(cudaMemcpyAsync(h_clen + b0, d_clen + b0, (size_t)m * 4, cudaMemcpyDeviceToHost, sk));
+        if (comp_len) CK(cudaMemcpyAsync(h_clen + b0, d_clen + b0, (size_t)m * 4, cudaMemcpyDeviceToHost, sk));
         CK(cudaEventRecord(ctx->evp[64 + c], sk));
     }
     for (uint32_t c = 0; c < nc; ++c) CKS(drain(c));
@@ -700,9 +709,12 @@ static int compress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t sr
     CK(cudaEventRecord(ctx->ev1, sks[0]));
     CK(cudaStreamSynchronize(sks[0]));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
-    memcpy(comp_len, h_clen, (size_t)n * 4);
-    for (uint32_t i = 0; i < n; ++i)
-        if (comp_len[i] == 0xFFFFFFFFu) return DLZ4_E_INVALID_ARG;
+    if (total_out) *total_out = host_pos;
+    if (comp_len) {
+        memcpy(comp_len, h_clen, (size_t)n * 4);
+        for (uint32_t i = 0; i < n; ++i)
+            if (comp_len[i] == 0xFFFFFFFFu) return DLZ4_E_INVALID_ARG;
+    }
     return DLZ4_OK;
 }
 
@@ -1073,6 +1085,34 @@ int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len,
     const uint64_t stride = (dlz4_compress_bound(B) + 15) & ~15ull;
 
     // device staging: work = dictionary window ++ input (the reference's workingBuffer, :121-124)
+    if (opts->block_independence && B <= 65536 && !have_dict && !opts->content_checksum && input_len >= ctx->frame_pipe_min_bytes &&
+        output_cap >= dlz4_frame_bound(input_len)) {     // (with a content checksum the serial xxh32 is the whole cost: old path)
+        // large frame of small independent blocks: the chunked host pipeline (H2D / kernels / D2H overlapped) writes the
+        // frame body straight into `output`; header, EndMark and the content checksum are added around it
+        uint8_t hdr[32];
+        size_t hp = 0;
+        wr32(hdr, 0x184D2204u); hp = 4;
+        uint8_t flg = (1 << 6) | 0x20;
+        if (opts->content_checksum) flg |= 0x04;
+        if (opts->add_content_size) flg |= 0x08;
+        if (opts->block_checksum) flg |= 0x10;
+        hdr[hp++] = flg;
+        hdr[hp++] = (uint8_t)((bd & 7) << 4);
+        if (opts->add_content_size) { wr32(hdr + hp, (uint32_t)input_len); wr32(hdr + hp + 4, 0); hp += 8; }
+        hdr[hp] = (uint8_t)((header_xxh32(hdr + 4, hp - 4) >> 8) & 0xFF); hp++;
+        memcpy(output, hdr, hp);
+        std::vector<uint64_t> off(n);
+        std::vector<uint32_t> len(n);
+        for (uint32_t i = 0; i < n; ++i) { off[i] = (uint64_t)i * B; len[i] = (uint32_t)std::min<uint64_t>(B, input_len - off[i]); }
+        uint64_t body = 0;
+        ctx->seg_jobs = ctx->seg_reruns = ctx->seg_rounds = 0;
+        CKS(compress_blocks_packed(ctx, input, input_len, off.data(), len.data(), n, B, output + hp, output_cap - hp - 8, nullptr, 1,
+                                   opts->block_checksum, &body));
+        uint8_t foot[8] = {0, 0, 0, 0, 0, 0, 0, 0};                         // EndMark (:244)
+        memcpy(output + hp + body, foot, opts->content_checksum ? 8 : 4);
+        *output_len = hp + body + 4 + (opts->content_checksum ? 4 : 0);
+        return DLZ4_OK;
+    }
     const uint64_t dpad = (dwin + 15) & ~15ull;                          // keep the input 16-byte aligned
     CKS(reserve(ctx, ctx->work, dict_len + dpad + input_len + 64));
     uint8_t *d_work = (uint8_t *)ctx->work.p + (dpad - dwin);            // dictionary window directly before the input

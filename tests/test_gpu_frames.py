@@ -167,3 +167,16 @@ def test_concatenated_and_skippable_frames(dl):
     bad[-1] ^= 0x55                                                              # second frame's content checksum
     with pytest.raises(dl.LZ4Error, match="Content Checksum"):
         dl.decompressFrames(bytes(bad))
+
+
+def test_large_independent_frame_takes_the_pipelined_path(dl):
+    """Frames of >= 32 MiB in independent 64 KiB blocks go through the chunked host pipeline (frame body packed per chunk)."""
+    from divortio_lz4_b200 import corpus
+    n = 40 * 1024 * 1024 + 1234
+    data = corpus.mixed(71, n)
+    for bc in (False, True):
+        for size in (True, False):
+            f = dl.compressBuffer(data, None, 65536, True, False, size, None, bc)
+            want = oracle.compress_buffer(data, None, 65536, True, False, size, None, bc)
+            assert len(f) == len(want) and f == want, (bc, size)
+    assert dl.decompressBuffer(f, None, True, True) == data.tobytes()
