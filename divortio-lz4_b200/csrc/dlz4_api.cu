@@ -787,21 +787,28 @@ int dlz4_compress_blocks(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_bytes, 
 }
 
 // Decode side of the chunked pipeline: packed compressed input (block i directly after block i-1), ascending disjoint outputs.
+// src_off_in (nullable): the blocks' positions in `src` when they are not back to back (blocks of a frame: size words and
+// checksums lie between them; ascending); stored_in (nullable): 1 = the block is stored raw (bufferDecompress.js:147-149).
 static int decompress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_bytes, const uint32_t *src_len, uint32_t n,
                                     uint8_t *dst, uint64_t dst_bytes, const uint64_t *dst_off, const uint32_t *dst_cap,
-                                    const uint8_t *dict, uint32_t dict_len, int hist_mode, uint32_t *out_len, uint8_t *status) {
+                                    const uint8_t *dict, uint32_t dict_len, int hist_mode, uint32_t *out_len, uint8_t *status,
+                                    const uint64_t *src_off_in = nullptr, const uint8_t *stored_in = nullptr) {
     std::vector<uint64_t> soff(n + 1, 0);
     uint64_t total_out = 0;
-    for (uint32_t i = 0; i < n; ++i) { soff[i + 1] = soff[i] + src_len[i]; total_out += dst_cap[i]; }
+    for (uint32_t i = 0; i < n; ++i) {
+        if (src_off_in) soff[i] = src_off_in[i];
+        soff[i + 1] = soff[i] + src_len[i];
+        total_out += dst_cap[i];
+    }
     if (soff[n] > src_bytes) return DLZ4_E_INVALID_ARG;
-    const uint64_t src_pad = (soff[n] + 15) & ~(uint64_t)15;
+    const uint64_t src_pad = ((src_off_in ? src_bytes : soff[n]) + 15) & ~(uint64_t)15;
     CKS(reserve(ctx, ctx->work, src_pad + dict_len + 32));
     CKS(reserve(ctx, ctx->out, dst_bytes + 64));
-    CKS(reserve(ctx, ctx->meta, (size_t)n * (8 + 8 + 4 + 4 + 4 + 1) + 64));
+    CKS(reserve(ctx, ctx->meta, (size_t)n * (8 + 8 + 4 + 4 + 4 + 1 + 1) + 64));
     uint8_t *d_src = (uint8_t *)ctx->work.p, *d_dict = d_src + src_pad, *d_dst = (uint8_t *)ctx->out.p;
     uint64_t *d_soff = (uint64_t *)ctx->meta.p, *d_doff = d_soff + n;
     uint32_t *d_slen = (uint32_t *)(d_doff + n), *d_cap = d_slen + n, *d_olen = d_cap + n;
-    uint8_t *d_status = (uint8_t *)(d_olen + n);
+    uint8_t *d_status = (uint8_t *)(d_olen + n), *d_stored = d_status + n;
     cudaStream_t *sks = ctx->lanes, si = ctx->copy_in, so = ctx->copy_out;
     const uint32_t nl = (uint32_t)ctx->n_lanes;
     cudaStream_t sk = sks[0];
@@ -816,6 +823,7 @@ static int decompress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t 
     }
     const uint32_t nc = (uint32_t)cb.size() - 1;
     if (dict_len) CK(cudaMemcpyAsync(d_dict, dict, dict_len, cudaMemcpyHostToDevice, sk));
+    if (stored_in) CK(cudaMemcpyAsync(d_stored, stored_in, n, cudaMemcpyHostToDevice, sk));
     CK(cudaMemcpyAsync(d_soff, soff.data(), (size_t)n * 8, cudaMemcpyHostToDevice, sk));
     CK(cudaMemcpyAsync(d_doff, dst_off, (size_t)n * 8, cudaMemcpyHostToDevice, sk));
     CK(cudaMemcpyAsync(d_slen, src_len, (size_t)n * 4, cudaMemcpyHostToDevice, sk));
@@ -827,12 +835,14 @@ static int decompress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t 
     const uint32_t lanes_used = hist_mode == DLZ4_HIST_FRAME ? 1u : nl;
     for (uint32_t c = 0; c < nc; ++c) {
         const uint32_t b0 = cb[c], b1 = cb[c + 1], m = b1 - b0;
-        if (soff[b1] > soff[b0]) CK(cudaMemcpyAsync(d_src + soff[b0], src + soff[b0], soff[b1] - soff[b0], cudaMemcpyHostToDevice, si));
+        const uint64_t s_lo = soff[b0], s_hi = soff[b1 - 1] + src_len[b1 - 1];
+        if (s_hi > s_lo) CK(cudaMemcpyAsync(d_src + s_lo, src + s_lo, s_hi - s_lo, cudaMemcpyHostToDevice, si));
         CK(cudaEventRecord(ctx->evp[c], si));
         cudaStream_t sc = sks[c % lanes_used];
         CK(cudaStreamWaitEvent(sc, ctx->evp[c], 0));
         CKS(launch_decompress(ctx, d_src, d_soff + b0, d_slen + b0, m, d_dst, d_doff + b0, d_cap + b0, dict_len ? d_dict : nullptr, dict_len,
-                              hist_mode == DLZ4_HIST_FRAME, nullptr, d_olen + b0, d_status + b0, sc, ctx->d_counter + 1 + (c % lanes_used)));
+                              hist_mode == DLZ4_HIST_FRAME, stored_in ? d_stored + b0 : nullptr, d_olen + b0, d_status + b0, sc,
+                              ctx->d_counter + 1 + (c % lanes_used)));
         CK(cudaEventRecord(ctx->evp[64 + c], sc));
         CK(cudaStreamWaitEvent(so, ctx->evp[64 + c], 0));
         const uint64_t lo = dst_off[b0], hi = dst_off[b1 - 1] + dst_cap[b1 - 1];
@@ -1366,6 +1376,37 @@ int dlz4_frame_decompress_ex(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame
     const uint64_t dwin = std::min<uint64_t>(dict_len, 65536);
     const uint32_t B = info.block_max_size;
 
+    if (info.block_independence && B <= 65536 && n >= 512 && !dict_len && !(flags & 2u) && info.content_size >= ctx->frame_pipe_min_bytes &&
+        info.content_size <= output_cap && (uint64_t)(n - 1) * B < info.content_size && info.content_size <= (uint64_t)n * B) {
+        // large frame of small independent blocks with a declared size: the chunked host pipeline (H2D / kernels / D2H
+        // overlapped), every block at i * blockMaxSize.  A frame whose inner blocks are not full falls through to the path below.
+        std::vector<uint64_t> soff(n), doff(n);
+        std::vector<uint32_t> slen(n), cap(n), olen(n);
+        std::vector<uint8_t> status(n), stored(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            soff[i] = blocks[i].off; slen[i] = blocks[i].len; stored[i] = blocks[i].stored;
+            doff[i] = (uint64_t)i * B;
+            cap[i] = (uint32_t)std::min<uint64_t>(B, info.content_size - doff[i]);
+        }
+        const int s = decompress_blocks_packed(ctx, frame, frame_len, slen.data(), n, output, info.content_size, doff.data(), cap.data(),
+                                               nullptr, 0, DLZ4_HIST_RAW, olen.data(), status.data(), soff.data(), stored.data());
+        if (s == DLZ4_E_CUDA || s == DLZ4_E_INVALID_ARG) return s;
+        bool full = s == DLZ4_OK;
+        for (uint32_t i = 0; full && i < n; ++i) full = olen[i] == cap[i];
+        if (full) {
+            if (info.has_content_checksum && (flags & 1u)) {             // :213-217 over the decoded bytes still resident in ctx->out
+                if (end + 4 > frame_len) return DLZ4_E_CONTENT_CHECKSUM;
+                uint32_t h = 0;
+                CKS(launch_xxh32_stream(ctx, (const uint8_t *)ctx->out.p, info.content_size, 0, ctx->d_hash, st));
+                CK(cudaMemcpyAsync(&h, ctx->d_hash, 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (h != rd32(frame + end)) return DLZ4_E_CONTENT_CHECKSUM;
+            }
+            *output_len = info.content_size;
+            return DLZ4_OK;
+        }
+        // an error or a short inner block: the general path below decides (same status order as ever)
+    }
     // capacity the decode may use: the reference allocates contentSize when present (:107), otherwise grows as needed
     uint64_t cap_total = info.content_size ? info.content_size : 0;
     if (!info.content_size) {

@@ -180,3 +180,17 @@ def test_large_independent_frame_takes_the_pipelined_path(dl):
             want = oracle.compress_buffer(data, None, 65536, True, False, size, None, bc)
             assert len(f) == len(want) and f == want, (bc, size)
     assert dl.decompressBuffer(f, None, True, True) == data.tobytes()
+    # decode side of the pipeline (declared size, no block-checksum verification asked): content-size frames, checksummed or not
+    for cc in (False, True):
+        g = oracle.compress_buffer(data, None, 65536, True, cc, True)
+        assert dl.decompressBuffer(g) == data.tobytes()
+        bad = bytearray(g)
+        bad[len(bad) // 2] ^= 0xFF                                   # somewhere inside a block: the general path names the error
+        try:
+            assert dl.decompressBuffer(bytes(bad), None, False) != data.tobytes()
+        except dl.LZ4Error:
+            pass
+        if cc:
+            tail = bytearray(g); tail[-2] ^= 1
+            with pytest.raises(dl.LZ4Error, match="Content Checksum Error"):
+                dl.decompressBuffer(bytes(tail))
