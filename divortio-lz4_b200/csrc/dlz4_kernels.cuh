@@ -1,13 +1,21 @@
 // dlz4_kernels.cuh -- sm_100a device code of the B200-native LZ4 block codec.
 //
-// One warp owns one LZ4 block.  The compressor reproduces the reference's greedy single-probe
-// match finder (src/block/blockCompress.js:31-233) bit for bit; the parallelism inside a block is
-// the *miss run*: the next 32 probe positions are a pure function of (sIndex, searchMatchCount),
-// so the 32 lanes probe them at once, resolve intra-batch hash collisions with match.any, a ballot
-// picks the first hit, and only lanes up to the hit commit their table inserts -- exactly the state
-// the serial loop would have left behind.  Match extension is a 128-byte-per-round ballot.
+// One warp owns one chain of the reference's greedy single-probe match finder (src/block/blockCompress.js:31-233) and
+// reproduces it bit for bit.  Parallelism inside a chain comes from the probe schedule: the next 32 probe positions are a
+// pure function of (sIndex, searchMatchCount), so 32 lanes probe them at once (compress_block_warp: batch step; and the
+// dense 32-position window of compress_span_warp).  Parallelism across chains comes from where the 32 KiB hash tables
+// live: a few in shared memory, most in L2-resident global scratch (TabG16 / Tab12e / TabOv / TabG32).
 //
-// No tensor cores: the work is byte-serial integer work bounded by latency and HBM, not FLOPs.
+//   compress    k_compress_fresh16h   fresh blocks <= 64 KiB (the headline kernel), 28 chains per SM
+//               k_compress_overlay    blocks <= 4 KiB behind a shared prefix, one read-only initial table + per-warp overlay
+//               k_compress_segments   linked chains and large blocks: speculative segments, k_seg_verify, k_seg_assemble
+//               k_compress_generic32 / k_compress_chain   Int32 table in shared memory (prefix + table, short chains, compressRaw)
+//   decompress  k_decompress_blocks   one warp per block, speculative lane-parallel token sizing, merged literal+match copy
+//               k_jd_* / k_jdp_*      jump decoder for linked frames and large blocks: token scan, pointer doubling
+//               k_decompress_chain    short linked frames, one warp
+//   xxh32       k_xxh32_batch (per block), k_xxh32_stream (whole stream, stateful), frame packing kernels at the end
+//
+// No tensor cores: the work is byte-serial integer work bounded by latency and by the memory system, not FLOPs.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -1099,66 +1107,6 @@ __device__ __forceinline__ void warp_match_copy(uint8_t *d, uint32_t offset, uin
             for (uint32_t k = lane; k < n; k += step) d[k] = v;
         }
     }
-}
-
-// decompressBlock (blockDecompress.js:30-275) with LZ4-spec copy semantics, one warp per block.
-// out0 = the output ARRAY's index 0 (the dictionary boundary, :142-147), out_pos = outputOffset,
-// out_total = output.length.  Everything is bounds-checked (the JS checks literals only).
-__device__ uint32_t decompress_block_warp(const uint8_t *__restrict__ in, const uint32_t n, uint8_t *const out0,
-                                          const int64_t out_pos, const int64_t out_total,
-                                          const uint8_t *__restrict__ dict, const int64_t dict_len, uint32_t *status) {
-    const uint32_t lane = lane_id();
-    uint32_t ip = 0;
-    int64_t op = out_pos;
-    uint32_t st = ST_OK;
-    while (ip < n) {                                             // :55
-        const uint32_t token = in[ip++];                         // :58
-        uint32_t lit = token >> 4;                               // :61
-        if (lit == 15u) {                                        // :62-68
-            uint32_t b;
-            do {
-                if (ip >= n) { st = ST_MALFORMED; break; }
-                b = in[ip++]; lit += b;
-            } while (b == 255u);
-            if (st) break;
-        }
-        if (op + lit > out_total) { st = ST_OUTPUT_TOO_SMALL; break; }   // :74
-        if ((uint64_t)ip + lit > n) { st = ST_MALFORMED; break; }        // :75
-        if (lit) warp_copy(out0 + op, in + ip, lit, lane);       // :79-121
-        op += lit; ip += lit;
-        if (ip >= n) break;                                      // :123
-        if (ip + 2 > n) { st = ST_MALFORMED; break; }
-        const uint32_t offset = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8);   // :126
-        ip += 2;
-        if (offset == 0) { st = ST_OFFSET_ZERO; break; }         // :128
-        uint32_t ml = token & 15u;                               // :131
-        if (ml == 15u) {                                         // :132-138
-            uint32_t b;
-            do {
-                if (ip >= n) { st = ST_MALFORMED; break; }
-                b = in[ip++]; ml += b;
-            } while (b == 255u);
-            if (st) break;
-        }
-        ml += 4;                                                 // :139
-        int64_t cs = op - (int64_t)offset;                       // :142
-        uint32_t rem = ml;
-        if (cs < 0) {                                            // :145-200 dictionary
-            int64_t from_dict = -cs;
-            if (from_dict > ml) from_dict = ml;
-            const int64_t di = dict_len + cs;
-            if (di < 0 || di + from_dict > dict_len) { st = ST_DICT_OOB; break; }   // :150-152
-            if (op + ml > out_total) { st = ST_OUTPUT_TOO_SMALL; break; }
-            warp_copy(out0 + op, dict + di, (uint32_t)from_dict, lane);
-            op += from_dict; rem -= (uint32_t)from_dict;
-        } else if (op + ml > out_total) { st = ST_OUTPUT_TOO_SMALL; break; }
-        __syncwarp();                                            // literals / dictionary bytes visible to all lanes
-        if (rem) warp_match_copy(out0 + op, offset, rem, lane);  // :194-199, :202-271
-        op += rem;
-        __syncwarp();
-    }
-    *status = st;
-    return (uint32_t)(op - out_pos);
 }
 
 // One sequence at in[ip], uniform across the warp (the loop body of blockDecompress.js:55-271).  Returns false when the block
