@@ -227,7 +227,14 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
     if (n == 0) return DLZ4_OK;
     // segment size: about 2048 segments over the call, at least 128 KiB; warm-up 512 KiB (tools/resync_stats.c)
     int64_t S = 128 << 10;
-    while (S < total / 2048) S <<= 1;
+    {
+        // up to ~130 MiB: as few segments as the shared-memory-table slots (3 per SM: those chains run twice as fast as the
+        // L2-table ones and a short call is one wave of (warm-up + segment) / chain speed); beyond that ~2048 segments
+        const int64_t slots = (int64_t)ctx->sm_count * kSegCtasPerSm;
+        const int64_t fit = (((total + slots - 1) / slots) + 65535) & ~(int64_t)65535;
+        if (fit <= (320 << 10)) S = std::max(S, fit);
+        else while (S < total / 2048) S <<= 1;
+    }
     if (const char *e = getenv("DLZ4_SEG_KIB")) S = (int64_t)std::max(64, atoi(e)) << 10;
     int64_t W = 512 << 10;
     if (const char *e = getenv("DLZ4_SEG_WARM_KIB")) W = (int64_t)std::max(0, atoi(e)) << 10;
