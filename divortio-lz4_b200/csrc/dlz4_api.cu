@@ -37,6 +37,9 @@ struct dlz4_ctx {
     cudaEvent_t evp[128] = {};          // event pool of the chunked host pipeline: [0,64) copies landed, [64,128) kernels done
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_side = nullptr, ev_fork = nullptr;
     uint32_t *d_counter = nullptr;      // work-queue heads (one per launch slot)
+    uint32_t *d_land = nullptr;         // kLandFlags "input chunk is in memory" flags (segment engine under a chunked H2D copy)
+    uint32_t *h_one = nullptr;          // pinned word holding 1: source of the flag copies
+    uint64_t seg_overlap_min_bytes = 64ull << 20;            // segment-engine frames at least this long overlap H2D and parse
     uint32_t *d_hash = nullptr;         // small result slots
     uint64_t *d_total = nullptr;
     int32_t *d_table = nullptr;         // int32[16384] scratch table
@@ -116,11 +119,13 @@ int block_id_for(uint64_t bytes) {          // bufferCompress.js:77-82
     return 7;
 }
 const uint32_t kBlockMax[8] = {0, 0, 0, 0, 65536, 262144, 1048576, 4194304};
+const uint32_t kLandFlags = 256, kLandShift = 24;      // 16 MiB H2D chunks, one flag each (inputs are < 2 GiB: <= 128 chunks)
 
 // ---- launch helpers ----------------------------------------------------------------------------------
 int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int64_t total, int64_t B, uint32_t n, bool linked,
                        const int32_t *init_table, uint8_t *d_comp, const uint64_t *d_coff, uint32_t *d_clen, cudaStream_t st,
-                       int32_t *final_table = nullptr);
+                       int32_t *final_table = nullptr, const uint32_t *landed = nullptr, int32_t land_origin = 0,
+                       uint32_t land_shift = 0);
 
 int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len, uint32_t n,
                     uint32_t max_len, const uint8_t *prefix, uint32_t prefix_len, const int32_t *init_table, uint8_t *dst,
@@ -223,7 +228,9 @@ int launch_xxh32_stream(dlz4_ctx *ctx, const uint8_t *data, uint64_t len, uint32
 // initial state), otherwise every block is its own chain with a fresh table.  Output: d_comp + d_coff[b], d_clen[b].
 int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int64_t total, int64_t B, uint32_t n, bool linked,
                        const int32_t *init_table, uint8_t *d_comp, const uint64_t *d_coff, uint32_t *d_clen, cudaStream_t st,
-                       int32_t *final_table /* nullable, device int32[16384]: the chain's table after its last block (linked only) */) {
+                       int32_t *final_table /* nullable, device int32[16384]: the chain's table after its last block (linked only) */,
+                       const uint32_t *landed /* nullable: input still arriving, see k_compress_segments */, int32_t land_origin,
+                       uint32_t land_shift) {
     if (n == 0) return DLZ4_OK;
     // segment size: about 2048 segments over the call, at least 128 KiB; warm-up 512 KiB (tools/resync_stats.c)
     int64_t S = 128 << 10;
@@ -288,17 +295,18 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
     CK(cudaMemcpyAsync(d_sc, slot_count.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d_plen, 0, (size_t)nslots * 4, st));
     uint32_t *counter = ctx->d_counter + 8;
-    auto launch = [&](const uint32_t *list, uint32_t count) -> int {
+    auto launch = [&](const uint32_t *list, uint32_t count, const uint32_t *land) -> int {
         CK(cudaMemsetAsync(counter, 0, 4, st));
         const int grid = (int)std::min<uint64_t>(count, (uint64_t)ctx->sm_count * kSegCtasPerSm);
         const uint32_t active = (uint32_t)std::min<uint64_t>((count + grid - 1) / grid, (uint64_t)kSegWarps);
         k_compress_segments<<<grid, kSegWarps * 32, kSegSmemBytes, st>>>(d_work, d_jobs, list, count, (int32_t)B, init_table, d_tab, d_snap,
-                                                                                  d_ss, d_es, d_buf, bstride, d_poff, d_plen, counter, active);
+                                                                                  d_ss, d_es, d_buf, bstride, d_poff, d_plen, counter, active, land,
+                                                                                  land_origin, land_shift);
         ctx->launches++;
         CK(cudaGetLastError());
         return DLZ4_OK;
     };
-    CKS(launch(nullptr, nj));
+    CKS(launch(nullptr, nj, landed));
     ctx->seg_jobs = nj; ctx->seg_reruns = 0; ctx->seg_rounds = 0;
     bool speculative = false;
     for (const SegJob &J : jobs) speculative |= !(J.flags & kSegFirst);
@@ -318,7 +326,7 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
             for (uint32_t j : list) jobs[j].flags |= kSegRerun;
             CK(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nj * sizeof(SegJob), cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(d_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, st));
-            CKS(launch(d_list, (uint32_t)list.size()));
+            CKS(launch(d_list, (uint32_t)list.size(), nullptr));
             CK(cudaStreamSynchronize(st));                                // `list` / `jobs` are reused next round
             ctx->seg_reruns += (uint32_t)list.size();
             ctx->seg_rounds++;
@@ -493,6 +501,10 @@ int dlz4_init(int device, dlz4_ctx **out) {
     if (const char *e = getenv("DLZ4_CHUNK_MIB")) ctx->chunk_bytes = (uint64_t)std::max(1, atoi(e)) << 20;
     if (const char *e = getenv("DLZ4_LANES")) ctx->n_lanes = std::min(4, std::max(1, atoi(e)));
     CK(cudaMalloc(&ctx->d_counter, 64));
+    CK(cudaMalloc(&ctx->d_land, kLandFlags * 4));
+    CK(cudaMallocHost(&ctx->h_one, 64));
+    *ctx->h_one = 1u;
+    if (const char *e = getenv("DLZ4_SEG_OVERLAP_MIN_MIB")) ctx->seg_overlap_min_bytes = (uint64_t)atoll(e) << 20;   // huge: never
     CK(cudaMalloc(&ctx->d_hash, 64));
     CK(cudaMalloc(&ctx->d_total, 64));
     CK(cudaMalloc(&ctx->d_table, kHashEntries * sizeof(int32_t)));
@@ -521,6 +533,8 @@ void dlz4_shutdown(dlz4_ctx *ctx) {
         if (b->p) cudaFree(b->p);
     if (ctx->pin.p) cudaFreeHost(ctx->pin.p);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->d_land) cudaFree(ctx->d_land);
+    if (ctx->h_one) cudaFreeHost(ctx->h_one);
     if (ctx->d_hash) cudaFree(ctx->d_hash);
     if (ctx->d_total) cudaFree(ctx->d_total);
     if (ctx->d_table) cudaFree(ctx->d_table);
@@ -1141,7 +1155,23 @@ int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len,
     uint64_t *d_soff = (uint64_t *)ctx->meta.p, *d_coff = d_soff + n, *d_pos = d_coff + n;
     uint32_t *d_slen = (uint32_t *)(d_pos + n + 1), *d_clen = d_slen + n;
 
-    if (input_len) CK(cudaMemcpyAsync(d_in, input, input_len, cudaMemcpyHostToDevice, st));
+    // Segment-engine frames of 64 MiB and more parse while the input is still arriving: the copy goes out in 16 MiB chunks on
+    // the copy stream, each followed by a 4-byte flag copy, and a segment waits for the flags of what it reads.
+    const bool segments = input_len >= ctx->seg_min_bytes && (!opts->block_independence || (B > 65536 && !dwin));
+    const bool overlap = segments && input_len >= ctx->seg_overlap_min_bytes;
+    if (overlap) {
+        CK(cudaMemsetAsync(ctx->d_land, 0, kLandFlags * 4, st));
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_fork, 0));
+        const uint64_t chunk = 1ull << kLandShift;
+        for (uint64_t c = 0, o = 0; o < input_len; ++c, o += chunk) {
+            CK(cudaMemcpyAsync(d_in + o, input + o, (size_t)std::min<uint64_t>(chunk, input_len - o), cudaMemcpyHostToDevice, ctx->copy_in));
+            CK(cudaMemcpyAsync(ctx->d_land + c, ctx->h_one, 4, cudaMemcpyHostToDevice, ctx->copy_in));
+        }
+        CK(cudaEventRecord(ctx->evp[0], ctx->copy_in));                 // whole input in memory
+    } else if (input_len) {
+        CK(cudaMemcpyAsync(d_in, input, input_len, cudaMemcpyHostToDevice, st));
+    }
     if (dwin) CK(cudaMemcpyAsync(d_work, dictionary + (dict_len - dwin), dwin, cudaMemcpyHostToDevice, st));
 
     // header (host, bufferCompress.js:147-178)
@@ -1177,6 +1207,7 @@ int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len,
     if (opts->content_checksum) {
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        if (overlap) CK(cudaStreamWaitEvent(ctx->side, ctx->evp[0], 0));
         CKS(launch_xxh32_stream(ctx, d_in, input_len, 0, ctx->d_hash, ctx->side));
         CK(cudaEventRecord(ctx->ev_side, ctx->side));
     }
@@ -1195,7 +1226,8 @@ int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len,
             if (dwin >= 4) { k_warm_jenkins<<<((int)dwin - 3 + 255) / 256, 256, 0, st>>>(d_work, (int32_t)dwin, ctx->d_table); ctx->launches++; }
             if (input_len >= ctx->seg_min_bytes)
                 // long chain: speculative segments, verified against the serial parse's state (k_compress_segments)
-                CKS(compress_segmented(ctx, d_work, (int64_t)dwin, (int64_t)input_len, (int64_t)B, n, true, ctx->d_table, d_comp, d_coff, d_clen, st));
+                CKS(compress_segmented(ctx, d_work, (int64_t)dwin, (int64_t)input_len, (int64_t)B, n, true, ctx->d_table, d_comp, d_coff, d_clen, st,
+                                       nullptr, overlap ? ctx->d_land : nullptr, (int32_t)dwin, kLandShift));
             else
                 CKS(launch_chain(ctx, d_work, (int32_t)dwin, (int32_t)input_len, (int32_t)B, n, ctx->d_table, d_comp, stride, d_clen, st));
         } else {
@@ -1212,11 +1244,13 @@ int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len,
             if (B > 65536 && n > first && input_len >= ctx->seg_min_bytes)
                 // large independent blocks: segments inside every block (the first segment of a block starts exactly)
                 CKS(compress_segmented(ctx, d_work, (int64_t)dwin + (int64_t)first * B, (int64_t)input_len - (int64_t)first * B, (int64_t)B,
-                                       n - first, false, nullptr, d_comp, d_coff + first, d_clen + first, st));
+                                       n - first, false, nullptr, d_comp, d_coff + first, d_clen + first, st, nullptr,
+                                       overlap ? ctx->d_land : nullptr, (int32_t)dwin, kLandShift));
             else
                 CKS(launch_compress(ctx, d_work, d_soff + first, d_slen + first, n - first, B, nullptr, 0, nullptr, d_comp, d_coff + first,
                                     d_clen + first, st));
         }
+        if (overlap) CK(cudaStreamWaitEvent(st, ctx->evp[0], 0));       // (stored blocks are copied from the input)
         CKS(dlz4_frame_pack_dev(ctx, d_work, d_soff, d_slen, d_comp, d_coff, d_clen, n, opts->block_checksum, (uint8_t *)ctx->seg.p,
                                 d_pos, st));
         CK(cudaMemcpyAsync(&seg_len, d_pos + n, 8, cudaMemcpyDeviceToHost, st));

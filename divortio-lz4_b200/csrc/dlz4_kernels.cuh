@@ -968,7 +968,9 @@ k_compress_segments(const uint8_t *__restrict__ base, const SegJob *__restrict__
                     uint32_t njobs, int32_t block_size, const int32_t *__restrict__ init_table /* nullable: chain 0 */,
                     int32_t *tables, int32_t *snaps, SegState *snap_state, SegState *end_state,
                     uint8_t *blockbuf, uint64_t blockbuf_stride, uint32_t *piece_off, uint32_t *piece_len, uint32_t *counter,
-                    uint32_t active_warps) {
+                    uint32_t active_warps,
+                    const uint32_t *landed /* nullable: flag per 2^land_shift input bytes, set once they are in memory */,
+                    int32_t land_origin, uint32_t land_shift) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     if (warp >= active_warps) return;
@@ -978,6 +980,26 @@ k_compress_segments(const uint8_t *__restrict__ base, const SegJob *__restrict__
         if (q >= njobs) break;
         const uint32_t j = job_list ? job_list[q] : q;
         const SegJob J = jobs[j];
+        if (landed) {
+            // the input is still arriving (chunked host-to-device copy on another stream, flags written in copy order):
+            // wait for everything this segment can read -- up to the end of the block that holds seg_end, as far as the
+            // stopping sequence's match may run
+            int32_t need = J.chain_end;
+            if (!(J.flags & kSegLast)) {
+                const int32_t be = J.chain_start + (J.seg_end - J.chain_start + block_size - 1) / block_size * block_size;
+                need = be < need ? be : need;
+            }
+            if (lane == 0) {
+                const volatile uint32_t *f = landed + ((uint32_t)(need - 1 - land_origin) >> land_shift);
+                const long long t0 = clock64();
+                while (*f == 0u) {
+                    __nanosleep(500);
+                    if (clock64() - t0 > (8ll << 30)) __trap();          // seconds without the copy: fail the call, do not hang
+                }
+                __threadfence_system();
+            }
+            __syncwarp();
+        }
         {   // this run's pieces replace whatever an earlier run of the segment left in its slots
             const int32_t last_pos = (J.seg_end < J.chain_end ? J.seg_end : J.chain_end) - 1;
             const uint32_t nslots = (uint32_t)((last_pos - J.chain_start) / block_size - (J.seg_begin - J.chain_start) / block_size) + 1u;
