@@ -246,13 +246,26 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
     int64_t W = 512 << 10;
     if (const char *e = getenv("DLZ4_SEG_WARM_KIB")) W = (int64_t)std::max(0, atoi(e)) << 10;
     if (!linked && S > B) S = B;
+    // Groups: the chains on shared-memory tables (one per CTA) run about 1.5 times as fast as those on L2 tables when the
+    // device is full, so once there are more segments than such slots, G consecutive segments form a group that one
+    // shared-memory warp runs back to back -- one warm-up for the group, every later member starts from its predecessor's end
+    // state (kSegCont) -- while the L2-table warps take single segments.  G makes the group's work, W + G S, about 1.5 times
+    // a single segment's, W + S: both kinds finish together and fewer L2-table chains compete for the L2
+    // (profiles/r01c_seg_groups.txt).  Members stay separate segments for verification, so a failed speculation still
+    // re-runs S bytes only.
+    const int64_t slots = (int64_t)ctx->sm_count * kSegCtasPerSm;
+    int64_t G = (total + S - 1) / S > slots ? std::max<int64_t>(2, (W + 3 * S) / (2 * S)) : 0;
+    if (const char *e = getenv("DLZ4_SEG_GROUP")) G = std::max(0, atoi(e));
+    if (G < 2) G = 0;
     std::vector<SegJob> jobs;
+    std::vector<uint32_t> heads, singles;                  // first-launch queues (job indices)
     std::vector<uint32_t> slot_first(n, 0), slot_count(n, 0);
     uint32_t nslots = 0;
     const uint32_t nchains = linked ? 1u : n;
     for (uint32_t c = 0; c < nchains; ++c) {
         const int64_t cs = linked ? start : start + (int64_t)c * B;
         const int64_t ce = linked ? start + total : std::min<int64_t>(cs + B, start + total);
+        const size_t j0 = jobs.size();
         for (int64_t sb = cs; sb < ce; sb += S) {
             SegJob J;
             J.chain_start = (int32_t)cs; J.chain_end = (int32_t)ce;
@@ -270,6 +283,23 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
             }
             jobs.push_back(J);
         }
+        // groups and single segments of this chain, interleaved evenly
+        const int64_t njc = (int64_t)(jobs.size() - j0);
+        // (never more groups than shared-memory slots over all chains: a group on an L2-table warp would be the tail)
+        const int64_t share = ((int64_t)(c + 1) * slots) / nchains - ((int64_t)c * slots) / nchains;
+        const int64_t nb = G ? std::min<int64_t>(njc / G, share) : 0, ns = njc - nb * G;
+        size_t j = j0;
+        for (int64_t k = 0; k < nb + ns; ++k) {
+            if (nb && (k + 1) * nb / (nb + ns) > k * nb / (nb + ns)) {
+                heads.push_back((uint32_t)j);
+                for (int64_t m = 0; m < G; ++m, ++j) {
+                    if (m) jobs[j].flags |= kSegCont;
+                    if (m + 1 < G) jobs[j].flags |= kSegMore;
+                }
+            } else {
+                singles.push_back((uint32_t)j++);
+            }
+        }
     }
     const uint32_t nj = (uint32_t)jobs.size();
     const uint64_t bstride = (uint64_t)((B + (B >> 3) + 64 + 15) & ~15ll);
@@ -277,7 +307,7 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
     size_t off = 0;
     auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_tab = carve((size_t)nj * kHashEntries * 4), o_snap = carve((size_t)nj * kHashEntries * 4);
-    const size_t o_jobs = carve((size_t)nj * sizeof(SegJob)), o_list = carve((size_t)nj * 4);
+    const size_t o_jobs = carve((size_t)nj * sizeof(SegJob)), o_list = carve((size_t)nj * 4), o_perm = carve((size_t)nj * 4);
     const size_t o_ss = carve((size_t)nj * sizeof(SegState)), o_es = carve((size_t)nj * sizeof(SegState)), o_bad = carve(nj);
     const size_t o_poff = carve((size_t)nslots * 4), o_plen = carve((size_t)nslots * 4);
     const size_t o_sf = carve((size_t)n * 4), o_sc = carve((size_t)n * 4), o_buf = carve((size_t)n * bstride + 64);
@@ -285,7 +315,7 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
     uint8_t *A = (uint8_t *)ctx->aux.p;
     int32_t *d_tab = (int32_t *)(A + o_tab), *d_snap = (int32_t *)(A + o_snap);
     SegJob *d_jobs = (SegJob *)(A + o_jobs);
-    uint32_t *d_list = (uint32_t *)(A + o_list);
+    uint32_t *d_list = (uint32_t *)(A + o_list), *d_perm = (uint32_t *)(A + o_perm);
     SegState *d_ss = (SegState *)(A + o_ss), *d_es = (SegState *)(A + o_es);
     uint8_t *d_bad = A + o_bad;
     uint32_t *d_poff = (uint32_t *)(A + o_poff), *d_plen = (uint32_t *)(A + o_plen), *d_sf = (uint32_t *)(A + o_sf), *d_sc = (uint32_t *)(A + o_sc);
@@ -295,18 +325,35 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
     CK(cudaMemcpyAsync(d_sc, slot_count.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d_plen, 0, (size_t)nslots * 4, st));
     uint32_t *counter = ctx->d_counter + 8;
-    auto launch = [&](const uint32_t *list, uint32_t count, const uint32_t *land) -> int {
-        CK(cudaMemsetAsync(counter, 0, 4, st));
-        const int grid = (int)std::min<uint64_t>(count, (uint64_t)ctx->sm_count * kSegCtasPerSm);
-        const uint32_t active = (uint32_t)std::min<uint64_t>((count + grid - 1) / grid, (uint64_t)kSegWarps);
+    auto launch = [&](const uint32_t *list, uint32_t count, const uint32_t *land, uint32_t nbig, uint32_t follow) -> int {
+        CK(cudaMemsetAsync(counter, 0, 8, st));
+        const uint64_t cap = (uint64_t)ctx->sm_count * kSegCtasPerSm;
+        int grid;
+        uint32_t active;
+        if (nbig) {     // warp 0 of every CTA takes the long segments, the others the short ones
+            const uint64_t nsmall = count - nbig;
+            grid = (int)std::min<uint64_t>(std::max<uint64_t>(nbig, (nsmall + kSegWarps - 2) / (kSegWarps - 1)), cap);
+            active = (uint32_t)std::min<uint64_t>(1 + (nsmall + grid - 1) / grid, (uint64_t)kSegWarps);
+        } else {
+            grid = (int)std::min<uint64_t>(count, cap);
+            active = (uint32_t)std::min<uint64_t>((count + grid - 1) / grid, (uint64_t)kSegWarps);
+        }
         k_compress_segments<<<grid, kSegWarps * 32, kSegSmemBytes, st>>>(d_work, d_jobs, list, count, (int32_t)B, init_table, d_tab, d_snap,
                                                                                   d_ss, d_es, d_buf, bstride, d_poff, d_plen, counter, active, land,
-                                                                                  land_origin, land_shift);
+                                                                                  land_origin, land_shift, nbig, follow);
         ctx->launches++;
         CK(cudaGetLastError());
         return DLZ4_OK;
     };
-    CKS(launch(nullptr, nj, landed));
+    const uint32_t nbig = (uint32_t)heads.size();
+    std::vector<uint32_t> perm(heads);
+    if (nbig) {
+        perm.insert(perm.end(), singles.begin(), singles.end());
+        CK(cudaMemcpyAsync(d_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice, st));
+        CKS(launch(d_perm, (uint32_t)perm.size(), landed, nbig, 1));
+    } else {
+        CKS(launch(nullptr, nj, landed, 0, 0));
+    }
     ctx->seg_jobs = nj; ctx->seg_reruns = 0; ctx->seg_rounds = 0;
     bool speculative = false;
     for (const SegJob &J : jobs) speculative |= !(J.flags & kSegFirst);
@@ -326,7 +373,7 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
             for (uint32_t j : list) jobs[j].flags |= kSegRerun;
             CK(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nj * sizeof(SegJob), cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(d_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, st));
-            CKS(launch(d_list, (uint32_t)list.size(), nullptr));
+            CKS(launch(d_list, (uint32_t)list.size(), nullptr, 0, 0));
             CK(cudaStreamSynchronize(st));                                // `list` / `jobs` are reused next round
             ctx->seg_reruns += (uint32_t)list.size();
             ctx->seg_rounds++;

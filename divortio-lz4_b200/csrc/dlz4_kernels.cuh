@@ -868,7 +868,9 @@ struct SegJob {
     uint32_t first_block;                // global index of that block
     uint32_t flags;                      // kSegFirst | kSegLast | kSegRerun
 };
-enum : uint32_t { kSegFirst = 1u, kSegLast = 2u, kSegRerun = 4u };
+enum : uint32_t { kSegFirst = 1u, kSegLast = 2u, kSegRerun = 4u,
+                  kSegCont = 8u,       // first launch: starts from its predecessor's end state (same warp ran it just before)
+                  kSegMore = 16u };    // first launch: the warp goes on with the next segment (which has kSegCont)
 struct SegState { int32_t s, head; };    // next probe position (== anchor, searchMatchCount == 67 there) and the stopping head
                                          // (-1: fresh start of the block that begins at s)
 // offset of the piece that starts at source offset x of its block (pieces of one block never overlap: a run of complete
@@ -921,8 +923,9 @@ __device__ __forceinline__ void seg_job(const uint8_t *__restrict__ base, const 
     constexpr uint32_t kVec = kHashEntries * 4 / 16;
     Tab T{live};
     SegState S;
-    if (J.flags & kSegRerun) {
-        // exact start: the predecessor's end state (its table buffer is final, nobody writes it during this launch)
+    if (J.flags & (kSegRerun | kSegCont)) {
+        // exact start: the predecessor's end state (its table buffer is final, nobody writes it during this launch --
+        // a re-run -- or this warp has just written it -- a group of segments run back to back)
         const uint4 *p4 = reinterpret_cast<const uint4 *>(tables + (size_t)(j - 1) * kHashEntries);
         uint4 *s4 = reinterpret_cast<uint4 *>(snaps + (size_t)j * kHashEntries);
         for (uint32_t i = lane; i < kVec; i += 32) { const uint4 v = __ldcg(p4 + i); put(i, v); __stcg(s4 + i, v); }
@@ -970,47 +973,67 @@ k_compress_segments(const uint8_t *__restrict__ base, const SegJob *__restrict__
                     uint8_t *blockbuf, uint64_t blockbuf_stride, uint32_t *piece_off, uint32_t *piece_len, uint32_t *counter,
                     uint32_t active_warps,
                     const uint32_t *landed /* nullable: flag per 2^land_shift input bytes, set once they are in memory */,
-                    int32_t land_origin, uint32_t land_shift) {
+                    int32_t land_origin, uint32_t land_shift,
+                    uint32_t nbig /* > 0: job_list[0, nbig) are heads of segment groups meant for the shared-memory warps */,
+                    uint32_t follow /* first launch: a warp runs on through kSegMore */) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     if (warp >= active_warps) return;
     uint32_t *ring = reinterpret_cast<uint32_t *>(smem + kHashEntries * 4 + warp * kRingBytes);
     for (;;) {
-        const uint32_t q = next_block(counter, lane);
-        if (q >= njobs) break;
-        const uint32_t j = job_list ? job_list[q] : q;
-        const SegJob J = jobs[j];
-        if (landed) {
-            // the input is still arriving (chunked host-to-device copy on another stream, flags written in copy order):
-            // wait for everything this segment can read -- up to the end of the block that holds seg_end, as far as the
-            // stopping sequence's match may run
-            int32_t need = J.chain_end;
-            if (!(J.flags & kSegLast)) {
-                const int32_t be = J.chain_start + (J.seg_end - J.chain_start + block_size - 1) / block_size * block_size;
-                need = be < need ? be : need;
+        uint32_t q;
+        if (nbig) {
+            // two queues (counter[0]: groups, counter[1]: single segments); a warp drains its own kind first
+            const bool fast = warp == 0;
+            const uint32_t n_own = fast ? nbig : njobs - nbig, n_other = njobs - n_own;
+            q = next_block(counter + (fast ? 0 : 1), lane);
+            if (q < n_own) {
+                q += fast ? 0u : nbig;
+            } else {
+                q = next_block(counter + (fast ? 1 : 0), lane);
+                if (q >= n_other) break;
+                q += fast ? nbig : 0u;
             }
-            if (lane == 0) {
-                const volatile uint32_t *f = landed + ((uint32_t)(need - 1 - land_origin) >> land_shift);
-                const long long t0 = clock64();
-                while (*f == 0u) {
-                    __nanosleep(500);
-                    if (clock64() - t0 > (8ll << 30)) __trap();          // seconds without the copy: fail the call, do not hang
+        } else {
+            q = next_block(counter, lane);
+            if (q >= njobs) break;
+        }
+        for (uint32_t j = job_list ? job_list[q] : q;; ++j) {
+            const SegJob J = jobs[j];
+            if (landed) {
+                // the input is still arriving (chunked host-to-device copy on another stream, flags written in copy order):
+                // wait for everything this segment can read -- up to the end of the block that holds seg_end, as far as the
+                // stopping sequence's match may run
+                int32_t need = J.chain_end;
+                if (!(J.flags & kSegLast)) {
+                    const int32_t be = J.chain_start + (J.seg_end - J.chain_start + block_size - 1) / block_size * block_size;
+                    need = be < need ? be : need;
                 }
-                __threadfence_system();
+                if (lane == 0) {
+                    const volatile uint32_t *f = landed + ((uint32_t)(need - 1 - land_origin) >> land_shift);
+                    const long long t0 = clock64();
+                    while (*f == 0u) {
+                        __nanosleep(500);
+                        if (clock64() - t0 > (8ll << 30)) __trap();          // seconds without the copy: fail the call, do not hang
+                    }
+                    __threadfence_system();
+                }
+                __syncwarp();
             }
-            __syncwarp();
+            {   // this run's pieces replace whatever an earlier run of the segment left in its slots
+                const int32_t last_pos = (J.seg_end < J.chain_end ? J.seg_end : J.chain_end) - 1;
+                const uint32_t nslots = (uint32_t)((last_pos - J.chain_start) / block_size - (J.seg_begin - J.chain_start) / block_size) + 1u;
+                for (uint32_t i = lane; i < nslots; i += 32) piece_len[J.first_slot + i] = 0;
+            }
+            if (warp == 0)
+                seg_job<Tab32, true>(base, J, j, block_size, init_table, reinterpret_cast<int32_t *>(smem), tables, snaps, snap_state, end_state,
+                                     blockbuf, blockbuf_stride, piece_off, piece_len, ring);
+            else
+                seg_job<TabG32, false>(base, J, j, block_size, init_table, tables + (size_t)j * kHashEntries, tables, snaps, snap_state,
+                                       end_state, blockbuf, blockbuf_stride, piece_off, piece_len, ring);
+            if (!follow || !(J.flags & kSegMore)) break;
+            __syncwarp();                        // the next segment reads this one's end state and table back
         }
-        {   // this run's pieces replace whatever an earlier run of the segment left in its slots
-            const int32_t last_pos = (J.seg_end < J.chain_end ? J.seg_end : J.chain_end) - 1;
-            const uint32_t nslots = (uint32_t)((last_pos - J.chain_start) / block_size - (J.seg_begin - J.chain_start) / block_size) + 1u;
-            for (uint32_t i = lane; i < nslots; i += 32) piece_len[J.first_slot + i] = 0;
-        }
-        if (warp == 0)
-            seg_job<Tab32, true>(base, J, j, block_size, init_table, reinterpret_cast<int32_t *>(smem), tables, snaps, snap_state, end_state,
-                                 blockbuf, blockbuf_stride, piece_off, piece_len, ring);
-        else
-            seg_job<TabG32, false>(base, J, j, block_size, init_table, tables + (size_t)j * kHashEntries, tables, snaps, snap_state,
-                                   end_state, blockbuf, blockbuf_stride, piece_off, piece_len, ring);
     }
 }
 
