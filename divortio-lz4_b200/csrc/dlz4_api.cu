@@ -257,6 +257,12 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
     int64_t G = (total + S - 1) / S > slots ? std::max<int64_t>(2, (W + 3 * S) / (2 * S)) : 0;
     if (const char *e = getenv("DLZ4_SEG_GROUP")) G = std::max(0, atoi(e));
     if (G < 2) G = 0;
+    // Verification unit U <= S: a warp's stretch of S bytes is itself a run of S/U segments (kSegCont / kSegMore), so that a
+    // failed speculation re-runs U bytes, not S: the re-run converges to the speculative run's state within the unit and
+    // the next member's snapshot then verifies (DLZ4_SEG_UNIT_KIB, 0 = S)
+    int64_t U = S % (128 << 10) == 0 ? (128 << 10) : S % (64 << 10) == 0 ? (64 << 10) : S;
+    if (const char *e = getenv("DLZ4_SEG_UNIT_KIB")) { const int64_t u = (int64_t)atoi(e) << 10; U = u > 0 && S % u == 0 ? u : S; }
+    const int64_t gs = S / U;
     std::vector<SegJob> jobs;
     std::vector<uint32_t> heads, singles;                  // first-launch queues (job indices)
     std::vector<uint32_t> slot_first(n, 0), slot_count(n, 0);
@@ -266,10 +272,10 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
         const int64_t cs = linked ? start : start + (int64_t)c * B;
         const int64_t ce = linked ? start + total : std::min<int64_t>(cs + B, start + total);
         const size_t j0 = jobs.size();
-        for (int64_t sb = cs; sb < ce; sb += S) {
+        for (int64_t sb = cs; sb < ce; sb += U) {
             SegJob J;
             J.chain_start = (int32_t)cs; J.chain_end = (int32_t)ce;
-            J.seg_begin = (int32_t)sb; J.seg_end = (int32_t)std::min<int64_t>(sb + S, ce);
+            J.seg_begin = (int32_t)sb; J.seg_end = (int32_t)std::min<int64_t>(sb + U, ce);
             J.warm_begin = (int32_t)std::max<int64_t>(cs, sb - W);
             J.flags = (sb == cs ? kSegFirst : 0u) | (J.seg_end == J.chain_end ? kSegLast : 0u);
             const int64_t b0 = (sb - cs) / B, b1 = (J.seg_end - 1 - cs) / B;          // blocks of the chain this segment overlaps
@@ -283,21 +289,20 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
             }
             jobs.push_back(J);
         }
-        // groups and single segments of this chain, interleaved evenly
+        // groups (G stretches) and single stretches of this chain, interleaved evenly
         const int64_t njc = (int64_t)(jobs.size() - j0);
+        const int64_t nst = (njc + gs - 1) / gs;                               // stretches of S bytes
         // (never more groups than shared-memory slots over all chains: a group on an L2-table warp would be the tail)
         const int64_t share = ((int64_t)(c + 1) * slots) / nchains - ((int64_t)c * slots) / nchains;
-        const int64_t nb = G ? std::min<int64_t>(njc / G, share) : 0, ns = njc - nb * G;
-        size_t j = j0;
+        const int64_t nb = G ? std::min<int64_t>(nst / G, share) : 0, ns = nst - nb * G;
+        int64_t j = 0;
         for (int64_t k = 0; k < nb + ns; ++k) {
-            if (nb && (k + 1) * nb / (nb + ns) > k * nb / (nb + ns)) {
-                heads.push_back((uint32_t)j);
-                for (int64_t m = 0; m < G; ++m, ++j) {
-                    if (m) jobs[j].flags |= kSegCont;
-                    if (m + 1 < G) jobs[j].flags |= kSegMore;
-                }
-            } else {
-                singles.push_back((uint32_t)j++);
+            const bool group = nb && (k + 1) * nb / (nb + ns) > k * nb / (nb + ns);
+            const int64_t members = std::min<int64_t>((group ? G : 1) * gs, njc - j);
+            (group ? heads : singles).push_back((uint32_t)(j0 + j));
+            for (int64_t m = 0; m < members; ++m, ++j) {
+                if (m) jobs[j0 + j].flags |= kSegCont;
+                if (m + 1 < members) jobs[j0 + j].flags |= kSegMore;
             }
         }
     }
@@ -325,8 +330,8 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
     CK(cudaMemcpyAsync(d_sc, slot_count.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d_plen, 0, (size_t)nslots * 4, st));
     uint32_t *counter = ctx->d_counter + 8;
-    auto launch = [&](const uint32_t *list, uint32_t count, const uint32_t *land, uint32_t nbig, uint32_t follow) -> int {
-        CK(cudaMemsetAsync(counter, 0, 8, st));
+    auto launch = [&](const uint32_t *list, uint32_t count, const uint32_t *land, uint32_t nbig, uint32_t follow, const uint8_t *chase) -> int {
+        CK(cudaMemsetAsync(counter, 0, 12, st));
         const uint64_t cap = (uint64_t)ctx->sm_count * kSegCtasPerSm;
         int grid;
         uint32_t active;
@@ -340,20 +345,16 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
         }
         k_compress_segments<<<grid, kSegWarps * 32, kSegSmemBytes, st>>>(d_work, d_jobs, list, count, (int32_t)B, init_table, d_tab, d_snap,
                                                                                   d_ss, d_es, d_buf, bstride, d_poff, d_plen, counter, active, land,
-                                                                                  land_origin, land_shift, nbig, follow);
+                                                                                  land_origin, land_shift, nbig, follow, chase, nj, counter + 2);
         ctx->launches++;
         CK(cudaGetLastError());
         return DLZ4_OK;
     };
     const uint32_t nbig = (uint32_t)heads.size();
     std::vector<uint32_t> perm(heads);
-    if (nbig) {
-        perm.insert(perm.end(), singles.begin(), singles.end());
-        CK(cudaMemcpyAsync(d_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice, st));
-        CKS(launch(d_perm, (uint32_t)perm.size(), landed, nbig, 1));
-    } else {
-        CKS(launch(nullptr, nj, landed, 0, 0));
-    }
+    perm.insert(perm.end(), singles.begin(), singles.end());
+    CK(cudaMemcpyAsync(d_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice, st));
+    CKS(launch(d_perm, (uint32_t)perm.size(), landed, nbig, 1, nullptr));
     ctx->seg_jobs = nj; ctx->seg_reruns = 0; ctx->seg_rounds = 0;
     bool speculative = false;
     for (const SegJob &J : jobs) speculative |= !(J.flags & kSegFirst);
@@ -373,9 +374,11 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
             for (uint32_t j : list) jobs[j].flags |= kSegRerun;
             CK(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nj * sizeof(SegJob), cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(d_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, st));
-            CKS(launch(d_list, (uint32_t)list.size(), nullptr, 0, 0));
+            CKS(launch(d_list, (uint32_t)list.size(), nullptr, 0, 0, getenv("DLZ4_SEG_NO_CHASE") ? nullptr : d_bad));
+            uint32_t chased = 0;
+            CK(cudaMemcpyAsync(&chased, counter + 2, 4, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));                                // `list` / `jobs` are reused next round
-            ctx->seg_reruns += (uint32_t)list.size();
+            ctx->seg_reruns += (uint32_t)list.size() + chased;
             ctx->seg_rounds++;
         }
     }

@@ -963,6 +963,22 @@ __device__ __forceinline__ void seg_job(const uint8_t *__restrict__ base, const 
     }
 }
 
+// Does the start state segment j+1 ran from (snapshot) differ from the end state of segment j?  (Same rule as k_seg_verify:
+// entries older than 65535 bytes count as empty.)  Whole warp.
+__device__ __forceinline__ bool seg_differs(const SegState *snap_next, const SegState *end_prev, const int32_t *tab_snap,
+                                            const int32_t *tab_end, uint32_t lane) {
+    const int2 a = __ldcg(reinterpret_cast<const int2 *>(snap_next)), b = __ldcg(reinterpret_cast<const int2 *>(end_prev));
+    int d = (a.x != b.x) | (a.y != b.y);
+    const int32_t horizon = b.x - 65535;
+    const int4 *A4 = reinterpret_cast<const int4 *>(tab_snap), *B4 = reinterpret_cast<const int4 *>(tab_end);
+    auto norm = [&](int32_t v) { v -= 1; return v < horizon ? -1 : v; };
+    for (uint32_t i = lane; i < kHashEntries / 4; i += 32) {
+        const int4 x = __ldcg(A4 + i), y = __ldcg(B4 + i);
+        d |= (norm(x.x) != norm(y.x)) | (norm(x.y) != norm(y.y)) | (norm(x.z) != norm(y.z)) | (norm(x.w) != norm(y.w));
+    }
+    return __any_sync(FULL, d) != 0;
+}
+
 constexpr int kSegWarps = 7;                       // warp 0: shared-memory table (64 KiB), warps 1..6: tables in L2
 constexpr int kSegCtasPerSm = 3;
 constexpr int kSegSmemBytes = kHashEntries * 4 + kSegWarps * kRingBytes;
@@ -975,7 +991,10 @@ k_compress_segments(const uint8_t *__restrict__ base, const SegJob *__restrict__
                     const uint32_t *landed /* nullable: flag per 2^land_shift input bytes, set once they are in memory */,
                     int32_t land_origin, uint32_t land_shift,
                     uint32_t nbig /* > 0: job_list[0, nbig) are heads of segment groups meant for the shared-memory warps */,
-                    uint32_t follow /* first launch: a warp runs on through kSegMore */) {
+                    uint32_t follow /* first launch: a warp runs on through kSegMore */,
+                    const uint8_t *chase_bad /* re-run launch: k_seg_verify's verdicts; a warp runs on while its new end state
+                                                differs from the next segment's snapshot (nullable) */,
+                    uint32_t total_jobs, uint32_t *chased /* count of segments re-run that way */) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     if (warp >= active_warps) return;
@@ -998,8 +1017,10 @@ k_compress_segments(const uint8_t *__restrict__ base, const SegJob *__restrict__
             q = next_block(counter, lane);
             if (q >= njobs) break;
         }
+        bool chasing = false;
         for (uint32_t j = job_list ? job_list[q] : q;; ++j) {
-            const SegJob J = jobs[j];
+            SegJob J = jobs[j];
+            if (chasing) J.flags |= kSegRerun;
             if (landed) {
                 // the input is still arriving (chunked host-to-device copy on another stream, flags written in copy order):
                 // wait for everything this segment can read -- up to the end of the block that holds seg_end, as far as the
@@ -1031,8 +1052,21 @@ k_compress_segments(const uint8_t *__restrict__ base, const SegJob *__restrict__
             else
                 seg_job<TabG32, false>(base, J, j, block_size, init_table, tables + (size_t)j * kHashEntries, tables, snaps, snap_state,
                                        end_state, blockbuf, blockbuf_stride, piece_off, piece_len, ring);
-            if (!follow || !(J.flags & kSegMore)) break;
             __syncwarp();                        // the next segment reads this one's end state and table back
+            if (follow) {
+                if (!(J.flags & kSegMore)) break;
+            } else if (chase_bad) {
+                // re-run launch: go on into the successor while it did not start from the state this segment now ends in --
+                // unless it heads this launch's list itself (bad, predecessor fine: another warp is on it)
+                if (j + 1 >= total_jobs || (jobs[j + 1].flags & kSegFirst)) break;
+                if (chase_bad[j + 1] && !chase_bad[j]) break;
+                if (!seg_differs(snap_state + j + 1, end_state + j, snaps + (size_t)(j + 1) * kHashEntries,
+                                 tables + (size_t)j * kHashEntries, lane)) break;
+                chasing = true;
+                if (lane == 0) atomicAdd(chased, 1u);
+            } else {
+                break;
+            }
         }
     }
 }

@@ -129,6 +129,6 @@ def test_reference_default_frame_1gib_linked_blocks_byte_exact(env):
     if f != want:
         a, b = np.frombuffer(f, dtype=np.uint8), np.frombuffer(want, dtype=np.uint8)
         raise AssertionError("first difference at frame byte %d" % int(np.nonzero(a != b)[0][0]))
-    assert segs == 2048 and reruns <= 64, (segs, reruns, rounds)
+    assert segs >= 2048 and reruns <= 64, (segs, reruns, rounds)
     back = dl.decompressBuffer(f, None, True, False, ctx=ctx)
     assert len(back) == n and np.array_equal(np.frombuffer(back, dtype=np.uint8), data)

@@ -93,6 +93,12 @@ def test_failed_speculation_is_rerun_not_emitted(dl):
     with seg_env(128, 512):
         segs2, reruns2, _ = _check(dl, data, 4194304, False)
     assert reruns2 <= 2, "512 KiB of warm-up should converge on log text"
+    # stretches of two and four 128 KiB verification units without warm-up: the head of every stretch fails, its re-run
+    # must hand a state to the next member that either verifies or re-runs that one as well
+    for kib in (256, 512):
+        with seg_env(kib, 0):
+            segs3, reruns3, rounds3 = _check(dl, data, 4194304, False)
+        assert segs3 == 32 and reruns3 >= 4 and rounds3 >= 1, (kib, segs3, reruns3, rounds3)
 
 
 def test_linked_chain_with_dictionary(dl):
