@@ -152,6 +152,10 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    near = None
+    if world > 1:                                 # several ranks share the host: stay on the GPU's own NUMA node
+        from divortio_lz4_b200 import sharded
+        near = sharded.bind_host_near(local)
     ctx = dl.Context(local)                       # raises if the CUDA extension or the device is missing
 
     # weak scaling: every rank owns `bytes` of the corpus = a contiguous block range of the N-GPU job
@@ -306,7 +310,8 @@ def run_b200(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round((tc + td) / args.steps * 1e3, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "block_bytes": BLOCK, "bytes_per_gpu": n, "blocks_per_gpu": nblk,
-                       "l2": "inputs (1 GiB) larger than L2 (126 MB), no flush needed", "sharding": "contiguous block range per rank, no collective"},
+                       "l2": "inputs (1 GiB) larger than L2 (126 MB), no flush needed", "sharding": "contiguous block range per rank, no collective",
+                       "host_cpus_per_rank": (len(near) if near else None)},
             "clocks": sampler.summary(),
             "e2e": ({"value": round(total / te / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
                     if e2e else None),

@@ -84,6 +84,26 @@ def compress_sharded(data, max_block_size=4194304, content_checksum=False, add_c
     return assemble(header, segs, chash)
 
 
+def bind_host_near(device_index):
+    """One process per GPU: keep this process's threads -- and therefore the pinned staging buffers it allocates next -- on
+    the CPUs of the GPU's own NUMA node (NVML's ideal CPU affinity), so that the ranks' host copies do not cross the socket
+    interconnect.  Returns the CPU set applied, or None when NVML / the affinity call is unavailable (nothing changed)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def _dist_gather(obj):
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
