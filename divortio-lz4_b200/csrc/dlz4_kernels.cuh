@@ -26,15 +26,17 @@ namespace dlz4 {
 // Phase timing (profiling build only: -DDLZ4_PHASE_TIMING): cycles per phase of the window path, summed over warps.
 #ifdef DLZ4_PHASE_TIMING
 __device__ unsigned long long g_phase[16];
-#define PT_DECL unsigned long long pt_acc[12] = {0,0,0,0,0,0,0,0,0,0,0,0}; long long pt_t = clock64();
+#define PT_DECL unsigned long long pt_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; long long pt_t = clock64();
 #define PT_MARK(i) { const long long pt_n = clock64(); pt_acc[i] += (unsigned long long)(pt_n - pt_t); pt_t = pt_n; }
 #define PT_COUNT(i, v) { pt_acc[i] += (v); }
-#define PT_FLUSH if (lane_id() == 0) { for (int pt_k = 0; pt_k < 12; ++pt_k) atomicAdd(&g_phase[pt_k], pt_acc[pt_k]); }
+#define PT_FLUSH if (lane_id() == 0) { for (int pt_k = 0; pt_k < 16; ++pt_k) atomicAdd(&g_phase[pt_k], pt_acc[pt_k]); }
+#define PT_USE(x) asm volatile("" ::"r"((uint32_t)(x)));
 #else
 #define PT_DECL
 #define PT_MARK(i)
 #define PT_COUNT(i, v)
 #define PT_FLUSH
+#define PT_USE(x)
 #endif
 
 constexpr uint32_t FULL = 0xffffffffu;
@@ -428,9 +430,11 @@ __device__ uint32_t compress_span_warp(const uint8_t *__restrict__ base, const i
 #pragma unroll
             for (int k = 0; k < 8; ++k) Sw[k] = __funnelshift_r(tw[k], tw[k + 1], sh);
             const uint32_t h = (Sw[0] * 2654435761u) >> 18;
+            PT_USE(h) PT_MARK(12)
             const uint32_t old = tab_raw(T, h);
             const int32_t cand = tab_dec(T, old);
             const bool ok = cand >= 0 && cand != p && (((uint32_t)(p - cand)) >> 16) == 0;
+            PT_USE(ok) PT_MARK(13)
             // candidate bytes cand .. cand+35 as three aligned 16-byte loads (3 L1 wavefronts per lane instead of 9)
             uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;
             uint32_t cs = 0;

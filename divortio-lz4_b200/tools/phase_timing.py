@@ -33,12 +33,15 @@ e1.record()
 torch.cuda.synchronize()
 L.dlz4_phase_counters(cnt)
 v = list(cnt)
-names = ["loop head/other", "line cache", "A: shfl+hash+lookup+issue loads", "insert/readback/ballot", "verify+extend (waits for loads)",
-         "B: resolve", "C+D: emit + un-insert", "trailing literals + sync", "batch step (fallback)"]
+names = ["loop head/other", "forward ring (cp.async refill + wait)", "A: shfl+hash+table gather+issue candidate loads",
+         "same-slot test (match.any + ballot)", "verify+extend (waits for the candidate loads)", "B: resolve (walk)",
+         "D+C: table scatter + emit", "trailing literals + sync", "batch step (fallback)"]
 windows, conflicts, batches = v[9], v[10], v[11]
-tot = sum(v[:9])
+tot = sum(v[:9]) + v[12] + v[13]
 print("%s %d MiB: %.2f ms, %d windows (%.1f B/window), %d conflict windows (%.1f%%), %d batch steps" %
       (kind, mib, e0.elapsed_time(e1), windows, n / max(windows, 1), conflicts, 100.0 * conflicts / max(windows, 1), batches))
 for i, nm in enumerate(names):
-    print("  %-42s %8.1f cycles/window  %5.1f%%" % (nm, v[i] / max(windows, 1), 100.0 * v[i] / tot))
+    x = v[i] + (v[12] + v[13] if i == 2 else 0)
+    print("  %-42s %8.1f cycles/window  %5.1f%%" % (nm, x / max(windows, 1), 100.0 * x / tot))
 print("  total %.1f cycles/window" % (tot / max(windows, 1)))
+print("  inside A: source bytes + hash %.1f, table gather until usable %.1f cycles/window" % (v[12] / max(windows, 1), v[13] / max(windows, 1)))
