@@ -21,8 +21,8 @@ def dl():
 class seg_env:
     """DLZ4_SEG_KIB / DLZ4_SEG_WARM_KIB are read by every call."""
 
-    def __init__(self, seg_kib=None, warm_kib=None):
-        self.new = {"DLZ4_SEG_KIB": seg_kib, "DLZ4_SEG_WARM_KIB": warm_kib}
+    def __init__(self, seg_kib=None, warm_kib=None, group=None, unit_kib=None):
+        self.new = {"DLZ4_SEG_KIB": seg_kib, "DLZ4_SEG_WARM_KIB": warm_kib, "DLZ4_SEG_GROUP": group, "DLZ4_SEG_UNIT_KIB": unit_kib}
 
     def __enter__(self):
         self.old = {k: os.environ.get(k) for k in self.new}
@@ -99,6 +99,19 @@ def test_failed_speculation_is_rerun_not_emitted(dl):
         with seg_env(kib, 0):
             segs3, reruns3, rounds3 = _check(dl, data, 4194304, False)
         assert segs3 == 32 and reruns3 >= 4 and rounds3 >= 1, (kib, segs3, reruns3, rounds3)
+
+
+@pytest.mark.parametrize("seg_kib,warm_kib,group,unit_kib", [(64, 128, 3, None), (128, 0, 2, 64), (256, 64, 5, 64), (128, 512, 4, 128)])
+def test_segment_groups_and_verification_units(dl, seg_kib, warm_kib, group, unit_kib):
+    """Groups of stretches on the shared-memory warps (two queues, kSegCont / kSegMore) and verification units smaller than
+    a stretch, forced at sizes where the defaults would not use them; short warm-ups make heads fail, so re-runs chase into
+    members that continued from a wrong state.  Linked chains and independent large blocks, every corpus."""
+    n = 6 * 1024 * 1024 + 4321
+    with seg_env(seg_kib, warm_kib, group, unit_kib):
+        for name, data in _corpora(n).items():
+            for bs, indep in ((4194304, False), (65536, False), (4194304, True), (1048576, True)):
+                segs, reruns, rounds = _check(dl, data, bs, indep)
+                assert segs >= 6, (name, bs, indep, segs)
 
 
 def test_linked_chain_with_dictionary(dl):
