@@ -45,6 +45,7 @@ struct dlz4_ctx {
     int32_t *d_table = nullptr;         // int32[16384] scratch table
     int hybrid = 1;                     // 64 KiB fresh blocks: hybrid kernel (L2-resident tables) instead of the 7-warp one
     int hy_grid = 0;                    // CTAs that fill the device (sm_count x kHyCtasPerSm)
+    int hy_active = 0;                  // cap on the warps used per hybrid CTA (DLZ4_HY_ACTIVE, 0 = all 7; A/B runs)
     uint16_t *d_gtabs = nullptr;        // kGtabRegions x hy_grid x kHyGlWarps tables of 16384 x u16 (one region per stream lane)
     Buf work, comp, seg, out, meta, aux, pin;
     std::string last_error;
@@ -142,7 +143,8 @@ int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, 
         // a batch on its own spreads over as many SMs as it has blocks (fewer active warps per CTA); a pipeline chunk
         // (`dense`) packs 7 chains per CTA so that the chunks in flight on the other lanes find free CTA slots
         const int grid = (int)std::min<uint64_t>(dense ? (n + kHyWarps - 1) / kHyWarps : n, (uint64_t)ctx->hy_grid);
-        const uint32_t active = dense ? (uint32_t)kHyWarps : (uint32_t)std::min<uint64_t>((n + grid - 1) / grid, (uint64_t)kHyWarps);
+        uint32_t active = dense ? (uint32_t)kHyWarps : (uint32_t)std::min<uint64_t>((n + grid - 1) / grid, (uint64_t)kHyWarps);
+        if (ctx->hy_active) active = std::min<uint32_t>(active, (uint32_t)ctx->hy_active);
         k_compress_fresh16h<<<grid, kHyWarps * 32, kHySmemBytes, st>>>(
             src, src_off, src_len, n, dst, dst_off, comp_len, counter,
             ctx->d_gtabs + region * (size_t)ctx->hy_grid * kHyGlWarps * kHashEntries, active);
@@ -564,6 +566,7 @@ int dlz4_init(int device, dlz4_ctx **out) {
     if (const char *e = getenv("DLZ4_JUMP_MIN_KIB")) ctx->jump_min_bytes = (uint64_t)atoll(e) << 10;
     if (const char *e = getenv("DLZ4_HYBRID")) ctx->hybrid = atoi(e) != 0;      // 0: the 7-warp shared-memory-only kernel (A/B runs)
     ctx->hy_grid = ctx->sm_count * kHyCtasPerSm;
+    if (const char *e = getenv("DLZ4_HY_ACTIVE")) ctx->hy_active = std::max(0, std::min(kHyWarps, atoi(e)));
     CK(cudaMalloc(&ctx->d_gtabs, (size_t)kGtabRegions * ctx->hy_grid * kHyGlWarps * kHashEntries * 2));
     CK(cudaFuncSetAttribute(k_compress_fresh16h, cudaFuncAttributeMaxDynamicSharedMemorySize, kHySmemBytes));
     CK(cudaFuncSetAttribute(k_compress_overlay, cudaFuncAttributeMaxDynamicSharedMemorySize, kHySmemBytes));
