@@ -159,6 +159,36 @@ class LZ4Encoder(object):
         return out
 
 
+class _Pinned(object):
+    """Grow-only page-locked staging buffer (the frame calls copy at the full PCIe rate from / to it)."""
+
+    def __init__(self):
+        self.ptr, self.arr = None, None
+
+    def get(self, nbytes):
+        if self.arr is None or self.arr.size < nbytes:
+            self.free()
+            cap = max(int(nbytes), 1 << 20)
+            cap += cap >> 2
+            self.ptr = api.lib().dlz4_pinned_alloc(cap)
+            if not self.ptr:
+                raise MemoryError("dlz4_pinned_alloc(%d)" % cap)
+            self.arr = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)), shape=(cap,))
+        return self.arr
+
+    def free(self):
+        if self.ptr:
+            self.arr = None
+            api.lib().dlz4_pinned_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class LZ4Decoder(object):
     """new LZ4Decoder(dictionary=null, verifyChecksum=true); update(chunk) -> list of decoded chunks (one per block)."""
 
@@ -167,7 +197,7 @@ class LZ4Decoder(object):
         self.dictionary = api.ensureBuffer(dictionary) if dictionary is not None and len(dictionary) > 0 else None
         self.verifyChecksum = bool(verifyChecksum)
         self.state = "magic"
-        self.buffer = b""
+        self.buffer = bytearray()
         self.hasher = None
         self.window = np.zeros(0, dtype=np.uint8)
         if self.dictionary is not None:
@@ -175,9 +205,10 @@ class LZ4Decoder(object):
         self.blockIndependence = True
         self.hasBlockChecksum = self.hasContentChecksum = self.hasContentSize = self.hasDictId = False
         self._bd = 0x70
+        self._pin_frame, self._pin_out = _Pinned(), _Pinned()
 
     def update(self, chunk):
-        self.buffer += bytes(api.ensureBuffer(chunk).tobytes())
+        self.buffer += memoryview(np.ascontiguousarray(api.ensureBuffer(chunk)))
         output = []
         while True:
             if self.state == "magic":                                            # lz4Decode.js:118-131
@@ -185,7 +216,7 @@ class LZ4Decoder(object):
                     break
                 if int.from_bytes(self.buffer[:4], "little") != 0x184D2204:
                     raise api.LZ4Error(api.E_BAD_MAGIC, "LZ4: Invalid Magic Number")
-                self.buffer = self.buffer[4:]
+                del self.buffer[:4]
                 self.state = "header"
                 self.hasher = api.XXHash32(0, ctx=self._ctx) if self.verifyChecksum else None
             if self.state == "header":                                           # :134-178
@@ -209,27 +240,28 @@ class LZ4Decoder(object):
                     actual = api.xxHash32(self.dictionary, 0, ctx=self._ctx)
                     if actual != expected:
                         raise api.LZ4Error(api.E_DICT_OOB, "LZ4: Dictionary ID Mismatch. Header: 0x%x, Provided: 0x%x" % (expected, actual))
-                self.buffer = self.buffer[need:]
+                del self.buffer[:need]
                 self.state = "blocks"
             if self.state == "blocks":                                           # :181-243, every complete block at once
-                blocks, pos, end_mark = [], 0, False
+                nblocks, pos, end_mark, body_end = 0, 0, False, 0
+                have = len(self.buffer)
                 while True:
-                    if len(self.buffer) - pos < 4:
+                    if have - pos < 4:
                         break
                     val = int.from_bytes(self.buffer[pos:pos + 4], "little")
                     if val == 0:
                         pos += 4
                         end_mark = True
                         break
-                    size = val & 0x7FFFFFFF
-                    need = size + (4 if self.hasBlockChecksum else 0)
-                    if len(self.buffer) - pos - 4 < need:
+                    need = (val & 0x7FFFFFFF) + (4 if self.hasBlockChecksum else 0)
+                    if have - pos - 4 < need:
                         break
-                    blocks.append((val, self.buffer[pos + 4:pos + 4 + size]))
+                    nblocks += 1
                     pos += 4 + need
-                if blocks:
-                    output.extend(self._decode(blocks))
-                self.buffer = self.buffer[pos:]
+                    body_end = pos
+                if nblocks:
+                    output.extend(self._decode(nblocks, body_end))
+                del self.buffer[:pos]
                 if not end_mark:
                     break
                 self.state = "checksum"
@@ -240,35 +272,45 @@ class LZ4Decoder(object):
                     if self.verifyChecksum and self.hasher:
                         if int.from_bytes(self.buffer[:4], "little") != self.hasher.digest():
                             raise api.LZ4Error(api.E_CONTENT_CHECKSUM, "LZ4: Content Checksum Error")
-                    self.buffer = self.buffer[4:]
+                    del self.buffer[:4]
                 self.state = "magic"
                 self.hasher = None
                 if len(self.buffer) == 0:
                     break
         return output
 
-    def _decode(self, blocks):
-        """All blocks of one update() as a synthetic frame: linked blocks see window ++ earlier output (:215-222,:240)."""
-        flg = (1 << 6) | (0x20 if self.blockIndependence else 0)
+    def _decode(self, nblocks, body_end):
+        """The `nblocks` complete blocks in buffer[:body_end] as a synthetic frame (size words, data and block checksums as
+        they came, copied once into page-locked memory): linked blocks see window ++ earlier output (:215-222,:240).  Block
+        checksums are skipped like in the reference's stream decoder."""
+        flg = (1 << 6) | (0x20 if self.blockIndependence else 0) | (0x10 if self.hasBlockChecksum else 0)
         body = bytes([flg, self._bd])
         hdr = _u32(0x184D2204) + body + bytes([(api.xxHash32(body, 0, ctx=self._ctx) >> 8) & 0xFF])
-        frame = hdr + b"".join(_u32(v) + d for v, d in blocks) + _u32(0)
-        f = np.frombuffer(frame, dtype=np.uint8)
+        total = len(hdr) + body_end + 4
+        f = self._pin_frame.get(total + 16)
+        f[:len(hdr)] = np.frombuffer(hdr, dtype=np.uint8)
+        src = np.frombuffer(self.buffer, dtype=np.uint8, count=body_end)
+        f[len(hdr):len(hdr) + body_end] = src
+        del src                                                                  # (the bytearray is resized by the caller)
+        f[len(hdr) + body_end:total] = 0                                         # EndMark
         bmax = BLOCK_MAX_SIZES.get((self._bd >> 4) & 7, 4194304)
-        out = np.empty(len(blocks) * bmax + 16, dtype=np.uint8)
+        out = self._pin_out.get(nblocks * bmax + 16)
         n = C.c_uint64(0)
-        olen = np.zeros(len(blocks), dtype=np.uint32)
+        olen = np.zeros(nblocks, dtype=np.uint32)
         hist = self.window if (not self.blockIndependence and self.window.size) else None
-        st = api.lib().dlz4_frame_decompress_ex(self._ctx.handle, api._ptr(f), f.size, api._ptr(hist), hist.size if hist is not None else 0, 0,
-                                                api._ptr(out), out.size - 16, C.byref(n), api._ptr(olen))
+        st = api.lib().dlz4_frame_decompress_ex(self._ctx.handle, api._ptr(f), total, api._ptr(hist), hist.size if hist is not None else 0, 0,
+                                                api._ptr(out), nblocks * bmax, C.byref(n), api._ptr(olen))
         self._ctx.check(st)
         chunks, p = [], 0
-        for k in range(len(blocks)):
+        for k in range(nblocks):
             chunks.append(out[p:p + int(olen[k])].tobytes())
             p += int(olen[k])
         decoded = out[:p]
         if self.hasher and p:
             self.hasher.update(decoded)
         if not self.blockIndependence and p:                                     # _updateWindow, :278-304: the last 64 KiB
-            self.window = np.concatenate([self.window, decoded])[-MAX_WINDOW_SIZE:].copy()
+            if p >= MAX_WINDOW_SIZE:
+                self.window = decoded[p - MAX_WINDOW_SIZE:].copy()
+            else:
+                self.window = np.concatenate([self.window, decoded])[-MAX_WINDOW_SIZE:].copy()
         return chunks
