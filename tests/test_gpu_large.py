@@ -132,3 +132,30 @@ def test_reference_default_frame_1gib_linked_blocks_byte_exact(env):
     assert segs >= 2048 and reruns <= 64, (segs, reruns, rounds)
     back = dl.decompressBuffer(f, None, True, False, ctx=ctx)
     assert len(back) == n and np.array_equal(np.frombuffer(back, dtype=np.uint8), data)
+
+
+def test_frames_compressed_while_the_input_is_still_arriving(env):
+    """Frames of 64 MiB and more are parsed under a chunked host-to-device copy (16 MiB chunks + landed flags).
+    Odd sizes, a dictionary (chunk and block boundaries no longer coincide), linked and independent large blocks, pageable
+    and page-locked callers' buffers: byte-exact against the oracle, and back."""
+    import ctypes as C
+    dl, corpus, dev, torch, ctx = env
+    n = 80 * 1024 * 1024 + 12345
+    data = corpus.mixed(9, n)
+    dic = corpus.log(10, 100000)
+    L = dl.lib()
+    pin = L.dlz4_pinned_alloc(n + 64)
+    pinned = np.ctypeslib.as_array(C.cast(pin, C.POINTER(C.c_uint8)), shape=(n + 64,))[:n]
+    pinned[:] = data
+    try:
+        for src in (data, pinned):
+            for bs, indep, d in ((4194304, False, None), (1048576, False, dic), (4194304, True, None), (262144, False, None)):
+                f = dl.compressBuffer(src, d, bs, indep, False, True, ctx=ctx)
+                want = oracle.compress_buffer(data, d, bs, indep, False, True)
+                assert len(f) == len(want) and f == want, (bs, indep, d is not None)
+                segs, reruns, rounds = ctx.segment_stats
+                assert segs >= 64
+        back = dl.decompressBuffer(f, None, True, False, ctx=ctx)
+        assert len(back) == n and np.array_equal(np.frombuffer(back, dtype=np.uint8), data)
+    finally:
+        L.dlz4_pinned_free(pin)
