@@ -1694,7 +1694,7 @@ k_jd_scan(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
 // reproduces the reference's error order; the chunked scan only ever handles well-formed blocks.
 constexpr uint32_t kJdpChunk = 2048;
 constexpr uint32_t kJdpSlowBit = 0x80000000u;
-struct JdpExit { uint32_t ex, cnt, adv, pad; };                 // ex: position where the chain leaves the chunk | kJdpSlowBit
+struct JdpExit { uint32_t ex, ca; };      // ex: position where the chain leaves the chunk | kJdpSlowBit; ca = hops:10 | output bytes:22
 struct JdpRun { uint32_t pos, ns, op, pad; };
 struct JdpSlow { uint32_t op, litp, lit, ml, off, ns, pad0, pad1; };
 
@@ -1788,7 +1788,12 @@ k_jdp_exit(const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ sr
     }
     for (int k = 0; k < PER; ++k) {
         const uint32_t i = threadIdx.x + k * 256, a = c0 + i;
-        if (a < cend) exits[g + a] = JdpExit{ex[i], cn[i], av[i], 0u};
+        if (a < cend) {
+            // 8 bytes per compressed byte.  A chain that would overflow the 22 bits (> 4 MiB out of one 2 KiB chunk, i.e.
+            // never in a valid 4 MiB block) is handed to the serial form token by token, which is exact for any token
+            const bool fits = av[i] < (1u << 22);
+            exits[g + a] = fits ? JdpExit{ex[i], (cn[i] << 22) | av[i]} : JdpExit{a | kJdpSlowBit, 0u};
+        }
     }
 }
 
@@ -1833,13 +1838,13 @@ k_jdp_hop(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
         if (n > block_max) fb = true;
     } else {
         while (pos < n) {
-            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(exits + g + pos));
-            const JdpExit E{raw.x, raw.y, raw.z, 0u};
-            if (E.cnt) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(exits + g + pos));
+            const JdpExit E{raw.x, raw.y};
+            if (E.ca >> 22) {
                 if (nr >= cap) { fb = true; break; }
                 if (lane == 0) R[nr] = JdpRun{pos, ns, (uint32_t)op, 0u};
                 ++nr;
-                ns += E.cnt; op += E.adv;
+                ns += E.ca >> 22; op += E.ca & ((1u << 22) - 1u);
                 if (op > block_max) { fb = true; break; }
             }
             if (!(E.ex & kJdpSlowBit)) { pos = E.ex; continue; }
