@@ -1780,11 +1780,13 @@ k_jdp_exit(const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ sr
             if (t != 0xFFFFu) { t2[k] = tgt[t]; e2[k] = ex[t]; c2[k] += cn[t]; v2[k] += av[t]; }
         }
         __syncthreads();
+        int open = 0;
         for (int k = 0; k < PER; ++k) {
             const uint32_t i = threadIdx.x + k * 256;
             tgt[i] = t2[k]; ex[i] = e2[k]; cn[i] = c2[k]; av[i] = v2[k];
+            open |= t2[k] != 0xFFFFu;
         }
-        __syncthreads();
+        if (!__syncthreads_or(open)) break;                      // every chain has left the chunk
     }
     for (int k = 0; k < PER; ++k) {
         const uint32_t i = threadIdx.x + k * 256, a = c0 + i;
