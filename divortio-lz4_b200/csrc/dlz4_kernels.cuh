@@ -1749,8 +1749,9 @@ k_jdp_next(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off
 __global__ void __launch_bounds__(256)
 k_jdp_exit(const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ src_len, const uint8_t *__restrict__ stored,
            const uint16_t *__restrict__ nx, const uint16_t *__restrict__ adv, JdpExit *exits) {
-    __shared__ uint16_t tgt[kJdpChunk];
-    __shared__ uint32_t ex[kJdpChunk], cn[kJdpChunk], av[kJdpChunk];
+    // per entry: where its chain stands (tgt: index inside the chunk, 0xFFFF once it has left), hops so far, the exit position
+    // and the output bytes so far; (hops << 16 | tgt) share a word so that a doubling step is three loads and three stores
+    __shared__ uint32_t ct[kJdpChunk], ex[kJdpChunk], av[kJdpChunk];
     const uint32_t b = blockIdx.y, n = src_len[b];
     const uint32_t c0 = blockIdx.x * kJdpChunk;
     if (c0 >= n || stored[b]) return;
@@ -1759,32 +1760,32 @@ k_jdp_exit(const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ sr
     constexpr int PER = kJdpChunk / 256;
     for (int k = 0; k < PER; ++k) {
         const uint32_t i = threadIdx.x + k * 256, a = c0 + i;
-        uint16_t t = 0xFFFFu; uint32_t e = 0, c = 0, v = 0;
+        uint32_t t = 0xFFFFu, e = 0, c = 0, v = 0;
         if (a < cend) {
             const uint32_t j = nx[g + a];
             if (j == 0) e = a | kJdpSlowBit;
             else {
                 c = 1; v = adv[g + a];
-                if (a + j >= cend) e = a + j; else t = (uint16_t)(i + j);
+                if (a + j >= cend) e = a + j; else t = i + j;
             }
         }
-        tgt[i] = t; ex[i] = e; cn[i] = c; av[i] = v;
+        ct[i] = (c << 16) | t; ex[i] = e; av[i] = v;
     }
     __syncthreads();
     for (int round = 0; round < 11; ++round) {                   // a hop is >= 3 bytes: <= 683 hops per chunk
-        uint16_t t2[PER]; uint32_t e2[PER], c2[PER], v2[PER];
+        uint32_t ct2[PER], e2[PER], v2[PER];
         for (int k = 0; k < PER; ++k) {
             const uint32_t i = threadIdx.x + k * 256;
-            const uint16_t t = tgt[i];
-            t2[k] = t; e2[k] = ex[i]; c2[k] = cn[i]; v2[k] = av[i];
-            if (t != 0xFFFFu) { t2[k] = tgt[t]; e2[k] = ex[t]; c2[k] += cn[t]; v2[k] += av[t]; }
+            const uint32_t c = ct[i], t = c & 0xFFFFu;
+            ct2[k] = c; e2[k] = ex[i]; v2[k] = av[i];
+            if (t != 0xFFFFu) { const uint32_t d = ct[t]; ct2[k] = (c & 0xFFFF0000u) + d; e2[k] = ex[t]; v2[k] += av[t]; }
         }
         __syncthreads();
         int open = 0;
         for (int k = 0; k < PER; ++k) {
             const uint32_t i = threadIdx.x + k * 256;
-            tgt[i] = t2[k]; ex[i] = e2[k]; cn[i] = c2[k]; av[i] = v2[k];
-            open |= t2[k] != 0xFFFFu;
+            ct[i] = ct2[k]; ex[i] = e2[k]; av[i] = v2[k];
+            open |= (ct2[k] & 0xFFFFu) != 0xFFFFu;
         }
         if (!__syncthreads_or(open)) break;                      // every chain has left the chunk
     }
@@ -1794,7 +1795,7 @@ k_jdp_exit(const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ sr
             // 8 bytes per compressed byte.  A chain that would overflow the 22 bits (> 4 MiB out of one 2 KiB chunk, i.e.
             // never in a valid 4 MiB block) is handed to the serial form token by token, which is exact for any token
             const bool fits = av[i] < (1u << 22);
-            exits[g + a] = fits ? JdpExit{ex[i], (cn[i] << 22) | av[i]} : JdpExit{a | kJdpSlowBit, 0u};
+            exits[g + a] = fits ? JdpExit{ex[i], ((ct[i] >> 16) << 22) | av[i]} : JdpExit{a | kJdpSlowBit, 0u};
         }
     }
 }
