@@ -409,7 +409,7 @@ int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, uint64_t frame_span, 
     const uint32_t per_unit = std::max<uint32_t>(1u, unit_bytes / B);
     const uint32_t nunits = (n + per_unit - 1) / per_unit;
     int rounds = 1;
-    while ((1ull << (2 * rounds)) < (uint64_t)per_unit * B) ++rounds;    // chain depth <= unit bytes, quartered per round (kJdHops = 4)
+    while ((1ull << (kJdHopBits * rounds)) < (uint64_t)per_unit * B) ++rounds;    // chain depth <= unit bytes, / kJdHops per round
     ++rounds;
     size_t off = 0;
     auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };

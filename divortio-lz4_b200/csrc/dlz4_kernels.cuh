@@ -1491,7 +1491,8 @@ k_decompress_chain(const uint8_t *__restrict__ src, const uint64_t *__restrict__
 // frame was parsed: the result is the byte-exact LZ4 decode whatever the dependency structure.
 struct JdSeq { uint32_t op, ip, lit, ml, off, m0, pad1, pad2; };      // block-relative output / input positions; m0 = first
                                                                       // output byte of the WHOLE match (chunked records share it)
-constexpr int kJdHops = 4;                                             // pointer links followed per element per round
+constexpr int kJdHopBits = 3;
+constexpr int kJdHops = 1 << kJdHopBits;                                // pointer links followed per element per round
 constexpr uint32_t kJdChunk = 4096;                                    // long literal runs / matches are recorded in chunks
 
 __device__ __forceinline__ void jd_emit_rec(JdSeq *rec, uint32_t &ns, uint32_t op, uint32_t ip, uint32_t lit, uint32_t ml, uint32_t off,
@@ -2037,7 +2038,7 @@ k_jd_round(int32_t *P, const uint64_t *__restrict__ base, uint32_t b0, uint32_t 
             if (i >= len) break;
             int32_t v = P[i];
             if (v >= 0) {
-                // up to kJdHops links per round (v < i: an earlier byte of the unit).  Every link read spans >= 4^round original
+                // up to kJdHops links per round (v < i: an earlier byte of the unit).  Every link read spans >= kJdHops^round original
                 // hops, whether it is this round's value or the last one's, so log4(unit bytes) rounds resolve any chain.
 #pragma unroll
                 for (int h = 0; h < kJdHops && v >= 0; ++h) v = P[v];
