@@ -1491,7 +1491,7 @@ k_decompress_chain(const uint8_t *__restrict__ src, const uint64_t *__restrict__
 // frame was parsed: the result is the byte-exact LZ4 decode whatever the dependency structure.
 struct JdSeq { uint32_t op, ip, lit, ml, off, m0, pad1, pad2; };      // block-relative output / input positions; m0 = first
                                                                       // output byte of the WHOLE match (chunked records share it)
-constexpr int kJdHopBits = 3;
+constexpr int kJdHopBits = 4;
 constexpr int kJdHops = 1 << kJdHopBits;                                // pointer links followed per element per round
 constexpr uint32_t kJdChunk = 4096;                                    // long literal runs / matches are recorded in chunks
 
