@@ -404,7 +404,9 @@ int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, uint64_t frame_span, 
                     cudaStream_t st, uint8_t *host_out, uint64_t host_cap, bool *copied_out) {
     std::vector<uint64_t> seq_base(n + 1, 0);
     for (uint32_t i = 0; i < n; ++i) seq_base[i + 1] = seq_base[i] + slen[i] / 3 + B / 2048 + 8;
-    uint32_t unit_bytes = 16u << 20;
+    // 16 MiB units; 32 MiB for frames of half a GiB and more (fewer launches; the first unit ships later, which only a long
+    // frame can afford: 1 GiB 40.2 -> 38.2 ms, 128 MiB 5.8 -> 6.0 ms)
+    uint32_t unit_bytes = (uint64_t)n * B >= (512ull << 20) ? 32u << 20 : 16u << 20;
     if (const char *e = getenv("DLZ4_JD_UNIT_MIB")) unit_bytes = (uint32_t)std::max(1, atoi(e)) << 20;
     const uint32_t per_unit = std::max<uint32_t>(1u, unit_bytes / B);
     const uint32_t nunits = (n + per_unit - 1) / per_unit;
