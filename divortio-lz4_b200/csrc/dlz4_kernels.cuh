@@ -1986,13 +1986,15 @@ k_jd_fill(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
     const uint8_t *in = src + src_off[b];
     const JdSeq *rec = seqs + seq_base[b];
     const uint64_t ustart = base[b0], bstart = base[b];
+    const int32_t brel = (int32_t)(bstart - ustart);             // the block's start relative to the unit (units are <= 64 MiB)
     const uint32_t ns = nseq[b];
     uint32_t pending = 0;
     for (uint32_t si = gw; si < ns; si += nw) {
         const JdSeq q = rec[si];
         const uint32_t total = q.lit + q.ml;
+        const int32_t xr0 = brel + (int32_t)q.op;                // the sequence's first output byte, relative to the unit
         for (uint32_t j = lane; j < total; j += 32) {
-            const uint64_t x = bstart + q.op + j;                // global output position
+            const int32_t xr = xr0 + (int32_t)j;
             int32_t v;
             if (j < q.lit) {
                 v = ~(int32_t)in[q.ip + j];
@@ -2000,19 +2002,23 @@ k_jd_fill(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
                 // a match longer than its offset repeats the `off` bytes in front of it: point every byte straight at them
                 // (a zero run of a whole block is then one link deep instead of a chain as long as the run)
                 const uint32_t dm = q.op + j - q.m0;             // distance into the whole match
-                const int64_t sg = dm < q.off ? (int64_t)x - q.off : (int64_t)bstart + q.m0 - q.off + (dm % q.off);   // global source
-                const int64_t sb = sg - (int64_t)bstart;         // relative to the block's start
-                if (sg >= (int64_t)ustart && (linked || sb >= 0)) {
-                    v = (int32_t)(sg - (int64_t)ustart);         // inside the unit: resolve by doubling
+                const int32_t sr = dm < q.off ? xr - (int32_t)q.off
+                                              : brel + (int32_t)q.m0 - (int32_t)q.off + (int32_t)(dm % q.off);   // source, relative to the unit
+                const int32_t sb = sr - brel;                    // relative to the block's start
+                if (sr >= 0 && (linked || sb >= 0)) {
+                    v = sr;                                      // inside the unit: resolve by doubling
                     ++pending;
-                } else if (linked ? sg >= 0 : sb >= 0) {
-                    v = ~(int32_t)out[sg];                       // earlier unit: final already
                 } else {
-                    // dictionary: directly before output position 0 (linked) / before every block (independent)
-                    v = ~(int32_t)dict[(int64_t)dict_len + (linked ? sg : sb)];
+                    const int64_t sg = (int64_t)ustart + sr;     // global output position
+                    if (linked ? sg >= 0 : sb >= 0) {
+                        v = ~(int32_t)out[sg];                   // earlier unit: final already
+                    } else {
+                        // dictionary: directly before output position 0 (linked) / before every block (independent)
+                        v = ~(int32_t)dict[(int64_t)dict_len + (linked ? sg : (int64_t)sb)];
+                    }
                 }
             }
-            P[x - ustart] = v;
+            P[xr] = v;
         }
     }
     pending = __reduce_add_sync(FULL, pending);
