@@ -18,6 +18,7 @@ namespace {
 constexpr int kWarpsFresh16 = 7;     // 7 x 32 KiB tables = 224 KiB of the 227 KiB a CTA may own
 constexpr int kWarpsGeneric32 = 3;   // 3 x 64 KiB
 constexpr int kWarpsDecode = 8;
+constexpr int kJdGroupEvent = 112;    // evp[112..127]: input groups of the jump decoder (evp[0..111]: its output units)
 constexpr int kGtabRegions = 5;      // L2-table regions: work-queue counter 0 (device API) and 1..4 (pipeline lanes)
 
 struct Buf {
@@ -401,7 +402,9 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
 int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, uint64_t frame_span, const uint64_t *d_soff, const uint32_t *d_slen, const uint8_t *d_stored,
                     const std::vector<uint32_t> &slen, uint32_t n, uint32_t B, uint8_t *d_out, uint64_t cap_total, const uint8_t *d_dict,
                     uint32_t dwin, bool linked, uint32_t *d_olen, uint8_t *d_status, std::vector<uint8_t> &status_h, uint64_t *total,
-                    cudaStream_t st, uint8_t *host_out, uint64_t host_cap, bool *copied_out) {
+                    cudaStream_t st, uint8_t *host_out, uint64_t host_cap, bool *copied_out,
+                    const std::vector<uint32_t> *groups = nullptr /* the frame is still arriving: group g = blocks [(*groups)[g],
+                                                                     (*groups)[g+1]) is in memory once event evp[kJdGroupEvent + g] fires */) {
     std::vector<uint64_t> seq_base(n + 1, 0);
     for (uint32_t i = 0; i < n; ++i) seq_base[i + 1] = seq_base[i] + slen[i] / 3 + B / 2048 + 8;
     // 16 MiB units; 32 MiB for frames of half a GiB and more (fewer launches; the first unit ships later, which only a long
@@ -456,8 +459,14 @@ int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, uint64_t frame_span, 
         uint32_t *d_nr = (uint32_t *)(A + o_nr), *d_nsl = (uint32_t *)(A + o_nsl);
         uint8_t *d_fb = A + o_fb;
         CK(cudaMemcpyAsync(d_lb, list_base.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-        k_jdp_next<<<dim3((max_slen + 255) / 256, n), 256, 0, st>>>(d_frame, d_soff, d_slen, d_stored, d_nx, d_adv);
-        k_jdp_exit<<<dim3((max_slen + kJdpChunk - 1) / kJdpChunk, n), 256, 0, st>>>(d_soff, d_slen, d_stored, d_nx, d_adv, d_ex);
+        const uint32_t ngroups = groups ? (uint32_t)groups->size() - 1 : 1;
+        for (uint32_t gi = 0; gi < ngroups; ++gi) {
+            // per-byte sizing and chunk exits need only a block's own bytes: start on every group of blocks as it lands
+            const uint32_t g0 = groups ? (*groups)[gi] : 0, g1 = groups ? (*groups)[gi + 1] : n;
+            if (groups) CK(cudaStreamWaitEvent(st, ctx->evp[kJdGroupEvent + gi], 0));
+            k_jdp_next<<<dim3((max_slen + 255) / 256, g1 - g0), 256, 0, st>>>(d_frame, d_soff + g0, d_slen + g0, d_stored + g0, d_nx, d_adv);
+            k_jdp_exit<<<dim3((max_slen + kJdpChunk - 1) / kJdpChunk, g1 - g0), 256, 0, st>>>(d_soff + g0, d_slen + g0, d_stored + g0, d_nx, d_adv, d_ex);
+        }
         k_jdp_hop<<<(n + 7) / 8, 256, 0, st>>>(d_frame, d_soff, d_slen, d_stored, n, B, d_ex, d_runs, d_slows, d_lb, d_nr, d_nsl, d_ns, d_olen,
                                                 d_reach, d_status, d_fb);
         k_jdp_emit<<<dim3(64, n), 256, 0, st>>>(d_frame, d_soff, d_slen, d_nx, d_adv, d_runs, d_slows, d_lb, d_nr, d_nsl, d_seq, d_sb, d_reach);
@@ -493,7 +502,7 @@ int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, uint64_t frame_span, 
     for (uint32_t i = 0; i < n; ++i)
         if (status_h[i]) return DLZ4_OK;                                  // the caller maps the first status to the error
     // a unit's bytes are final once its k_jd_emit ran: ship them while the later units resolve
-    const bool ship = host_out && *total <= host_cap && nunits <= 128;
+    const bool ship = host_out && *total <= host_cap && nunits <= (uint32_t)kJdGroupEvent;
     if (copied_out) *copied_out = ship;
     const int wide = ctx->sm_count * 8;
     for (uint32_t u = 0; u < nunits; ++u) {
@@ -1519,7 +1528,28 @@ int dlz4_frame_decompress_ex(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame
     uint32_t *d_slen = (uint32_t *)(d_doff + n), *d_cap = d_slen + n, *d_olen = d_cap + n, *d_bhash = d_olen + n;
     uint8_t *d_status = (uint8_t *)(d_bhash + n), *d_stored = d_status + n;
 
-    CK(cudaMemcpyAsync(d_frame, frame, frame_len, cudaMemcpyHostToDevice, st));
+    // A long frame for the jump decoder's chunked scan is copied in up to 16 groups of whole blocks on the copy stream; the scan
+    // of a group starts when it has landed (decompress_jump), the rest of the decoder waits for all of them through `st`.
+    std::vector<uint32_t> groups;
+    const bool jump_scan = n && frame_len >= ctx->jump_min_bytes && (!info.block_independence || (B > 65536 && n < 1024)) && B > 65536 &&
+                           !getenv("DLZ4_JD_SERIAL_SCAN");
+    if (jump_scan && frame_len >= (64ull << 20) && !((flags & 2u) && info.has_block_checksum) && !getenv("DLZ4_JD_NO_OVERLAP")) {
+        const uint64_t target = std::max<uint64_t>(16ull << 20, (frame_len + 14) / 15);     // <= 16 groups
+        uint64_t begin = 0;
+        groups.push_back(0);
+        for (uint32_t i = 0; i < n; ++i) {
+            const bool last = i + 1 == n;
+            const uint64_t end = last ? frame_len : blocks[i + 1].off;           // (runs into the next block's size word: harmless)
+            if (last || end - begin >= target) {
+                CK(cudaMemcpyAsync(d_frame + begin, frame + begin, end - begin, cudaMemcpyHostToDevice, ctx->copy_in));
+                CK(cudaEventRecord(ctx->evp[kJdGroupEvent + groups.size() - 1], ctx->copy_in));
+                groups.push_back(i + 1);
+                begin = end;
+            }
+        }
+    } else {
+        CK(cudaMemcpyAsync(d_frame, frame, frame_len, cudaMemcpyHostToDevice, st));
+    }
     if (dwin) CK(cudaMemcpyAsync(d_dict, dictionary + (dict_len - dwin), dwin, cudaMemcpyHostToDevice, st));
 
     std::vector<uint64_t> soff(n), doff(n);
@@ -1544,7 +1574,8 @@ int dlz4_frame_decompress_ex(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame
         if (jump) {
             // linked blocks (block k reads block k-1's output) or few large blocks: token scan + pointer doubling
             CKS(decompress_jump(ctx, d_frame, fpad, d_soff, d_slen, d_stored, slen, n, B, d_out, cap_total, dwin ? d_dict : nullptr, (uint32_t)dwin,
-                                !info.block_independence, d_olen, d_status, status, &total, st, output, output_cap, &shipped));
+                                !info.block_independence, d_olen, d_status, status, &total, st, output, output_cap, &shipped,
+                                groups.empty() ? nullptr : &groups));
             for (uint32_t i = 0; i < n && !first_status; ++i) first_status = status[i];
         } else if (!info.block_independence) {
             // short linked frame: serial chain (one warp)
