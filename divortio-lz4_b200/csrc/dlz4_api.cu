@@ -1528,13 +1528,13 @@ int dlz4_frame_decompress_ex(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame
     uint32_t *d_slen = (uint32_t *)(d_doff + n), *d_cap = d_slen + n, *d_olen = d_cap + n, *d_bhash = d_olen + n;
     uint8_t *d_status = (uint8_t *)(d_bhash + n), *d_stored = d_status + n;
 
-    // A long frame for the jump decoder's chunked scan is copied in up to 16 groups of whole blocks on the copy stream; the scan
+    // A frame of 8 MiB and more for the jump decoder's chunked scan is copied in up to 16 groups of whole blocks on the copy stream; the scan
     // of a group starts when it has landed (decompress_jump), the rest of the decoder waits for all of them through `st`.
     std::vector<uint32_t> groups;
     const bool jump_scan = n && frame_len >= ctx->jump_min_bytes && (!info.block_independence || (B > 65536 && n < 1024)) && B > 65536 &&
                            !getenv("DLZ4_JD_SERIAL_SCAN");
-    if (jump_scan && frame_len >= (64ull << 20) && !((flags & 2u) && info.has_block_checksum) && !getenv("DLZ4_JD_NO_OVERLAP")) {
-        const uint64_t target = std::max<uint64_t>(16ull << 20, (frame_len + 14) / 15);     // <= 16 groups
+    if (jump_scan && frame_len >= (8ull << 20) && !((flags & 2u) && info.has_block_checksum) && !getenv("DLZ4_JD_NO_OVERLAP")) {
+        const uint64_t target = std::max<uint64_t>(4ull << 20, (frame_len + 14) / 15);      // <= 16 groups
         uint64_t begin = 0;
         groups.push_back(0);
         for (uint32_t i = 0; i < n; ++i) {
