@@ -74,3 +74,19 @@ def test_header_matches_oracle_header():
                 h = sharded.frame_header(12345, 65536, True, cc, size, bc, oracle.xxh32)
                 want = oracle.compress_buffer(bytes(12345), None, 65536, True, cc, size, None, bc)
                 assert want.startswith(h)
+
+
+def test_bind_host_near_never_widens_the_affinity_and_survives_missing_nvml():
+    """One rank per GPU pins its host threads to the GPU's NUMA node when NVML can say which CPUs that is; without a GPU or
+    NVML it must leave the process alone and say so."""
+    import os
+    import importlib
+    sharded = importlib.import_module("divortio_lz4_b200.sharded")
+    before = os.sched_getaffinity(0)
+    got = sharded.bind_host_near(0)
+    after = os.sched_getaffinity(0)
+    if got is None:
+        assert after == before
+    else:
+        assert after == got and got <= before
+        os.sched_setaffinity(0, before)
