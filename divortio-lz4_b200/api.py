@@ -88,6 +88,8 @@ def lib():
         "dlz4_segment_stats": (None, [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "dlz4_pinned_alloc": (vp, [u64]),
         "dlz4_pinned_free": (None, [vp]),
+        "dlz4_host_register": (C.c_int, [vp, u64]),
+        "dlz4_host_unregister": (C.c_int, [vp]),
         "dlz4_compress_bound": (u64, [u64]),
         "dlz4_frame_bound": (u64, [u64]),
         "dlz4_shard_range": (None, [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]),
@@ -112,6 +114,11 @@ def lib():
         "dlz4_xxh32_update": (C.c_int, [vp, C.POINTER(Xxh32State), vp, u64]),
         "dlz4_xxh32_digest": (u32, [C.POINTER(Xxh32State)]),
         "dlz4_chain_compress": (C.c_int, [vp, vp, u64, i32, i32, i32, vp, vp, u64, vp]),
+        "dlz4_frame_body_compress": (C.c_int, [vp, vp, u64, u32, C.c_int, C.POINTER(u64)]),
+        "dlz4_frame_body_fetch": (C.c_int, [vp, vp, u64]),
+        "dlz4_frame_header": (C.c_size_t, [C.POINTER(FrameOpts), u64, C.c_int, u32, vp]),
+        "dlz4_frame_decompress_range": (C.c_int, [vp, vp, u64, u32, u32, vp, u64, u32, vp, u64, C.POINTER(u64), vp]),
+        "dlz4_xxh32_update_resident": (C.c_int, [vp, C.POINTER(Xxh32State), C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -123,11 +130,12 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "dlz4_init", "dlz4_shutdown", "dlz4_strerror", "dlz4_last_error", "dlz4_launch_count", "dlz4_last_kernel_ms", "dlz4_segment_stats",
-    "dlz4_pinned_alloc", "dlz4_pinned_free", "dlz4_compress_bound", "dlz4_frame_bound", "dlz4_shard_range",
+    "dlz4_pinned_alloc", "dlz4_pinned_free", "dlz4_host_register", "dlz4_host_unregister", "dlz4_compress_bound", "dlz4_frame_bound", "dlz4_shard_range",
     "dlz4_compress_blocks_dev", "dlz4_compress_blocks", "dlz4_decompress_blocks_dev", "dlz4_decompress_blocks",
     "dlz4_compress_block", "dlz4_decompress_block", "dlz4_xxh32_batch_dev", "dlz4_xxh32_stream_dev", "dlz4_xxh32",
     "dlz4_xxh32_batch", "dlz4_frame_compress", "dlz4_frame_info", "dlz4_frame_decompress", "dlz4_frame_pack_dev", "dlz4_frames_decompress", "dlz4_frames_info", "dlz4_frame_decompress_ex", "dlz4_xxh32_reset", "dlz4_xxh32_update", "dlz4_xxh32_digest",
-    "dlz4_chain_compress",
+    "dlz4_chain_compress", "dlz4_frame_body_compress", "dlz4_frame_body_fetch", "dlz4_frame_header", "dlz4_frame_decompress_range",
+    "dlz4_xxh32_update_resident",
 ]
 
 
@@ -225,6 +233,15 @@ def compress_bound(n):
 
 def frame_bound(n):
     return int(lib().dlz4_frame_bound(int(n)))
+
+
+def host_register(array):
+    """Page-locks a caller-owned numpy buffer (dlz4_host_register); True when the driver accepted it."""
+    return lib().dlz4_host_register(_ptr(array), int(array.nbytes)) == 0
+
+
+def host_unregister(array):
+    return lib().dlz4_host_unregister(_ptr(array)) == 0
 
 
 def shard_range(nblocks, world, rank):

@@ -44,6 +44,7 @@ struct dlz4_ctx {
     uint32_t *d_hash = nullptr;         // small result slots
     uint64_t *d_total = nullptr;
     int32_t *d_table = nullptr;         // int32[16384] scratch table
+    int wide = 1;                       // shared-memory-table chains use the 64-position window (dlz4_wide.cuh); 0: A/B runs
     int hybrid = 1;                     // 64 KiB fresh blocks: hybrid kernel (L2-resident tables) instead of the 7-warp one
     int hy_grid = 0;                    // CTAs that fill the device (sm_count x kHyCtasPerSm)
     int hy_active = 0;                  // cap on the warps used per hybrid CTA (DLZ4_HY_ACTIVE, 0 = all 7; A/B runs)
@@ -56,6 +57,11 @@ struct dlz4_ctx {
     uint32_t seg_jobs = 0, seg_reruns = 0, seg_rounds = 0;   // last segment-parallel call: segments, re-run segments, rounds
     uint64_t launches = 0;
     float last_ms = 0.f;
+    // what the last frame-body / frame-range call left resident on the device (sharded frames): the rank's input
+    // slice, its packed frame body, the decoded bytes of its block range -- read by dlz4_frame_body_fetch and by the
+    // content-checksum relay dlz4_xxh32_update_resident
+    const uint8_t *res_in = nullptr, *res_out = nullptr;
+    uint64_t res_in_len = 0, res_out_len = 0, res_body_len = 0;
 };
 
 namespace {
@@ -159,8 +165,12 @@ int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, 
             ctx->d_gtabs + region * (size_t)ctx->hy_grid * kHyGlWarps * kHashEntries, active);
     } else if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr) {
         const int grid = (int)std::min<uint64_t>((n + kWarpsFresh16 - 1) / kWarpsFresh16, (uint64_t)ctx->sm_count);
-        k_compress_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * (kHashEntries * 2 + kRingBytes), st>>>(
-            src, src_off, src_len, n, dst, dst_off, comp_len, counter);
+        if (ctx->wide)
+            k_compress_fresh16<kWarpsFresh16, true><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * (kHashEntries * 2 + kRingBytes), st>>>(
+                src, src_off, src_len, n, dst, dst_off, comp_len, counter);
+        else
+            k_compress_fresh16<kWarpsFresh16, false><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * (kHashEntries * 2 + kRingBytes), st>>>(
+                src, src_off, src_len, n, dst, dst_off, comp_len, counter);
     } else {
         if (max_len > 65536 && prefix_len == 0 && init_table == nullptr && n <= 65536) {
             // blocks > 64 KiB: if they tile one contiguous range uniformly (the usual batch), cut them into segments
@@ -571,10 +581,13 @@ int dlz4_init(int device, dlz4_ctx **out) {
     CK(cudaMalloc(&ctx->d_hash, 64));
     CK(cudaMalloc(&ctx->d_total, 64));
     CK(cudaMalloc(&ctx->d_table, kHashEntries * sizeof(int32_t)));
-    CK(cudaFuncSetAttribute(k_compress_fresh16<kWarpsFresh16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CK(cudaFuncSetAttribute(k_compress_fresh16<kWarpsFresh16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            kWarpsFresh16 * (kHashEntries * 2 + kRingBytes)));
+    CK(cudaFuncSetAttribute(k_compress_fresh16<kWarpsFresh16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kWarpsFresh16 * (kHashEntries * 2 + kRingBytes)));
     if (const char *e = getenv("DLZ4_SEG_MIN_KIB")) ctx->seg_min_bytes = (uint64_t)atoll(e) << 10;     // huge value: serial chain only
     if (const char *e = getenv("DLZ4_JUMP_MIN_KIB")) ctx->jump_min_bytes = (uint64_t)atoll(e) << 10;
+    if (const char *e = getenv("DLZ4_WIDE")) ctx->wide = atoi(e) != 0;
     if (const char *e = getenv("DLZ4_HYBRID")) ctx->hybrid = atoi(e) != 0;      // 0: the 7-warp shared-memory-only kernel (A/B runs)
     ctx->hy_grid = ctx->sm_count * kHyCtasPerSm;
     if (const char *e = getenv("DLZ4_HY_ACTIVE")) ctx->hy_active = std::max(0, std::min(kHyWarps, atoi(e)));
@@ -672,6 +685,17 @@ void *dlz4_pinned_alloc(uint64_t bytes) {
     return p;
 }
 void dlz4_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+// Page-locks memory the caller already owns (a Node Buffer, a shared mapping the ranks of a box all map): portable, so
+// every context of the process sees it as pinned.  Returns DLZ4_OK, or DLZ4_E_CUDA when the driver refuses (the memory
+// stays usable, just pageable).
+int dlz4_host_register(void *p, uint64_t bytes) {
+    if (!p || !bytes) return DLZ4_E_INVALID_ARG;
+    return cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable) == cudaSuccess ? DLZ4_OK : (cudaGetLastError(), DLZ4_E_CUDA);
+}
+int dlz4_host_unregister(void *p) {
+    if (!p) return DLZ4_E_INVALID_ARG;
+    return cudaHostUnregister(p) == cudaSuccess ? DLZ4_OK : (cudaGetLastError(), DLZ4_E_CUDA);
+}
 
 // ---- batched raw blocks ---------------------------------------------------------------------------------
 int dlz4_compress_blocks_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len,
@@ -703,6 +727,19 @@ int dlz4_compress_blocks_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *
 // the drain is bounded below by the latency of one block chain (~3 ms for a 64 KiB text block) whatever the chunk size,
 // and smaller chunks only add launches (profiles/r01_e2e_chunk_sweep.txt).
 // Blocks must be ascending and non-overlapping in `src`; output is packed (block i directly after block i-1).
+// Error exits of the chunked pipelines: copies into the caller's buffers and kernels on the lanes may still be in flight
+// (a later chunk's D2H, queued launches).  Nothing of this call may outlive it -- the caller frees or reuses its buffers and
+// the next call reuses the event pool and the scratch -- so every exit that is not the normal one drains all streams first.
+struct PipeGuard {
+    dlz4_ctx *ctx;
+    bool armed = true;
+    ~PipeGuard() {
+        if (!armed) return;
+        cudaStreamSynchronize(ctx->copy_in);
+        cudaStreamSynchronize(ctx->copy_out);
+        for (int l = 0; l < 4; ++l) if (ctx->lanes[l]) cudaStreamSynchronize(ctx->lanes[l]);
+    }
+};
 static const uint32_t kMaxChunks = 56;
 
 // frame_mode: the packed stream is the body of an LZ4 frame -- [u32 size | stored bit][payload][u32 xxh32]* with the
@@ -728,6 +765,7 @@ static int compress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t sr
     cudaStream_t *sks = ctx->lanes, si = ctx->copy_in, so = ctx->copy_out;
     const uint32_t nl = (uint32_t)ctx->n_lanes;
     cudaStream_t sk = sks[0];
+    PipeGuard guard{ctx};
 
     // chunk boundaries by source bytes
     std::vector<uint32_t> cb{0};
@@ -794,6 +832,7 @@ static int compress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t sr
     CK(cudaEventRecord(ctx->ev1, sks[0]));
     CK(cudaStreamSynchronize(sks[0]));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    guard.armed = false;
     if (total_out) *total_out = host_pos;
     if (comp_len) {
         memcpy(comp_len, h_clen, (size_t)n * 4);
@@ -897,6 +936,7 @@ static int decompress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t 
     cudaStream_t *sks = ctx->lanes, si = ctx->copy_in, so = ctx->copy_out;
     const uint32_t nl = (uint32_t)ctx->n_lanes;
     cudaStream_t sk = sks[0];
+    PipeGuard guard{ctx};
     const uint64_t target = std::max<uint64_t>(ctx->chunk_bytes, total_out / kMaxChunks + 1);
     std::vector<uint32_t> cb{0};
     uint64_t acc = 0;
@@ -940,6 +980,7 @@ static int decompress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t 
     CK(cudaStreamSynchronize(sk));
     CK(cudaStreamSynchronize(so));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    guard.armed = false;
     for (uint32_t i = 0; i < n; ++i)
         if (status[i]) return status[i];
     return DLZ4_OK;
@@ -1165,12 +1206,34 @@ int dlz4_frame_pack_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_o
     return DLZ4_OK;
 }
 
+// ---- frame header (bufferCompress.js:147-178): the one writer every path uses (frame calls, sharded frames, stream encoder)
+size_t dlz4_frame_header(const dlz4_frame_opts *opts, uint64_t content_len, int have_dict, uint32_t dict_id, uint8_t out[19]) {
+    size_t hp = 0;
+    wr32(out, 0x184D2204u); hp = 4;                                     // :147 magic
+    uint8_t flg = 1 << 6;                                               // :150 version 01
+    if (opts->block_independence) flg |= 0x20;
+    if (opts->content_checksum) flg |= 0x04;
+    if (have_dict) flg |= 0x01;
+    if (opts->add_content_size) flg |= 0x08;
+    if (opts->block_checksum) flg |= 0x10;                              // addition (LZ4 frame spec)
+    out[hp++] = flg;
+    out[hp++] = (uint8_t)((block_id_for(opts->max_block_size) & 7) << 4);   // :160 BD
+    if (opts->add_content_size) {                                       // :163-168 u64 from len|0 (frames are < 2 GiB)
+        wr32(out + hp, (uint32_t)content_len); wr32(out + hp + 4, (uint32_t)(content_len >> 32)); hp += 8;
+    }
+    if (have_dict) { wr32(out + hp, dict_id); hp += 4; }                // :171-175
+    out[hp] = (uint8_t)((header_xxh32(out + 4, hp - 4) >> 8) & 0xFF); hp++;   // :177-178 HC
+    return hp;
+}
+
 // ---- frame compress (compressBuffer) ---------------------------------------------------------------------------------
-int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len, const uint8_t *dictionary, uint64_t dict_len,
-                        const dlz4_frame_opts *opts, uint8_t *output, uint64_t output_cap, uint64_t *output_len) {
-    if (!ctx || !opts || !output_len || (input_len && !input)) return DLZ4_E_INVALID_ARG;
-    if (input_len >= 0x7FFF0000ull) return DLZ4_E_TOO_LARGE;            // bufferCompress.js:127 len|0
-    CK(cudaSetDevice(ctx->device));
+// The block loop of compressBuffer (bufferCompress.js:209-239) for one input of < 2 GiB, everything on the device: stages
+// dictionary window ++ input, launches the content checksum on the side stream, compresses every block and packs
+// [u32 size | stored bit][payload][u32 xxh32]* into ctx->seg.  On return the stream is idle, *seg_len = bytes of that body,
+// hdr[0, *hp) the frame header; the caller adds EndMark / checksum.  The input stays resident (ctx->res_in) for
+// dlz4_xxh32_update_resident.
+static int frame_body(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len, const uint8_t *dictionary, uint64_t dict_len,
+                      const dlz4_frame_opts *opts, uint8_t *hdr, size_t *hp_out, uint64_t *seg_len_out) {
     cudaStream_t st = ctx->stream;
     const bool have_dict = dictionary && dict_len > 0;                  // :109
     const uint64_t dwin = have_dict ? std::min<uint64_t>(dict_len, 65536) : 0;   // :115
@@ -1178,36 +1241,6 @@ int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len,
     const uint32_t B = kBlockMax[bd];
     const uint32_t n = (uint32_t)((input_len + B - 1) / B);
     const uint64_t stride = (dlz4_compress_bound(B) + 15) & ~15ull;
-
-    // device staging: work = dictionary window ++ input (the reference's workingBuffer, :121-124)
-    if (opts->block_independence && B <= 65536 && !have_dict && !opts->content_checksum && input_len >= ctx->frame_pipe_min_bytes &&
-        output_cap >= dlz4_frame_bound(input_len)) {     // (with a content checksum the serial xxh32 is the whole cost: old path)
-        // large frame of small independent blocks: the chunked host pipeline (H2D / kernels / D2H overlapped) writes the
-        // frame body straight into `output`; header, EndMark and the content checksum are added around it
-        uint8_t hdr[32];
-        size_t hp = 0;
-        wr32(hdr, 0x184D2204u); hp = 4;
-        uint8_t flg = (1 << 6) | 0x20;
-        if (opts->content_checksum) flg |= 0x04;
-        if (opts->add_content_size) flg |= 0x08;
-        if (opts->block_checksum) flg |= 0x10;
-        hdr[hp++] = flg;
-        hdr[hp++] = (uint8_t)((bd & 7) << 4);
-        if (opts->add_content_size) { wr32(hdr + hp, (uint32_t)input_len); wr32(hdr + hp + 4, 0); hp += 8; }
-        hdr[hp] = (uint8_t)((header_xxh32(hdr + 4, hp - 4) >> 8) & 0xFF); hp++;
-        memcpy(output, hdr, hp);
-        std::vector<uint64_t> off(n);
-        std::vector<uint32_t> len(n);
-        for (uint32_t i = 0; i < n; ++i) { off[i] = (uint64_t)i * B; len[i] = (uint32_t)std::min<uint64_t>(B, input_len - off[i]); }
-        uint64_t body = 0;
-        ctx->seg_jobs = ctx->seg_reruns = ctx->seg_rounds = 0;
-        CKS(compress_blocks_packed(ctx, input, input_len, off.data(), len.data(), n, B, output + hp, output_cap - hp - 8, nullptr, 1,
-                                   opts->block_checksum, &body));
-        uint8_t foot[8] = {0, 0, 0, 0, 0, 0, 0, 0};                         // EndMark (:244)
-        memcpy(output + hp + body, foot, opts->content_checksum ? 8 : 4);
-        *output_len = hp + body + 4 + (opts->content_checksum ? 4 : 0);
-        return DLZ4_OK;
-    }
     const uint64_t dpad = (dwin + 15) & ~15ull;                          // keep the input 16-byte aligned
     CKS(reserve(ctx, ctx->work, dict_len + dpad + input_len + 64));
     uint8_t *d_work = (uint8_t *)ctx->work.p + (dpad - dwin);            // dictionary window directly before the input
@@ -1239,18 +1272,6 @@ int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len,
     if (dwin) CK(cudaMemcpyAsync(d_work, dictionary + (dict_len - dwin), dwin, cudaMemcpyHostToDevice, st));
 
     // header (host, bufferCompress.js:147-178)
-    uint8_t hdr[32];
-    size_t hp = 0;
-    wr32(hdr, 0x184D2204u); hp = 4;
-    uint8_t flg = 1 << 6;
-    if (opts->block_independence) flg |= 0x20;
-    if (opts->content_checksum) flg |= 0x04;
-    if (have_dict) flg |= 0x01;
-    if (opts->add_content_size) flg |= 0x08;
-    if (opts->block_checksum) flg |= 0x10;
-    hdr[hp++] = flg;
-    hdr[hp++] = (uint8_t)((bd & 7) << 4);
-    if (opts->add_content_size) { wr32(hdr + hp, (uint32_t)input_len); wr32(hdr + hp + 4, 0); hp += 8; }
     uint32_t dict_id = 0;
     if (have_dict) {                                                    // :112 dictId = xxHash32(dict) on the GPU
         if (dict_len > dwin) {
@@ -1263,9 +1284,8 @@ int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len,
         }
         CK(cudaMemcpyAsync(&dict_id, ctx->d_hash + 1, 4, cudaMemcpyDeviceToHost, ctx->side));
         CK(cudaStreamSynchronize(ctx->side));
-        wr32(hdr + hp, dict_id); hp += 4;
     }
-    hdr[hp] = (uint8_t)((header_xxh32(hdr + 4, hp - 4) >> 8) & 0xFF); hp++;
+    const size_t hp = dlz4_frame_header(opts, input_len, have_dict ? 1 : 0, dict_id, hdr);
 
     // content checksum: serial xxh32 over the whole input on the side stream, overlapped with the block kernels (:248-252)
     if (opts->content_checksum) {
@@ -1323,6 +1343,50 @@ int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len,
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
 
+    ctx->res_in = d_in; ctx->res_in_len = input_len;
+    *hp_out = hp;
+    *seg_len_out = seg_len;
+    return DLZ4_OK;
+}
+
+int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len, const uint8_t *dictionary, uint64_t dict_len,
+                        const dlz4_frame_opts *opts, uint8_t *output, uint64_t output_cap, uint64_t *output_len) {
+    if (!ctx || !opts || !output_len || (input_len && !input)) return DLZ4_E_INVALID_ARG;
+    if (input_len >= 0x7FFF0000ull) return DLZ4_E_TOO_LARGE;            // bufferCompress.js:127 len|0
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const bool have_dict = dictionary && dict_len > 0;                  // :109
+    const uint64_t dwin = have_dict ? std::min<uint64_t>(dict_len, 65536) : 0;   // :115
+    const int bd = block_id_for(opts->max_block_size);                  // :128
+    const uint32_t B = kBlockMax[bd];
+    const uint32_t n = (uint32_t)((input_len + B - 1) / B);
+    const uint64_t stride = (dlz4_compress_bound(B) + 15) & ~15ull;
+
+    // device staging: work = dictionary window ++ input (the reference's workingBuffer, :121-124)
+    if (opts->block_independence && B <= 65536 && !have_dict && !opts->content_checksum && input_len >= ctx->frame_pipe_min_bytes &&
+        output_cap >= dlz4_frame_bound(input_len)) {     // (with a content checksum the serial xxh32 is the whole cost: old path)
+        // large frame of small independent blocks: the chunked host pipeline (H2D / kernels / D2H overlapped) writes the
+        // frame body straight into `output`; header, EndMark and the content checksum are added around it
+        uint8_t hdr[32];
+        const size_t hp = dlz4_frame_header(opts, input_len, 0, 0, hdr);
+        memcpy(output, hdr, hp);
+        std::vector<uint64_t> off(n);
+        std::vector<uint32_t> len(n);
+        for (uint32_t i = 0; i < n; ++i) { off[i] = (uint64_t)i * B; len[i] = (uint32_t)std::min<uint64_t>(B, input_len - off[i]); }
+        uint64_t body = 0;
+        ctx->seg_jobs = ctx->seg_reruns = ctx->seg_rounds = 0;
+        CKS(compress_blocks_packed(ctx, input, input_len, off.data(), len.data(), n, B, output + hp, output_cap - hp - 8, nullptr, 1,
+                                   opts->block_checksum, &body));
+        uint8_t foot[8] = {0, 0, 0, 0, 0, 0, 0, 0};                         // EndMark (:244)
+        memcpy(output + hp + body, foot, opts->content_checksum ? 8 : 4);
+        *output_len = hp + body + 4 + (opts->content_checksum ? 4 : 0);
+        return DLZ4_OK;
+    }
+    uint8_t hdr[32];
+    size_t hp = 0;
+    uint64_t seg_len = 0;
+    CKS(frame_body(ctx, input, input_len, dictionary, dict_len, opts, hdr, &hp, &seg_len));
+
     const uint64_t total = hp + seg_len + 4 + (opts->content_checksum ? 4 : 0);
     *output_len = total;
     // an undersized outputBuffer truncates silently in the reference (typed-array stores are dropped); same here
@@ -1347,6 +1411,53 @@ int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len,
     }
     put(foot, opts->content_checksum ? 8 : 4);
     CK(cudaStreamSynchronize(st));
+    return DLZ4_OK;
+}
+
+// ---- sharded frames: one rank's contiguous range of independent blocks ------------------------------------
+int dlz4_frame_body_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len, uint32_t max_block_size, int block_checksum,
+                             uint64_t *body_len) {
+    if (!ctx || !body_len || (input_len && !input)) return DLZ4_E_INVALID_ARG;
+    if (input_len >= 0x7FFF0000ull) return DLZ4_E_TOO_LARGE;
+    CK(cudaSetDevice(ctx->device));
+    dlz4_frame_opts o{max_block_size, 1, 0, 0, block_checksum};
+    uint8_t hdr[32];
+    size_t hp = 0;
+    ctx->res_body_len = 0;
+    CKS(frame_body(ctx, input, input_len, nullptr, 0, &o, hdr, &hp, body_len));
+    ctx->res_body_len = *body_len;
+    return DLZ4_OK;
+}
+
+int dlz4_frame_body_fetch(dlz4_ctx *ctx, uint8_t *dst, uint64_t dst_cap) {
+    if (!ctx || (ctx->res_body_len && !dst)) return DLZ4_E_INVALID_ARG;
+    if (ctx->res_body_len > dst_cap) return DLZ4_E_OUTPUT_TOO_SMALL;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->res_body_len) CK(cudaMemcpyAsync(dst, ctx->seg.p, ctx->res_body_len, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DLZ4_OK;
+}
+
+int dlz4_xxh32_update_resident(dlz4_ctx *ctx, dlz4_xxh32_state *s, int which) {
+    if (!ctx || !s || (which != DLZ4_RESIDENT_INPUT && which != DLZ4_RESIDENT_OUTPUT)) return DLZ4_E_INVALID_ARG;
+    const uint8_t *d = which == DLZ4_RESIDENT_INPUT ? ctx->res_in : ctx->res_out;
+    const uint64_t len = which == DLZ4_RESIDENT_INPUT ? ctx->res_in_len : ctx->res_out_len;
+    if (len == 0) return DLZ4_OK;
+    if (!d || s->memsize != 0) return DLZ4_E_INVALID_ARG;               // pieces before the last are whole stripes (whole blocks)
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t body = len & ~15ull;
+    if (body) {
+        CK(cudaMemcpyAsync(ctx->d_hash + 4, s->v, 16, cudaMemcpyHostToDevice, st));
+        k_xxh32_stream<<<1, 32, 0, st>>>(d, body, s->seed, nullptr, ctx->d_hash + 4, ctx->d_hash + 8);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(s->v, ctx->d_hash + 8, 16, cudaMemcpyDeviceToHost, st));
+    }
+    if (len > body) CK(cudaMemcpyAsync(s->mem, d + body, len - body, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    s->memsize = (uint32_t)(len - body);
+    s->total += len;
     return DLZ4_OK;
 }
 
@@ -1398,7 +1509,10 @@ static int walk_blocks(const uint8_t *f, uint64_t len, const dlz4_frame_info_t *
         if (pos + actual > len) return DLZ4_E_MALFORMED;
         if (blocks) blocks->push_back({pos, actual, (uint8_t)((bs >> 31) & 1)});
         pos += actual;
-        if (info->has_block_checksum) pos += 4;                          // :191
+        if (info->has_block_checksum) {                                  // :191
+            if (pos + 4 > len) return DLZ4_E_MALFORMED;                   // truncated frame: the checksum bytes must exist
+            pos += 4;
+        }
     }
     *end_pos = pos;
     return DLZ4_OK;
@@ -1462,20 +1576,54 @@ int dlz4_frame_decompress(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_le
     return dlz4_frame_decompress_ex(ctx, frame, frame_len, dictionary, dict_len, flags, output, output_cap, output_len, nullptr);
 }
 
-int dlz4_frame_decompress_ex(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_len, const uint8_t *dictionary, uint64_t dict_len,
-                             uint32_t flags, uint8_t *output, uint64_t output_cap, uint64_t *output_len, uint32_t *block_out_len) {
-    if (!ctx || !frame || !output_len) return DLZ4_E_INVALID_ARG;
+static int frame_decompress_impl(dlz4_ctx *ctx, const uint8_t *frame_in, uint64_t frame_len_in, const uint8_t *dictionary, uint64_t dict_len,
+                                 uint32_t flags, uint8_t *output, uint64_t output_cap, uint64_t *output_len, uint32_t *block_out_len,
+                                 uint32_t first_block, uint32_t block_count /* 0xFFFFFFFF: to the end */) {
+    if (!ctx || !frame_in || !output_len) return DLZ4_E_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     dlz4_frame_info_t info;
     uint64_t pos = 0, end = 0;
-    CKS(parse_header(frame, frame_len, &info, &pos));
+    CKS(parse_header(frame_in, frame_len_in, &info, &pos));
     if ((flags & 4u)) {
         const uint64_t hc_pos = pos - 1;
-        if ((uint8_t)((header_xxh32(frame + 4, (size_t)(hc_pos - 4)) >> 8) & 0xFF) != frame[hc_pos]) return DLZ4_E_HEADER_CHECKSUM;
+        if ((uint8_t)((header_xxh32(frame_in + 4, (size_t)(hc_pos - 4)) >> 8) & 0xFF) != frame_in[hc_pos]) return DLZ4_E_HEADER_CHECKSUM;
     }
     std::vector<BlockRef> blocks;
-    CKS(walk_blocks(frame, frame_len, &info, pos, &blocks, &end));
+    CKS(walk_blocks(frame_in, frame_len_in, &info, pos, &blocks, &end));
+    // A block range (sharded decode, SURVEY 8e: rank r decodes blocks dlz4_shard_range(...) into its slice of the output):
+    // the range is treated as a frame of its own whose bytes start at its first block's size word.  Independent blocks only
+    // (a linked block needs the output before it), inner blocks must be full (checked by the caller through block_out_len),
+    // and the whole-stream content checksum is the caller's business (dlz4_xxh32_update_resident relay).
+    const uint32_t n_all = (uint32_t)blocks.size();
+    const bool ranged = !(first_block == 0 && block_count >= n_all);
+    const uint8_t *frame = frame_in;
+    uint64_t frame_len = frame_len_in;
+    ctx->res_out = nullptr; ctx->res_out_len = 0;
+    if (ranged) {
+        if (first_block > n_all) return DLZ4_E_INVALID_ARG;
+        block_count = std::min<uint32_t>(block_count, n_all - first_block);
+        if (!info.block_independence && first_block != 0) return DLZ4_E_INVALID_ARG;
+        const uint64_t B0 = info.block_max_size;
+        if (info.content_size) {
+            const uint64_t lo_c = std::min<uint64_t>(info.content_size, (uint64_t)first_block * B0);
+            const uint64_t hi_c = first_block + block_count >= n_all ? info.content_size
+                                                                     : std::min<uint64_t>(info.content_size, (uint64_t)(first_block + block_count) * B0);
+            info.content_size = hi_c - lo_c;
+            info.has_content_size = info.content_size != 0;
+        }
+        flags &= ~1u;                                                    // content checksum: not over a part
+        info.has_content_checksum = 0;
+        if (block_count == 0) { *output_len = 0; return DLZ4_OK; }
+        const uint64_t lo = blocks[first_block].off - 4;
+        const BlockRef &lb = blocks[first_block + block_count - 1];
+        const uint64_t hi = lb.off + lb.len + (info.has_block_checksum ? 4 : 0);
+        blocks.assign(blocks.begin() + first_block, blocks.begin() + first_block + block_count);
+        for (BlockRef &b : blocks) b.off -= lo;
+        frame = frame_in + lo;
+        frame_len = hi - lo;
+        end = frame_len;
+    }
     const uint32_t n = (uint32_t)blocks.size();
     if (!dictionary) dict_len = 0;
     const uint64_t dwin = std::min<uint64_t>(dict_len, 65536);
@@ -1508,6 +1656,8 @@ int dlz4_frame_decompress_ex(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame
                 if (h != rd32(frame + end)) return DLZ4_E_CONTENT_CHECKSUM;
             }
             *output_len = info.content_size;
+            if (block_out_len) memcpy(block_out_len, olen.data(), (size_t)n * 4);
+            ctx->res_out = (const uint8_t *)ctx->out.p; ctx->res_out_len = info.content_size;
             return DLZ4_OK;
         }
         // an error or a short inner block: the general path below decides (same status order as ever)
@@ -1589,39 +1739,55 @@ int dlz4_frame_decompress_ex(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame
             for (uint32_t i = 0; i < n && !first_status; ++i) first_status = status[i];
         } else {
             // independent blocks: every block is decoded by its own warp at i * blockMaxSize (every writer this library
-            // meets -- the reference, liblz4, the lz4 CLI -- emits full blocks except the last); a short block is detected
-            // afterwards and the output is closed up on the device.
-            for (uint32_t i = 0; i < n; ++i) {
-                doff[i] = (uint64_t)i * B;
-                const uint64_t room = doff[i] < cap_total ? cap_total - doff[i] : 0;
-                cap[i] = (uint32_t)std::min<uint64_t>(room, B);
-            }
-            CK(cudaMemcpyAsync(d_doff, doff.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(d_cap, cap.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-            // history of an independent block is the dictionary only (LZ4 frame spec; for frames the reference writes,
-            // blocks > 0 never reach before their own start, so this equals bufferDecompress.js:153 on them)
-            CKS(launch_decompress(ctx, d_frame, d_soff, d_slen, n, d_out, d_doff, d_cap, dwin ? d_dict : nullptr, (uint32_t)dwin, 0,
-                                  d_stored, d_olen, d_status, st));
-            CK(cudaMemcpyAsync(olen.data(), d_olen, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(status.data(), d_status, n, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            bool contiguous = true;
-            for (uint32_t i = 0; i < n; ++i) {
-                if (status[i] && !first_status) first_status = status[i];
-                if (i + 1 < n && olen[i] != B) contiguous = false;
-            }
-            if (!first_status && !contiguous) {
-                // close the gaps front to back (forward moves never overlap later data)
-                uint64_t w = 0;
+            // meets -- the reference, liblz4, the lz4 CLI -- emits full blocks except the last); a short inner block is
+            // detected afterwards and the output is closed up on the device.  That layout needs room for n - 1 full blocks:
+            // a frame that cannot have them (flushed short inner blocks, LZ4F_flush-style writers, a stream's update() that
+            // carries several small blocks), or one where a block ran out of its strided room, is decoded at running
+            // offsets instead, like the reference's sequential loop (bufferDecompress.js:133-192): token scan -> exact
+            // sizes -> exclusive scan -> decode (the jump decoder with independent history).
+            bool running = !((uint64_t)(n - 1) * B < cap_total);
+            if (!running) {
                 for (uint32_t i = 0; i < n; ++i) {
-                    const uint64_t gap = doff[i] - w;                 // pieces of <= gap bytes never overlap their source
-                    for (uint64_t done = 0; gap && done < olen[i]; done += gap)
-                        CK(cudaMemcpyAsync(d_out + w + done, d_out + doff[i] + done, (size_t)std::min<uint64_t>(gap, olen[i] - done),
-                                           cudaMemcpyDeviceToDevice, st));
-                    w += olen[i];
+                    doff[i] = (uint64_t)i * B;
+                    const uint64_t room = doff[i] < cap_total ? cap_total - doff[i] : 0;
+                    cap[i] = (uint32_t)std::min<uint64_t>(room, B);
                 }
+                CK(cudaMemcpyAsync(d_doff, doff.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(d_cap, cap.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+                // history of an independent block is the dictionary only (LZ4 frame spec; for frames the reference writes,
+                // blocks > 0 never reach before their own start, so this equals bufferDecompress.js:153 on them)
+                CKS(launch_decompress(ctx, d_frame, d_soff, d_slen, n, d_out, d_doff, d_cap, dwin ? d_dict : nullptr, (uint32_t)dwin, 0,
+                                      d_stored, d_olen, d_status, st));
+                CK(cudaMemcpyAsync(olen.data(), d_olen, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(status.data(), d_status, n, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                bool contiguous = true;
+                for (uint32_t i = 0; i < n; ++i) {
+                    if (status[i] && !first_status) first_status = status[i];
+                    if (i + 1 < n && olen[i] != B) contiguous = false;
+                }
+                // "too small" may be the strided room, not the caller's: only the running-offset decode can tell
+                for (uint32_t i = 0; i < n; ++i)
+                    if (status[i] == DLZ4_E_OUTPUT_TOO_SMALL && (uint64_t)i * B + B > cap_total) running = true;
+                if (running) first_status = 0;
+                if (!running && !first_status && !contiguous) {
+                    // close the gaps front to back (forward moves never overlap later data)
+                    uint64_t w = 0;
+                    for (uint32_t i = 0; i < n; ++i) {
+                        const uint64_t gap = doff[i] - w;                 // pieces of <= gap bytes never overlap their source
+                        for (uint64_t done = 0; gap && done < olen[i]; done += gap)
+                            CK(cudaMemcpyAsync(d_out + w + done, d_out + doff[i] + done, (size_t)std::min<uint64_t>(gap, olen[i] - done),
+                                               cudaMemcpyDeviceToDevice, st));
+                        w += olen[i];
+                    }
+                }
+                if (!running) for (uint32_t i = 0; i < n; ++i) total += olen[i];
             }
-            for (uint32_t i = 0; i < n; ++i) total += olen[i];
+            if (running) {
+                CKS(decompress_jump(ctx, d_frame, fpad, d_soff, d_slen, d_stored, slen, n, B, d_out, cap_total, dwin ? d_dict : nullptr,
+                                    (uint32_t)dwin, false, d_olen, d_status, status, &total, st, output, output_cap, &shipped, nullptr));
+                for (uint32_t i = 0; i < n && !first_status; ++i) first_status = status[i];
+            }
         }
     }
     CK(cudaEventRecord(ctx->ev1, st));
@@ -1647,7 +1813,21 @@ int dlz4_frame_decompress_ex(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame
     if (total && !shipped) CK(cudaMemcpyAsync(output, d_out, total, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    ctx->res_out = d_out; ctx->res_out_len = total;
     return DLZ4_OK;
+}
+
+int dlz4_frame_decompress_ex(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_len, const uint8_t *dictionary, uint64_t dict_len,
+                             uint32_t flags, uint8_t *output, uint64_t output_cap, uint64_t *output_len, uint32_t *block_out_len) {
+    return frame_decompress_impl(ctx, frame, frame_len, dictionary, dict_len, flags, output, output_cap, output_len, block_out_len, 0,
+                                 0xFFFFFFFFu);
+}
+
+int dlz4_frame_decompress_range(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_len, uint32_t first_block, uint32_t block_count,
+                                const uint8_t *dictionary, uint64_t dict_len, uint32_t flags, uint8_t *output, uint64_t output_cap,
+                                uint64_t *output_len, uint32_t *block_out_len) {
+    return frame_decompress_impl(ctx, frame, frame_len, dictionary, dict_len, flags, output, output_cap, output_len, block_out_len,
+                                 first_block, block_count);
 }
 
 // ---- stateful xxh32 (the reference's XXHash32 class: update / digest, src/xxhash32/xxhash32Stateful.js) ---------------

@@ -688,6 +688,10 @@ __device__ __forceinline__ uint32_t compress_block_warp_v2(const uint8_t *__rest
     return compress_span_warp<Tab, true>(base, start, len, T, out, ring, st, INT_MAX);
 }
 
+}  // namespace dlz4
+#include "dlz4_wide.cuh"
+namespace dlz4 {
+
 // ------------------------------------------------------------------ compress kernels
 __device__ __forceinline__ uint32_t next_block(uint32_t *counter, uint32_t lane) {
     uint32_t b = 0;
@@ -696,7 +700,7 @@ __device__ __forceinline__ uint32_t next_block(uint32_t *counter, uint32_t lane)
 }
 
 // Independent blocks <= 64 KiB, fresh table, no history: 16-bit table, 32 KiB of shared memory per warp.
-template <int WARPS>
+template <int WARPS, bool kWide>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_compress_fresh16(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
                    const uint32_t *__restrict__ src_len, uint32_t nblocks, uint8_t *__restrict__ dst,
@@ -714,7 +718,13 @@ k_compress_fresh16(const uint8_t *__restrict__ src, const uint64_t *__restrict__
         for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         Tab16 T{tab, 0};
-        const uint32_t c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], ring);
+        uint32_t c;
+        if (kWide) {
+            SpanState st{0, 0, 67u, 0u, 0u, -1};
+            c = compress_span64_warp<Tab16, true>(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], st, INT_MAX);
+        } else {
+            c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], ring);
+        }
         if (lane == 0) comp_len[b] = c;
         __syncwarp();
     }

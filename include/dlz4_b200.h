@@ -73,6 +73,10 @@ void dlz4_segment_stats(const dlz4_ctx *ctx, uint32_t *segments, uint32_t *rerun
  * ArrayBuffers with it).  Any host pointer is accepted everywhere; pageable ones are simply slower. */
 void *dlz4_pinned_alloc(uint64_t bytes);
 void dlz4_pinned_free(void *p);
+/* Page-locks / releases memory the caller already owns (a Node Buffer's backing store, a mapping shared by the ranks of a
+ * box): the way ordinary caller-owned Uint8Arrays (bufferCompress.js:100) reach the pinned PCIe rate without a bounce copy. */
+int dlz4_host_register(void *p, uint64_t bytes);
+int dlz4_host_unregister(void *p);
 
 /* Worst-case compressed size of one n-byte block: n + n/255 + 16. */
 uint64_t dlz4_compress_bound(uint64_t n);
@@ -225,6 +229,37 @@ int dlz4_frame_decompress_ex(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame
 int dlz4_frame_pack_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len,
                         const uint8_t *comp, const uint64_t *comp_off, const uint32_t *comp_len, uint32_t nblocks,
                         int block_checksum, uint8_t *segment, uint64_t *block_pos /* nblocks+1 */, void *stream);
+
+/* ---- sharded frames (block i -> GPU floor(i*G/n); one process and one context per GPU) ----------------------
+ * The block loop of compressBuffer (bufferCompress.js:209-239) over one rank's contiguous range of INDEPENDENT blocks.
+ * dlz4_frame_body_compress compresses `input` (the rank's slice, < 2 GiB, whole blocks except at the frame's end) and packs
+ * [u32 size | stored bit][payload][u32 xxh32]* -- exactly the bytes dlz4_frame_compress writes for those blocks -- in
+ * device memory; *body_len = its length.  The host then scans the ranks' lengths and every rank copies its body to its
+ * place in the host frame with dlz4_frame_body_fetch (no collective touches the data).  Header and EndMark come from
+ * dlz4_frame_header / four zero bytes.
+ */
+int dlz4_frame_body_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len, uint32_t max_block_size,
+                             int block_checksum, uint64_t *body_len);
+int dlz4_frame_body_fetch(dlz4_ctx *ctx, uint8_t *dst, uint64_t dst_cap);
+/* The frame header every path writes (bufferCompress.js:147-178): magic, FLG, BD, [content size u64], [dictID], HC.
+ * Returns its length (7..19).  Host-only arithmetic (xxh32 of <= 14 bytes). */
+size_t dlz4_frame_header(const dlz4_frame_opts *opts, uint64_t content_len, int have_dict, uint32_t dict_id, uint8_t out[19]);
+/* The block loop of decompressBuffer (bufferDecompress.js:133-192) over blocks [first_block, first_block + block_count) of an
+ * independent-block frame: decodes them into `output` (block first_block at output[0]); block_out_len (nullable) receives the
+ * decoded length of each block of the range so that the caller can check that inner blocks are full before trusting the
+ * i * blockMaxSize placement.  flags as dlz4_frame_decompress, except that the content checksum is never verified over a
+ * part (use the relay below).  A linked-block frame is accepted only as a whole (first_block == 0, all blocks). */
+int dlz4_frame_decompress_range(dlz4_ctx *ctx, const uint8_t *frame, uint64_t frame_len, uint32_t first_block,
+                                uint32_t block_count, const uint8_t *dictionary, uint64_t dict_len, uint32_t flags,
+                                uint8_t *output, uint64_t output_cap, uint64_t *output_len, uint32_t *block_out_len);
+/* Whole-stream content checksum across ranks (xxhash32.js:34-57 is one serial chain: "replicas only"): a relay.
+ * Rank r receives the 16-byte accumulator state from rank r-1, runs the stripe loop over the bytes its last
+ * dlz4_frame_body_compress (which = DLZ4_RESIDENT_INPUT) or dlz4_frame_decompress[_range] (DLZ4_RESIDENT_OUTPUT) call left
+ * on its GPU -- nothing is uploaded twice -- and passes the state on; the last rank calls dlz4_xxh32_digest.  Pieces before
+ * the last must be multiples of 16 bytes (whole blocks are). */
+#define DLZ4_RESIDENT_INPUT   0
+#define DLZ4_RESIDENT_OUTPUT  1
+int dlz4_xxh32_update_resident(dlz4_ctx *ctx, dlz4_xxh32_state *s, int which);
 
 #ifdef __cplusplus
 }

@@ -194,3 +194,43 @@ def test_large_independent_frame_takes_the_pipelined_path(dl):
             tail = bytearray(g); tail[-2] ^= 1
             with pytest.raises(dl.LZ4Error, match="Content Checksum Error"):
                 dl.decompressBuffer(bytes(tail))
+
+
+def _flushed_frame(pieces, bd, with_size, stored_first=False):
+    """A spec-valid independent-block frame whose inner blocks are SHORT (what LZ4F_flush-style writers and a stream's
+    update() produce): header by hand, every piece one block compressed by the oracle (stored when that is not smaller)."""
+    import struct
+    from divortio_lz4_b200 import sharded
+    total = sum(len(p) for p in pieces)
+    flg = 0x40 | 0x20 | (0x08 if with_size else 0)
+    desc = bytes([flg, bd << 4]) + (struct.pack("<Q", total) if with_size else b"")
+    out = bytearray(struct.pack("<I", 0x184D2204) + desc + bytes([(oracle.xxh32(desc) >> 8) & 0xFF]))
+    for k, p in enumerate(pieces):
+        c = oracle.compress_block_bytes(np.frombuffer(p, dtype=np.uint8))
+        if (stored_first and k == 0) or len(c) >= len(p):
+            out += struct.pack("<I", len(p) | 0x80000000) + p
+        else:
+            out += struct.pack("<I", len(c)) + c
+    out += struct.pack("<I", 0)
+    return bytes(out), b"".join(pieces)
+
+
+@pytest.mark.parametrize("with_size", [False, True])
+def test_short_inner_blocks_decode_at_running_offsets(dl, with_size):
+    """content_size = 3B with blocks [B/2, B, B, B/2] must decode (the reference decodes sequentially at
+    resultPos, bufferDecompress.js:133-192); so must small blocks under a large blockMaxSize and a stored short first block."""
+    from divortio_lz4_b200 import corpus
+    B = 65536
+    text = corpus.log(11, 3 * B).tobytes()
+    cases = [
+        ([text[:B // 2], text[B // 2:B // 2 + B], text[B // 2 + B:B // 2 + 2 * B], text[B // 2 + 2 * B:]], 4, False),
+        ([text[i:i + 1000] for i in range(0, 40000, 1000)], 7, False),            # 40 small blocks, blockMaxSize 4 MiB
+        ([text[:100], text[100:100 + B], text[100 + B:2 * B]], 4, True),          # stored short block first
+        ([corpus.rand(5, 3000).tobytes(), text[:B], corpus.zero(70).tobytes(), text[B:B + 5]], 4, False),
+    ]
+    for pieces, bd, stored_first in cases:
+        frame, plain = _flushed_frame(pieces, bd, with_size, stored_first)
+        assert oracle.decompress_buffer(frame) == plain
+        assert dl.decompressBuffer(frame) == plain
+        info = dl.frame_info(frame)
+        assert info.nblocks == len(pieces)

@@ -60,19 +60,125 @@ def test_config3_shape_4m_blocks_block_and_content_checksums(env):
     got = dl.compressBuffer(host, None, 4194304, True, True, True, None, True)
     assert len(got) == len(want) and got == want
     assert dl.decompressBuffer(got, None, True, True) == host.tobytes()
-    # the same frame from 4 block-range shards, concatenated on the host (ranks emulated one after the other on this GPU)
-    store = {}
+    # the same frame from 4 block-range shards placed in one host frame (ranks emulated by threads, one context each), and
+    # the sharded decode of it
+    back = np.zeros(n + 64, dtype=np.uint8)
+    out = np.zeros(len(want) + 4096, dtype=np.uint8)
+    total, got_n = _run_thread_ranks(dl, 4, host, out, back, 4194304, True, True)
+    assert bytes(out[:total].tobytes()) == want
+    assert got_n == n and np.array_equal(back[:n], host)
 
-    def make_gather(r):
-        def g(seg):
-            store[r] = seg
-            return [store[k] for k in range(4)] if r == 0 else None
-        return g
 
-    frame = None
-    for r in (1, 2, 3, 0):
-        frame = sharded.compress_sharded(host, 4194304, True, True, True, rank=r, world=4, gather=make_gather(r))
-    assert frame == want
+def _run_thread_ranks(dl, world, host, out, back, bs, cc, bc, frame_max=None):
+    """compress_sharded + decompress_sharded with `world` ranks emulated by threads (own dlz4_ctx each) on this GPU."""
+    import threading
+    from divortio_lz4_b200 import sharded
+    comms = sharded.ThreadComm.group(world)
+    res = [None] * world
+    err = []
+
+    def run(r):
+        try:
+            be = sharded.GpuBackend(dl.Context(0))
+            kw = {} if frame_max is None else {"frame_max": frame_max}
+            t = sharded.compress_sharded(host, out, bs, cc, True, bc, comm=comms[r], backend=be, **kw)
+            g = sharded.decompress_sharded(out[:t], back, True, bc, comm=comms[r], backend=be)
+            res[r] = (t, g)
+        except Exception as e:  # noqa: BLE001
+            err.append(e)
+            comms[r].s.bar.abort()
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=600)
+    assert not err, err
+    assert all(r == res[0] for r in res)
+    return res[0]
+
+
+def test_sharded_multi_frame_and_ragged_world_sizes(env):
+    """The >= 2 GiB rule scaled down: frame_max = 24 MiB cuts a 100 MiB input into 5 frames; 3 ranks (ragged ranges), 64 KiB and
+    4 MiB blocks.  The concatenated frames equal the oracle's per-span frames and decode back (sharded decode, relay checksum)."""
+    dl, corpus, dev, torch, ctx = env
+    from divortio_lz4_b200 import sharded
+    n = 100 * 1024 * 1024 + 777
+    host = corpus.mixed(13, n)
+    for bs in (65536, 4194304):
+        fm = 24 << 20
+        want = b"".join(oracle.compress_buffer(host[lo:hi], None, bs, True, True, True, None, True)
+                        for lo, hi in sharded.frame_spans(n, fm))
+        out = np.zeros(len(want) + 4096, dtype=np.uint8)
+        back = np.zeros(n + 64, dtype=np.uint8)
+        total, got_n = _run_thread_ranks(dl, 3, host, out, back, bs, True, True, frame_max=fm)
+        assert bytes(out[:total].tobytes()) == want, bs
+        assert got_n == n and np.array_equal(back[:n], host)
+        # any frame reader decodes the concatenation as one stream
+        assert dl.decompressFrames(out[:total])[0] == host.tobytes()
+
+
+def _two_gpu_worker(rank, world, port, tag, q):
+    import os
+    import sys
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import divortio_lz4_b200 as dl
+        from divortio_lz4_b200 import corpus, sharded
+        import oracle as orc
+        n = 192 * 1024 * 1024 + 4321
+        cap = n + n // 100 + 65536
+        names = ["in", "out", "back"]
+        sizes = [n, cap, n + 64]
+        bufs = {}
+        if rank == 0:
+            for nm, sz in zip(names, sizes):
+                bufs[nm] = sharded.SharedBuffer("dlz4_t2_%s_%s" % (nm, tag), sz, True)
+            bufs["in"].array[:] = corpus.mixed(31, n)
+        dist.barrier()
+        if rank != 0:
+            for nm, sz in zip(names, sizes):
+                bufs[nm] = sharded.SharedBuffer("dlz4_t2_%s_%s" % (nm, tag), sz, False)
+        be = sharded.GpuBackend(dl.Context(rank))
+        comm = sharded.DistComm()
+        tm = {}
+        total = sharded.compress_sharded(bufs["in"].array, bufs["out"].array, 4194304, True, True, True, comm=comm, backend=be, timings=tm)
+        got = sharded.decompress_sharded(bufs["out"].array[:total], bufs["back"].array, True, True, comm=comm, backend=be)
+        if rank == 0:
+            want = orc.compress_buffer(bufs["in"].array, None, 4194304, True, True, True, None, True)
+            q.put((bytes(bufs["out"].array[:total].tobytes()) == want, got == n,
+                   bool(np.array_equal(bufs["back"].array[:n], bufs["in"].array)), all(b.registered for b in bufs.values())))
+        dist.barrier()
+        for b in bufs.values():
+            b.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_on_two_real_gpus(env):
+    """compress_sharded / decompress_sharded with one process per GPU over a page-locked shared host mapping (NCCL carries the
+    integers and the checksum state only).  Needs >= 2 GPUs (gpurun --gpus 2); skipped on a one-GPU box."""
+    dl, corpus, dev, torch, ctx = env
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    import torch.multiprocessing as mp
+    c = mp.get_context("spawn")
+    q = c.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [c.Process(target=_two_gpu_worker, args=(r, 2, port, str(os.getpid()), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    same, n_ok, back_ok, pinned = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert same and n_ok and back_ok and pinned
 
 
 def test_config4_shape_small_messages_with_dictionary(env):
