@@ -20,6 +20,7 @@ constexpr int kWarpsGeneric32 = 3;   // 3 x 64 KiB
 constexpr int kWarpsDecode = 8;
 constexpr int kJdGroupEvent = 112;    // evp[112..127]: input groups of the jump decoder (evp[0..111]: its output units)
 constexpr int kGtabRegions = 5;      // L2-table regions: work-queue counter 0 (device API) and 1..4 (pipeline lanes)
+constexpr uint32_t kMaxSplitBlocks = 1u << 20;   // blocks per launch of the split (parse + encode) path
 
 struct Buf {
     void *p = nullptr;
@@ -45,6 +46,9 @@ struct dlz4_ctx {
     uint64_t *d_total = nullptr;
     int32_t *d_table = nullptr;         // int32[16384] scratch table
     int wide = 1;                       // shared-memory-table chains use the 64-position window (dlz4_wide.cuh); 0: A/B runs
+    int split = 1;                      // fresh blocks <= 64 KiB: match finder (k_parse_fresh16) + encoder (k_encode_blocks); 0: A/B runs
+    Buf rec;                            // match records of the split path: kGtabRegions regions (one per work-queue counter)
+    uint32_t *d_nrec = nullptr;         // matches per block (split path), kGtabRegions regions of kMaxSplitBlocks
     int hybrid = 1;                     // 64 KiB fresh blocks: hybrid kernel (L2-resident tables) instead of the 7-warp one
     int hy_grid = 0;                    // CTAs that fill the device (sm_count x kHyCtasPerSm)
     int hy_active = 0;                  // cap on the warps used per hybrid CTA (DLZ4_HY_ACTIVE, 0 = all 7; A/B runs)
@@ -144,7 +148,29 @@ int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, 
     // a prefix without an initial table is never referenced: every table entry was inserted by the block itself
     // (blockCompress.js:54-55), so the bytes are those of the block compressed alone
     if (init_table == nullptr) { prefix = nullptr; prefix_len = 0; }
-    if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr && ctx->hybrid) {
+    if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr && ctx->split && n <= kMaxSplitBlocks) {
+        // match finder, then encoder (dlz4_parse.cuh).  Records: len/4 + 1 per block, one scratch region per work-queue counter
+        // so that the chunks of the host pipeline (one counter each) do not share it.
+        const size_t region = (size_t)(counter - ctx->d_counter) % kGtabRegions;
+        const uint64_t rstride = (uint64_t)max_len / 4 + 2;
+        const size_t region_bytes = (((size_t)n * rstride * 8) * 9 / 8 + 255) & ~(size_t)255;      // (headroom: chunks differ a little)
+        if (ctx->rec.cap < region_bytes * kGtabRegions + 256) {
+            // grow-only scratch: every stream that may still read the old one is idle after this
+            CK(cudaDeviceSynchronize());
+            CKS(reserve(ctx, ctx->rec, std::max(region_bytes, (size_t)ctx->rec.cap / kGtabRegions) * kGtabRegions));
+        }
+        const size_t per_region = ((ctx->rec.cap - 256) / kGtabRegions) & ~(size_t)255;
+        uint64_t *recs = (uint64_t *)((uint8_t *)ctx->rec.p + region * per_region);
+        uint32_t *nrec = ctx->d_nrec + region * (size_t)kMaxSplitBlocks;
+        const int grid = (int)std::min<uint64_t>((n + kWarpsFresh16 - 1) / kWarpsFresh16, (uint64_t)ctx->sm_count);
+        k_parse_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * kHashEntries * 2, st>>>(
+            src, src_off, src_len, n, recs, rstride, nrec, counter);
+        CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+        const int egrid = (int)std::min<uint64_t>((n + kWarpsDecode - 1) / kWarpsDecode, (uint64_t)ctx->sm_count * 8);
+        k_encode_blocks<kWarpsDecode><<<egrid, kWarpsDecode * 32, 0, st>>>(src, src_off, src_len, n, recs, rstride, nrec, dst, dst_off,
+                                                                            comp_len, counter);
+        ctx->launches++;
+    } else if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr && ctx->hybrid) {
         // one table region per work-queue counter: kernels of different pipeline lanes run concurrently
         const size_t region = (size_t)(counter - ctx->d_counter) % kGtabRegions;
         // a batch on its own spreads over as many SMs as it has blocks (fewer active warps per CTA); a pipeline chunk
@@ -588,10 +614,13 @@ int dlz4_init(int device, dlz4_ctx **out) {
     if (const char *e = getenv("DLZ4_SEG_MIN_KIB")) ctx->seg_min_bytes = (uint64_t)atoll(e) << 10;     // huge value: serial chain only
     if (const char *e = getenv("DLZ4_JUMP_MIN_KIB")) ctx->jump_min_bytes = (uint64_t)atoll(e) << 10;
     if (const char *e = getenv("DLZ4_WIDE")) ctx->wide = atoi(e) != 0;
+    if (const char *e = getenv("DLZ4_SPLIT")) ctx->split = atoi(e) != 0;
     if (const char *e = getenv("DLZ4_HYBRID")) ctx->hybrid = atoi(e) != 0;      // 0: the 7-warp shared-memory-only kernel (A/B runs)
     ctx->hy_grid = ctx->sm_count * kHyCtasPerSm;
     if (const char *e = getenv("DLZ4_HY_ACTIVE")) ctx->hy_active = std::max(0, std::min(kHyWarps, atoi(e)));
     CK(cudaMalloc(&ctx->d_gtabs, (size_t)kGtabRegions * ctx->hy_grid * kHyGlWarps * kHashEntries * 2));
+    CK(cudaMalloc(&ctx->d_nrec, (size_t)kGtabRegions * kMaxSplitBlocks * 4));
+    CK(cudaFuncSetAttribute(k_parse_fresh16<kWarpsFresh16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpsFresh16 * kHashEntries * 2));
     CK(cudaFuncSetAttribute(k_compress_fresh16h, cudaFuncAttributeMaxDynamicSharedMemorySize, kHySmemBytes));
     CK(cudaFuncSetAttribute(k_compress_overlay, cudaFuncAttributeMaxDynamicSharedMemorySize, kHySmemBytes));
     CK(cudaFuncSetAttribute(k_compress_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, kSegSmemBytes));
@@ -616,6 +645,8 @@ void dlz4_shutdown(dlz4_ctx *ctx) {
     if (ctx->d_total) cudaFree(ctx->d_total);
     if (ctx->d_table) cudaFree(ctx->d_table);
     if (ctx->d_gtabs) cudaFree(ctx->d_gtabs);
+    if (ctx->d_nrec) cudaFree(ctx->d_nrec);
+    if (ctx->rec.p) cudaFree(ctx->rec.p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);

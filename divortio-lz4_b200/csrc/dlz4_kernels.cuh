@@ -699,6 +699,10 @@ __device__ __forceinline__ uint32_t next_block(uint32_t *counter, uint32_t lane)
     return __shfl_sync(FULL, b, 0);
 }
 
+}  // namespace dlz4
+#include "dlz4_parse.cuh"
+namespace dlz4 {
+
 // Independent blocks <= 64 KiB, fresh table, no history: 16-bit table, 32 KiB of shared memory per warp.
 template <int WARPS, bool kWide>
 __global__ void __launch_bounds__(WARPS * 32, 1)

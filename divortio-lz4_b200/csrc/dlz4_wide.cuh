@@ -23,30 +23,32 @@
 
 namespace dlz4 {
 
-__device__ __forceinline__ uint64_t mask_lt64(uint32_t n) { return n >= 64u ? ~0ull : ((1ull << n) - 1ull); }
-
 // candidate bytes (three aligned 16-byte granules, `cs` = byte offset of the candidate inside the first) against the
-// position's own 32 bytes Sw[0..7]: returns the match length pre-extended to at most 32, 0 when the first four bytes differ
+// position's own 32 bytes Sw[0..7]: returns the match length pre-extended to at most 32, 0 when the first four bytes differ.
+// Branch-free on purpose (selects only): the two positions of a lane are independent instruction streams, and only
+// straight-line code lets the scheduler interleave them.
 __device__ __forceinline__ uint32_t wide_verify(const uint4 &q0, const uint4 &q1, const uint4 &q2, const uint32_t cs,
                                                 const uint32_t *Sw) {
     uint32_t v[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-    if (cs & 8u) {
+    const bool s8 = (cs & 8u) != 0, s4 = (cs & 4u) != 0;
 #pragma unroll
-        for (int k = 0; k < 10; ++k) v[k] = v[k + 2];
-    }
-    if (cs & 4u) {
+    for (int k = 0; k < 10; ++k) v[k] = s8 ? v[k + 2] : v[k];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) v[k] = v[k + 1];
-    }
+    for (int k = 0; k < 9; ++k) v[k] = s4 ? v[k + 1] : v[k];
     const uint32_t csh = (cs & 3u) * 8u;
-    if (__funnelshift_r(v[0], v[1], csh) != Sw[0]) return 0u;
-    uint32_t n = 28;
+    uint32_t x[8];
 #pragma unroll
-    for (int k = 7; k >= 1; --k) {
-        const uint32_t x = Sw[k] ^ __funnelshift_r(v[k], v[k + 1], csh);
-        if (x) n = 4u * (uint32_t)(k - 1) + ((uint32_t)(__ffs(x) - 1) >> 3);
-    }
-    return 4u + n;
+    for (int k = 0; k < 8; ++k) x[k] = Sw[k] ^ __funnelshift_r(v[k], v[k + 1], csh);
+    // first differing byte among bytes 4..31 (words x[1..7]; a sentinel behind them stands for "all 28 equal"): halving
+    // with selects, one find-first-set at the end
+    const bool h4 = (x[1] | x[2] | x[3] | x[4]) == 0u;
+    const uint32_t y1 = h4 ? x[5] : x[1], y2 = h4 ? x[6] : x[2], y3 = h4 ? x[7] : x[3], y4 = h4 ? 1u : x[4];
+    const bool h2 = (y1 | y2) == 0u;
+    const uint32_t z1 = h2 ? y3 : y1, z2 = h2 ? y4 : y2;
+    const bool h1 = z1 == 0u;
+    const uint32_t zz = h1 ? z2 : z1;
+    const uint32_t n = (h4 ? 16u : 0u) + (h2 ? 8u : 0u) + (h1 ? 4u : 0u) + ((uint32_t)(__ffs(zz) - 1) >> 3);
+    return x[0] == 0u ? 4u + n : 0u;
 }
 
 // Runs the single-warp parse of the block [start, start + len) from state `st`; arguments and return value as
@@ -114,20 +116,15 @@ __device__ uint32_t compress_span64_warp(const uint8_t *__restrict__ base, const
             const int32_t canda = tab_dec(T, olda), candb = tab_dec(T, oldb);
             const bool oka = canda >= 0 && canda != pa && (((uint32_t)(pa - canda)) >> 16) == 0;
             const bool okb = candb >= 0 && candb != pb && (((uint32_t)(pb - candb)) >> 16) == 0;
-            uint4 qa0 = make_uint4(0, 0, 0, 0), qa1 = qa0, qa2 = qa0, qb0 = qa0, qb1 = qa0, qb2 = qa0;
-            uint32_t csa = 0, csb = 0;
-            if (oka) {            // canda + 35 < pa + 35 <= w + 98 < sEnd; the 16-byte granules holding them are read whole
-                csa = (A0 + (uint32_t)canda) & 15u;
-                const uint4 *cq = reinterpret_cast<const uint4 *>(base + (canda - (int32_t)csa));
-                qa0 = __ldg(cq); qa1 = __ldg(cq + 1);
-                if (csa + 36u > 32u) qa2 = __ldg(cq + 2);
-            }
-            if (okb) {
-                csb = (A0 + (uint32_t)candb) & 15u;
-                const uint4 *cq = reinterpret_cast<const uint4 *>(base + (candb - (int32_t)csb));
-                qb0 = __ldg(cq); qb1 = __ldg(cq + 1);
-                if (csb + 36u > 32u) qb2 = __ldg(cq + 2);
-            }
+            // candidate bytes: three aligned 16-byte granules each (cand + 35 < p + 35 <= w + 98 < sEnd; the granules holding
+            // them are read whole).  A position without a usable candidate reads at its own address instead -- always valid,
+            // already in L1 -- so that the loads and the verification below are straight-line code for both positions.
+            const int32_t la = oka ? canda : pa, lb_ = okb ? candb : pb;
+            const uint32_t csa = (A0 + (uint32_t)la) & 15u, csb = (A0 + (uint32_t)lb_) & 15u;
+            const uint4 *cqa = reinterpret_cast<const uint4 *>(base + (la - (int32_t)csa));
+            const uint4 *cqb = reinterpret_cast<const uint4 *>(base + (lb_ - (int32_t)csb));
+            const uint4 qa0 = __ldg(cqa), qa1 = __ldg(cqa + 1), qa2 = __ldg(cqa + 2);
+            const uint4 qb0 = __ldg(cqb), qb1 = __ldg(cqb + 1), qb2 = __ldg(cqb + 2);
             // ---- same-slot pairs inside the window: tag every slot, read it back
             const uint32_t taga = tab_enc(T, pa), tagb = tab_enc(T, pb);
             __syncwarp();
@@ -152,30 +149,47 @@ __device__ uint32_t compress_span64_warp(const uint8_t *__restrict__ base, const
                 __syncwarp();
             }
             // ---- verify + pre-extend
-            uint32_t mla = oka ? wide_verify(qa0, qa1, qa2, csa, Sx) : 0u;
-            uint32_t mlb = okb ? wide_verify(qb0, qb1, qb2, csb, Sx + 8) : 0u;
-            const uint64_t HM = ((uint64_t)__ballot_sync(FULL, mlb != 0u) << 32) | (uint64_t)__ballot_sync(FULL, mla != 0u);
-            const uint32_t mlpack = mla | (mlb << 8);
-            // ---- walk (uniform): first hit at or behind `cur`, jump behind its match
+            const uint32_t va_ = wide_verify(qa0, qa1, qa2, csa, Sx), vb_ = wide_verify(qb0, qb1, qb2, csb, Sx + 8);
+            const uint32_t mla = oka ? va_ : 0u, mlb = okb ? vb_ : 0u;
+            // hits that take part: positions below the cut
+            uint32_t HMa = __ballot_sync(FULL, mla != 0u), HMb = __ballot_sync(FULL, mlb != 0u);
+            if (trunc < 64u) {
+                HMa &= trunc >= 32u ? FULL : ((1u << trunc) - 1u);
+                HMb &= trunc >= 32u ? ((1u << (trunc - 32u)) - 1u) : 0u;          // trunc - 32 < 32 here
+            }
+            // first hit at or behind relative position e (64: none), from the two 32-bit masks
+            auto first_hit_from = [&](uint32_t e) -> uint32_t {
+                const uint32_t ma = e < 32u ? (HMa >> e) << e : 0u;
+                const uint32_t mb = e < 32u ? HMb : (e < 64u ? (HMb >> (e - 32u)) << (e - 32u) : 0u);
+                return ma ? (uint32_t)__ffs(ma) - 1u : (mb ? 31u + (uint32_t)__ffs(mb) : 64u);
+            };
+            // every hit position's successor in the chain of heads (the first hit at or behind its match's end), computed by
+            // all lanes at once; the serial part below only follows these links.  A pre-extended length of 32 may be a longer
+            // match: its successor is computed in the chain once the length is known.
+            const uint32_t suca = first_hit_from(lane + mla), sucb = first_hit_from(lane + 32u + mlb);
+            const uint32_t pack = (mla | (suca << 6)) | ((mlb | (sucb << 6)) << 16);     // ml: 6 bits, successor: 7 bits, per half
+            // ---- walk (uniform): follow the links from the first hit inside the dense stretch
             const int32_t a_rel0 = anchor - w;                                 // <= 0: literals pending from earlier windows
             int32_t a_rel = a_rel0;
-            uint32_t cur = 0, dl = 128u - smc;                                 // dense probing reaches [cur, dl)
-            uint64_t heads = 0, lits = 0;
-            uint32_t lit0 = 0, D0 = 0;                                         // first head of the window (re-copy of pending literals)
-            uint32_t myDa = 0, myLita = 0, myMla = 0, myDb = 0, myLitb = 0, myMlb = 0;
-            uint32_t lba = 0, lbb = 0;                                         // out[lb + rel] is this position's literal byte
-            for (;;) {
-                const uint32_t bound = min(trunc, dl);
-                if (cur >= bound) break;
-                const uint64_t m = (HM >> cur << cur) & mask_lt64(bound);
-                if (!m) break;
-                const int hl = __ffsll((long long)m) - 1;
-                const uint32_t pk = __shfl_sync(FULL, mlpack, hl);
-                int32_t mlh = (int32_t)((hl & 32) ? (pk >> 8) : (pk & 255u));
-                const int32_t s0 = w + hl;
-                if (mlh == 32 && matchLimit - s0 > 32) {
+            const uint32_t dl0 = 128u - smc;                                   // dense probing reaches [0, dl0) before the first match
+            uint32_t hl = first_hit_from(0u);
+            if (hl >= dl0) hl = 64u;                                           // (dl0 >= 32, trunc already applied)
+            const bool any_head = hl < 64u;
+            const uint32_t D0 = D, lit0 = (uint32_t)((int32_t)hl - a_rel0);     // first head of the window (re-copy of pending literals)
+            constexpr uint32_t kNone = 0xFFFFFFFFu;
+            // out[lb + rel] is where a probed position of a closed sequence stores: a literal lane its own byte, the head lane
+            // (the one position of the range that has a match) the two offset bytes that follow the literals
+            uint32_t lba = kNone, lbb = kNone;
+            uint32_t cur = 0;                                                  // next probe position behind the last match
+            while (hl < 64u) {
+                const uint32_t pk = __shfl_sync(FULL, pack, hl);
+                const uint32_t fld = (pk >> ((hl >> 1) & 16u)) & 0xFFFFu;
+                int32_t mlh = (int32_t)(fld & 63u);
+                uint32_t nxt = fld >> 6;
+                if (mlh == 32 && matchLimit - (w + (int32_t)hl) > 32) {
                     // long match: continue cooperatively, 128 bytes per round
-                    const int32_t m0 = __shfl_sync(FULL, (hl & 32) ? candb : canda, hl);
+                    const int32_t s0 = w + (int32_t)hl;
+                    const int32_t m0 = __shfl_sync(FULL, (hl & 32u) ? candb : canda, hl);
                     for (int32_t eb = 32;; eb += 128) {
                         const int32_t q = s0 + eb + 4 * (int32_t)lane;
                         int32_t nv = matchLimit - q;
@@ -193,45 +207,56 @@ __device__ uint32_t compress_span64_warp(const uint8_t *__restrict__ base, const
                             break;
                         }
                     }
+                    nxt = first_hit_from(hl + (uint32_t)mlh);
                 }
-                const uint32_t lit = (uint32_t)(hl - a_rel);
+                // the sequence: token, [literal length], literals, offset, [match length] (blockCompress.js:75-90, :153-170).
+                // Everything uniform is stored by lane 0 right here; literals and offset by their own lanes after the walk.
+                const uint32_t lit = (uint32_t)((int32_t)hl - a_rel);
                 const uint32_t code = (uint32_t)(mlh - 4);
-                uint32_t litx = 0, mlx = code >= 15u;
-                if (lit >= 15u) litx = 1u + (lit - 15u) / 255u;
-                if (code >= 15u + 255u) mlx = 1u + (code - 15u) / 255u;
-                if (!heads) { lit0 = lit; D0 = D; }
-                const int32_t lo = a_rel > 0 ? a_rel : 0;                      // literal lanes of this sequence: [lo, hl)
-                const uint32_t lb = D + 1u + litx - (uint32_t)a_rel;
-                if ((int32_t)lane >= lo && (int32_t)lane < hl) lba = lb;
-                if ((int32_t)lane + 32 >= lo && (int32_t)lane + 32 < hl) lbb = lb;
-                lits |= mask_lt64((uint32_t)hl) & ~mask_lt64((uint32_t)lo);
-                if (lane == (uint32_t)(hl & 31)) {
-                    if (hl & 32) { myDb = D; myLitb = lit; myMlb = (uint32_t)mlh; }
-                    else { myDa = D; myLita = lit; myMla = (uint32_t)mlh; }
+                uint32_t litx = 0, mlx = 0;
+                if (kEmit && lane == 0) out[D] = (uint8_t)(((lit < 15u ? lit : 15u) << 4) | (code < 15u ? code : 15u));
+                if (lit >= 15u) {                                              // uniform and rare (3 % of sequences on text)
+                    const uint32_t rest = lit - 15u, n255 = rest / 255u;
+                    if (kEmit) {
+                        for (uint32_t i = lane; i < n255; i += 32) out[D + 1u + i] = 255;
+                        if (lane == 0) out[D + 1u + n255] = (uint8_t)(rest - n255 * 255u);
+                    }
+                    litx = n255 + 1u;
                 }
+                if (code >= 15u) {
+                    const uint32_t rest = code - 15u, n255 = rest / 255u;      // n255 > 0 only for a long match (continued above)
+                    if (kEmit) {
+                        uint8_t *const d = out + D + 3u + litx + lit;
+                        for (uint32_t i = lane; i < n255; i += 32) d[i] = 255;
+                        if (lane == 0) d[n255] = (uint8_t)(rest - n255 * 255u);
+                    }
+                    mlx = n255 + 1u;
+                }
+                // probed positions of this sequence: the literal lanes [max(a_rel, 0), hl) and the head hl itself
+                const uint32_t lo = a_rel > 0 ? (uint32_t)a_rel : 0u;
+                const uint32_t lb = D + 1u + litx - (uint32_t)a_rel;
+                if (lane - lo <= hl - lo) lba = lb;
+                if (lane + 32u - lo <= hl - lo) lbb = lb;
                 D += 3u + litx + lit + mlx;
-                heads |= 1ull << hl;
-                a_rel = hl + mlh;
-                cur = (uint32_t)a_rel;
-                dl = cur + 61u;
+                a_rel = (int32_t)hl + mlh;
+                hl = nxt;                                                      // (behind a match dense probing reaches 61 positions: past the window)
             }
+            if (any_head) cur = (uint32_t)a_rel;
             // the window ends where dense probing, the cut or the 64 positions end -- or behind the last match
-            const uint32_t stop = min(trunc, dl);                              // <= 64
+            const uint32_t stop = any_head ? trunc : min(trunc, dl0);         // <= 64
             uint32_t next_rel, tail = 0;
             if (cur < stop) {
                 // trailing probed positions [cur, stop): literals of the still-open sequence, stored provisionally
                 tail = stop - cur;
-                const uint32_t pend0 = heads ? 0u : pend;
+                const uint32_t pend0 = any_head ? 0u : pend;
                 const uint32_t lb = D + 1u + pend0 - cur;
-                if (lane >= cur && lane < stop) lba = lb;
-                if (lane + 32u >= cur && lane + 32u < stop) lbb = lb;
-                lits |= mask_lt64(stop) & ~mask_lt64(cur);
+                if (lane - cur < tail) lba = lb;
+                if (lane + 32u - cur < tail) lbb = lb;
                 next_rel = stop;
             } else {
                 next_rel = cur;
             }
-            const uint64_t probed = lits | heads;
-            const bool pra = (probed >> lane) & 1ull, prb = (probed >> (lane + 32u)) & 1ull;
+            const bool pra = lba != kNone, prb = lbb != kNone;
             // ---- table: exactly the probed positions keep their entry (blockCompress.js:55)
             if (conf) {
                 if (lane < trunc) tab_set_raw(T, ha, pra ? taga : olda);
@@ -240,57 +265,25 @@ __device__ uint32_t compress_span64_warp(const uint8_t *__restrict__ base, const
                 if (!pra) tab_set_raw(T, ha, olda);
                 if (!prb) tab_set_raw(T, hb, oldb);
             }
-            // ---- emission
+            // ---- emission by the probed positions: a position with a match is the head of its sequence (the first hit at or
+            //      behind the previous match's end), any other one a literal
             if (kEmit) {
-                if (heads && a_rel0 < 0 && lit0 >= 15u) {
+                if (any_head && a_rel0 < 0 && lit0 >= 15u) {
                     // the open run reached 15 literals: its provisional bytes sit one length field too low -> re-copy them
                     warp_copy(out + D0 + 2u + (lit0 - 15u) / 255u, base + anchor, (uint32_t)(-a_rel0), lane);
                 }
-                if ((lits >> lane) & 1ull) out[lba + lane] = (uint8_t)Sx[0];
-                if ((lits >> (lane + 32u)) & 1ull) out[lbb + lane + 32u] = (uint8_t)Sx[8];
-                if ((heads >> lane) & 1ull) {
-                    uint8_t *q = out + myDa;
-                    const uint32_t code = myMla - 4u;
-                    q[0] = (uint8_t)(((myLita < 15u ? myLita : 15u) << 4) | (code < 15u ? code : 15u));
-                    q += 1;
-                    if (myLita >= 15u) {
-                        uint32_t rest = myLita - 15u;
-                        while (rest >= 255u) { *q++ = 255; rest -= 255u; }
-                        *q++ = (uint8_t)rest;
-                    }
-                    q += myLita;
-                    const uint32_t offset = (uint32_t)(pa - canda);
-                    q[0] = (uint8_t)offset;
-                    q[1] = (uint8_t)(offset >> 8);
-                    if (code >= 15u) {
-                        uint32_t rest = code - 15u;
-                        q += 2;
-                        while (rest >= 255u) { *q++ = 255; rest -= 255u; }
-                        *q = (uint8_t)rest;
-                    }
+                if (pra) {
+                    uint8_t *const q = out + lba + lane;
+                    if (mla) { const uint32_t offset = (uint32_t)(pa - canda); q[0] = (uint8_t)offset; q[1] = (uint8_t)(offset >> 8); }
+                    else q[0] = (uint8_t)Sx[0];
                 }
-                if ((heads >> (lane + 32u)) & 1ull) {
-                    uint8_t *q = out + myDb;
-                    const uint32_t code = myMlb - 4u;
-                    q[0] = (uint8_t)(((myLitb < 15u ? myLitb : 15u) << 4) | (code < 15u ? code : 15u));
-                    q += 1;
-                    if (myLitb >= 15u) {
-                        uint32_t rest = myLitb - 15u;
-                        while (rest >= 255u) { *q++ = 255; rest -= 255u; }
-                        *q++ = (uint8_t)rest;
-                    }
-                    q += myLitb;
-                    const uint32_t offset = (uint32_t)(pb - candb);
-                    q[0] = (uint8_t)offset;
-                    q[1] = (uint8_t)(offset >> 8);
-                    if (code >= 15u) {
-                        uint32_t rest = code - 15u;
-                        q += 2;
-                        while (rest >= 255u) { *q++ = 255; rest -= 255u; }
-                        *q = (uint8_t)rest;
-                    }
+                if (prb) {
+                    uint8_t *const q = out + lbb + lane + 32u;
+                    if (mlb) { const uint32_t offset = (uint32_t)(pb - candb); q[0] = (uint8_t)offset; q[1] = (uint8_t)(offset >> 8); }
+                    else q[0] = (uint8_t)Sx[8];
                 }
             }
+            const bool heads = any_head;
             if (heads) {
                 anchor = w + a_rel;
                 pend = tail;
