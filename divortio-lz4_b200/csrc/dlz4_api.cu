@@ -46,7 +46,10 @@ struct dlz4_ctx {
     uint64_t *d_total = nullptr;
     int32_t *d_table = nullptr;         // int32[16384] scratch table
     int wide = 1;                       // shared-memory-table chains use the 64-position window (dlz4_wide.cuh); 0: A/B runs
-    int split = 1;                      // fresh blocks <= 64 KiB: match finder (k_parse_fresh16) + encoder (k_encode_blocks); 0: A/B runs
+    int split = 1;                      // fresh blocks <= 64 KiB: match finder (k_parse_pw / k_parse_fresh16) + encoder (k_encode_blocks); 0: A/B runs
+    int pw = 3;                         // producers per chain of the match finder (k_parse_pw<2|3>); 0: one warp per chain (k_parse_fresh16)
+    int pw_sleep = 400;                 // ns a producer sleeps when its ring is full
+    int pw_lead = 6;                    // windows a producer may run ahead of the walker (3..8)
     Buf rec;                            // match records of the split path: kGtabRegions regions (one per work-queue counter)
     uint32_t *d_nrec = nullptr;         // matches per block (split path), kGtabRegions regions of kMaxSplitBlocks
     int hybrid = 1;                     // 64 KiB fresh blocks: hybrid kernel (L2-resident tables) instead of the 7-warp one
@@ -162,9 +165,20 @@ int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, 
         const size_t per_region = ((ctx->rec.cap - 256) / kGtabRegions) & ~(size_t)255;
         uint64_t *recs = (uint64_t *)((uint8_t *)ctx->rec.p + region * per_region);
         uint32_t *nrec = ctx->d_nrec + region * (size_t)kMaxSplitBlocks;
-        const int grid = (int)std::min<uint64_t>((n + kWarpsFresh16 - 1) / kWarpsFresh16, (uint64_t)ctx->sm_count);
-        k_parse_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * kHashEntries * 2, st>>>(
-            src, src_off, src_len, n, recs, rstride, nrec, counter);
+        if (ctx->pw) {
+            // teams spread over the SMs first (a small batch uses one chain per SM), six teams per CTA at most
+            const int grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count);
+            if (ctx->pw == 2)
+                k_parse_pw<2><<<grid, kPwChains * 3 * 32, kPwChains * kPwChainBytes, st>>>(src, src_off, src_len, n, recs, rstride, nrec,
+                                                                                         counter, (uint32_t)ctx->pw_lead, (uint32_t)ctx->pw_sleep);
+            else
+                k_parse_pw<3><<<grid, kPwChains * 4 * 32, kPwChains * kPwChainBytes, st>>>(src, src_off, src_len, n, recs, rstride, nrec,
+                                                                                         counter, (uint32_t)ctx->pw_lead, (uint32_t)ctx->pw_sleep);
+        } else {
+            const int grid = (int)std::min<uint64_t>((n + kWarpsFresh16 - 1) / kWarpsFresh16, (uint64_t)ctx->sm_count);
+            k_parse_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * kHashEntries * 2, st>>>(
+                src, src_off, src_len, n, recs, rstride, nrec, counter);
+        }
         CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
         const int egrid = (int)std::min<uint64_t>((n + kWarpsDecode - 1) / kWarpsDecode, (uint64_t)ctx->sm_count * 8);
         k_encode_blocks<kWarpsDecode><<<egrid, kWarpsDecode * 32, 0, st>>>(src, src_off, src_len, n, recs, rstride, nrec, dst, dst_off,
@@ -615,12 +629,17 @@ int dlz4_init(int device, dlz4_ctx **out) {
     if (const char *e = getenv("DLZ4_JUMP_MIN_KIB")) ctx->jump_min_bytes = (uint64_t)atoll(e) << 10;
     if (const char *e = getenv("DLZ4_WIDE")) ctx->wide = atoi(e) != 0;
     if (const char *e = getenv("DLZ4_SPLIT")) ctx->split = atoi(e) != 0;
+    if (const char *e = getenv("DLZ4_PW")) ctx->pw = std::max(0, std::min(3, atoi(e)));
+    if (const char *e = getenv("DLZ4_PW_SLEEP")) ctx->pw_sleep = std::max(0, atoi(e));
+    if (const char *e = getenv("DLZ4_PW_LEAD")) ctx->pw_lead = std::max(3, std::min(8, atoi(e)));
     if (const char *e = getenv("DLZ4_HYBRID")) ctx->hybrid = atoi(e) != 0;      // 0: the 7-warp shared-memory-only kernel (A/B runs)
     ctx->hy_grid = ctx->sm_count * kHyCtasPerSm;
     if (const char *e = getenv("DLZ4_HY_ACTIVE")) ctx->hy_active = std::max(0, std::min(kHyWarps, atoi(e)));
     CK(cudaMalloc(&ctx->d_gtabs, (size_t)kGtabRegions * ctx->hy_grid * kHyGlWarps * kHashEntries * 2));
     CK(cudaMalloc(&ctx->d_nrec, (size_t)kGtabRegions * kMaxSplitBlocks * 4));
     CK(cudaFuncSetAttribute(k_parse_fresh16<kWarpsFresh16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpsFresh16 * kHashEntries * 2));
+    CK(cudaFuncSetAttribute(k_parse_pw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwChains * kPwChainBytes));
+    CK(cudaFuncSetAttribute(k_parse_pw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwChains * kPwChainBytes));
     CK(cudaFuncSetAttribute(k_compress_fresh16h, cudaFuncAttributeMaxDynamicSharedMemorySize, kHySmemBytes));
     CK(cudaFuncSetAttribute(k_compress_overlay, cudaFuncAttributeMaxDynamicSharedMemorySize, kHySmemBytes));
     CK(cudaFuncSetAttribute(k_compress_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, kSegSmemBytes));

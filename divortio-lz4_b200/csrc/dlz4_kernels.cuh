@@ -701,6 +701,7 @@ __device__ __forceinline__ uint32_t next_block(uint32_t *counter, uint32_t lane)
 
 }  // namespace dlz4
 #include "dlz4_parse.cuh"
+#include "dlz4_pw.cuh"
 namespace dlz4 {
 
 // Independent blocks <= 64 KiB, fresh table, no history: 16-bit table, 32 KiB of shared memory per warp.

@@ -1,0 +1,422 @@
+// dlz4_pw.cuh -- the match finder of compressBlock (blockCompress.js:48-71,143-150) as a producer/walker pipeline.
+//
+// Why: the exact greedy parse is one dependent chain per block, and a chain's table is 32 KiB whatever is done, so an SM holds
+// at most six or seven chains with their tables on chip.  One warp per chain (k_parse_fresh16) leaves that warp alone with
+// both halves of the work -- the memory round trips (table entry -> candidate bytes -> compare) and the decisions (which
+// position is probed next) -- and the chain runs at the SUM of their latencies with the SM's issue slots 30 % used.  Here a
+// chain is a team of warps and the two halves overlap:
+//
+//   producers (kNP warps)   walk a FIXED grid of 32-position windows ahead of the parse.  For every position p of a window:
+//                           hash (:53), the table entry as it is at that moment, the candidate's bytes, verification and
+//                           pre-extension to 32 bytes (:63, :147-150).  Result: one 8-byte ring entry per position in shared
+//                           memory {slot, entry seen, match length against it, window number}.  Nothing a producer does
+//                           depends on the parse except the table entry it happened to read.
+//   walker (1 warp)         the serial loop itself, 32 upcoming probe positions per step (the skip schedule :66-67 makes them a
+//                           function of (sIndex, searchMatchCount)).  A lane takes its position's ring entry and the slot's
+//                           CURRENT value; if that equals the value the producer saw, the producer's match length is the
+//                           serial loop's (same candidate, same bytes).  The step ends at the first hit: lanes up to it tag
+//                           their slots (= the inserts of :55), the hit lane's match becomes a record.  Same-slot pairs among
+//                           the tagging lanes (read-back differs) and stale entries (slot changed since the producer looked)
+//                           cut the step in front of them; a stale position at the head of a step is probed the slow way,
+//                           from global memory.  Measured on log text (profiles/scratch/r02/pw_stats.c): 1.01 steps per
+//                           sequence, 3.3 % of the steps cut, 0.1-0.3 % of the probes stale with producers <= 128 positions ahead.
+//
+// The walker never waits for global memory on its common path (ring and table are shared memory), the producers never wait
+// for the walker except for ring space.  Sparse stretches (searchMatchCount > kPwRingSmc: incompressible data) and the last
+// bytes of a block are probed by the walker alone with the batch step of dlz4_parse.cuh while the producers sleep.
+//
+// Exactness: a producer's entry is used only under `slot value now == slot value seen`; everything else is decided by the
+// walker from the table it alone writes, in probe order.  Output: the match records of dlz4_parse.cuh (k_encode_blocks
+// turns them into the block's bytes).
+#pragma once
+
+namespace dlz4 {
+
+constexpr int kPwChains = 6;                  // chains (teams) per CTA: 6 x (32 KiB table + 2 KiB ring) of 227 KiB
+constexpr int kPwRing = 256;                  // ring entries (positions) per chain: 8 windows
+constexpr int kPwCtl = 64;                    // control bytes per chain
+constexpr int kPwChainBytes = kHashEntries * 2 + kPwRing * 8 + kPwCtl;
+constexpr uint32_t kPwRingSmc = 160u;         // the walker uses the ring while searchMatchCount <= this (steps of 1 and 2)
+constexpr uint32_t kPwDone = 0x80000000u, kPwSparse = 0x40000000u;
+
+struct PwCtl {                                // one per chain, in shared memory
+    volatile uint32_t w_pos;                  // walker's position (block-relative) | kPwSparse | kPwDone
+    volatile uint32_t block;                  // block index of the team, 0xFFFFFFFF: no more work
+};
+
+__device__ __forceinline__ void pw_bar(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint64_t pw_lds64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void pw_sts64(uint64_t *p, uint64_t v) {
+    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "l"(v) : "memory");
+}
+
+// common prefix of base[s0 + eb ..] and base[m0 + eb ..] from byte eb on, bounded by matchLimit (:147-150); all lanes.
+__device__ __forceinline__ uint32_t pw_extend(const uint8_t *__restrict__ base, int32_t s0, int32_t m0, int32_t eb,
+                                              int32_t matchLimit, uint32_t lane) {
+    for (;; eb += 256) {
+        const int32_t q0 = s0 + eb + 4 * (int32_t)lane, q1 = q0 + 128;
+        int32_t nv0 = matchLimit - q0, nv1 = matchLimit - q1;
+        nv0 = nv0 > 4 ? 4 : nv0; nv1 = nv1 > 4 ? 4 : nv1;
+        int32_t eq0 = 0, eq1 = 0;
+        uint32_t x0 = 0, x1 = 0;
+        if (nv0 > 0) x0 = ld32u(base + q0) ^ ld32u(base + (m0 - s0) + q0);
+        if (nv1 > 0) x1 = ld32u(base + q1) ^ ld32u(base + (m0 - s0) + q1);
+        if (nv0 > 0) { eq0 = x0 ? ((__ffs(x0) - 1) >> 3) : 4; eq0 = eq0 < nv0 ? eq0 : nv0; }
+        if (nv1 > 0) { eq1 = x1 ? ((__ffs(x1) - 1) >> 3) : 4; eq1 = eq1 < nv1 ? eq1 : nv1; }
+        const uint32_t stop0 = __ballot_sync(FULL, eq0 < 4);
+        if (stop0) { const int l = __ffs(stop0) - 1; return (uint32_t)(eb + 4 * l + __shfl_sync(FULL, eq0, l)); }
+        const uint32_t stop1 = __ballot_sync(FULL, eq1 < 4);
+        if (stop1) { const int l = __ffs(stop1) - 1; return (uint32_t)(eb + 128 + 4 * l + __shfl_sync(FULL, eq1, l)); }
+    }
+}
+
+// ---- producer: window k (positions 32k .. 32k+31) of the block at `base`
+__device__ __forceinline__ void pw_produce(const uint8_t *__restrict__ base, const uint32_t k, const uint16_t *tab, uint64_t *ring,
+                                           const uint32_t lane) {
+    const uint32_t p = 32u * k + lane;
+    const uintptr_t ba = reinterpret_cast<uintptr_t>(base);
+    const uint32_t a = (uint32_t)(ba & 3u) + p;
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(ba & ~(uintptr_t)3) + (a >> 2);
+    const uint32_t sh = (a & 3u) * 8u;
+    uint32_t w[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) w[i] = __ldg(wp + i);
+    uint32_t S[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) S[i] = __funnelshift_r(w[i], w[i + 1], sh);
+    const uint32_t h = (S[0] * 2654435761u) >> 18;                                   // :53
+    const uint32_t seen = *reinterpret_cast<const volatile uint16_t *>(tab + h);    // the slot as it is right now
+    const bool ok = seen != p;                                                       // :62 with the 16-bit table (Tab16: 0 = position 0)
+    const uint32_t la = ok ? seen : p;                                               // no candidate: read at the own address
+    const uint32_t cs = ((uint32_t)(ba & 15u) + la) & 15u;
+    const uint4 *cq = reinterpret_cast<const uint4 *>(base + la - cs);
+    const uint4 q0 = __ldg(cq), q1 = __ldg(cq + 1), q2 = __ldg(cq + 2);
+    const uint32_t v = wide_verify(q0, q1, q2, cs, S);                               // 0 or 4..32
+    const uint32_t ml = ok ? v : 0u;
+    const uint32_t lo = h | (ml << 14) | (((k + 1u) & 0xFFFu) << 20);
+    pw_sts64(ring + (p & (kPwRing - 1)), (uint64_t)lo | ((uint64_t)seen << 32));
+}
+
+template <int kNP>
+__device__ __forceinline__ void pw_producer(const uint8_t *__restrict__ base, const uint32_t nwin, const uint32_t lead,
+                                            const uint32_t j, const uint16_t *tab, uint64_t *ring, PwCtl *ctl, const uint32_t lane,
+                                            const uint32_t full_ns) {
+    uint32_t k = j;
+    for (;;) {
+        const uint32_t wpos = ctl->w_pos;
+        if (wpos & kPwDone) break;
+        if (wpos & kPwSparse) { __nanosleep(256); continue; }
+        const uint32_t wk = wpos >> 5;
+        if (k < wk) k = wk + ((j + (uint32_t)kNP - wk % (uint32_t)kNP) % (uint32_t)kNP);      // first window >= wk of this warp's class
+        if (k >= nwin) { __nanosleep(1024); continue; }
+        if (k >= wk + lead) { __nanosleep(full_ns); continue; }
+        pw_produce(base, k, tab, ring, lane);
+        k += (uint32_t)kNP;
+    }
+}
+
+// ---- walker: the serial loop.  Returns the number of records written.
+__device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, const int32_t len, const uint32_t nwin, uint16_t *tab,
+                                              const uint64_t *ring, PwCtl *ctl, uint64_t *__restrict__ rec, const uint32_t lane) {
+    const uint32_t lt = (1u << lane) - 1u;
+    const int32_t sEnd = len;
+    const int32_t mflimit = sEnd - 12;                                          // blockCompress.js:34
+    const int32_t matchLimit = sEnd - 5;                                        // :35
+    const int32_t plimit = (int32_t)(32u * nwin);                               // positions below have ring entries
+    const int32_t rlimit = plimit < mflimit ? plimit : mflimit;
+    int32_t sIndex = 0;
+    uint32_t smc = 67;                                                          // :40 searchMatchCount
+    uint32_t nrec = 0;
+    uint32_t pub = 0;                                                           // what ctl->w_pos holds
+    const SrcFlat S{base};
+    Tab16 T{tab, 0};
+    uint2 *const rec2 = reinterpret_cast<uint2 *>(rec);
+
+    while (sIndex < mflimit) {                                                  // :48
+        if (smc <= 96u && sIndex + 32 <= rlimit) {
+            // ---- path step: while searchMatchCount stays below 128 the schedule steps by 1 (:66-67), so the parse inside the
+            //      next 32 positions is a walk over the producers' match lengths: from a hit to the position behind its match,
+            //      from a miss to the next position.  Every lane computes the positions reachable from its own by pointer
+            //      doubling; lane 0's set is the set of PROBED positions.  Those lanes validate (slot unchanged since the
+            //      producer looked, no two of them in one slot) and insert themselves; the hits among them are the records.
+            const uint32_t s = (uint32_t)sIndex;
+            if ((s ^ pub) >> 5) { pub = s; if (lane == 0) ctl->w_pos = s; }
+            const uint32_t p = s + lane;
+            const uint64_t *slot = ring + (p & (kPwRing - 1));
+            const uint32_t want = ((p >> 5) + 1u) & 0xFFFu;
+            uint64_t e;
+            for (;;) {
+                e = pw_lds64(slot);
+                if (__all_sync(FULL, ((uint32_t)e >> 20) == want)) break;
+                __nanosleep(32);
+            }
+            const uint32_t lo = (uint32_t)e, seen = (uint32_t)(e >> 32);
+            const uint32_t h = lo & 0x3FFFu, ml = (lo >> 14) & 63u;
+            const uint32_t cur = tab[h];                                       // :54 (state before this step)
+            // reach: n = where the walk from this lane stands (>= 32: left the step; a pre-extension that hit its cap of 32
+            // ends the walk at that position, n = 64), m = positions visited so far
+            uint32_t n = ml == 32u ? 64u : lane + (ml ? ml : 1u);
+            uint32_t m = 1u << lane;
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                const uint32_t mj = __shfl_sync(FULL, m, n), nj = __shfl_sync(FULL, n, n);      // (source lane = n mod 32)
+                if (n < 32u) { m |= mj; n = nj; }
+            }
+            const uint32_t PM = __shfl_sync(FULL, m, 0), exitp = __shfl_sync(FULL, n, 0);
+            const bool probed = (PM >> lane) & 1u;
+            const uint32_t tag = p & 0xFFFFu;
+            __syncwarp();                                                      // every lane holds its `cur` before any slot changes
+            if (probed) tab[h] = (uint16_t)tag;                                 // :55
+            __syncwarp();
+            const uint32_t r = probed ? (uint32_t)tab[h] : tag;
+            const uint32_t bad = __ballot_sync(FULL, probed && (r != tag || cur != seen));
+            const uint32_t claim = __ballot_sync(FULL, ml != 0u);
+            if (!bad) {
+                const uint32_t HM = PM & claim;                                // the matches, in order
+                const uint32_t nh = (uint32_t)__popc(HM);
+                if (((HM >> lane) & 1u) && ml != 32u) rec2[nrec + (uint32_t)__popc(HM & lt)] = rec_pack(p, ml, p - cur);
+                if (exitp == 64u) {
+                    // the walk ended at a match of 32 or more bytes (the last probed position): its real length (:147-150)
+                    const uint32_t c = 31u - (uint32_t)__clz(PM);
+                    const uint32_t pc = s + c, curc = __shfl_sync(FULL, cur, c);
+                    const uint32_t mlx = pw_extend(base, (int32_t)pc, (int32_t)curc, 32, matchLimit, lane);
+                    if (lane == 0) rec2[nrec + nh - 1u] = rec_pack(pc, mlx, pc - curc);
+                    sIndex = (int32_t)(pc + mlx);
+                    smc = 67u;
+                } else {
+                    sIndex = (int32_t)(s + exitp);
+                    if (HM) smc = 67u + (uint32_t)__popc(PM & ~((2u << (31 - __clz(HM))) - 1u));      // misses behind the last match
+                    else smc += (uint32_t)__popc(PM);
+                }
+                nrec += nh;
+                continue;
+            }
+            // ---- a same-slot pair or a stale entry among the probed positions: the probed positions in front of the first
+            //      such position are still the serial loop's (validated one by one, pairwise different slots); keep them, undo
+            //      the rest, and probe the first position behind them the slow way
+            const uint32_t inv = (probed && r != tag) ? min(tag, r) : 0xFFFFFFFFu;              // lower position of a pair
+            const uint32_t cutpos = __reduce_min_sync(FULL, inv);
+            const uint32_t stale = __ballot_sync(FULL, probed && cur != seen);
+            const uint32_t Bl = min(cutpos == 0xFFFFFFFFu ? 32u : ((cutpos - s) & 0xFFFFu) + 1u, stale ? (uint32_t)__ffs(stale) - 1u : 32u);
+            const uint32_t below = (1u << Bl) - 1u;                            // Bl <= 31
+            if (probed && lane >= Bl) tab[h] = (uint16_t)cur;                   // undo
+            __syncwarp();
+            if (probed && lane < Bl) tab[h] = (uint16_t)tag;                    // (a kept lane may share its slot with an undone one)
+            __syncwarp();
+            const uint32_t keep = PM & below, HMk = keep & claim;
+            if ((HMk >> lane) & 1u) rec2[nrec + (uint32_t)__popc(HMk & lt)] = rec_pack(p, ml, p - cur);
+            nrec += (uint32_t)__popc(HMk);
+            if (HMk) smc = 67u + (uint32_t)__popc(keep & ~((2u << (31 - __clz(HMk))) - 1u));
+            else smc += (uint32_t)__popc(keep);
+            sIndex = (int32_t)(s + (uint32_t)__ffs(PM & ~below) - 1u);
+            // one position, :50-71
+            const uint32_t hx = __shfl_sync(FULL, h, (uint32_t)sIndex - s);
+            const uint32_t cand = tab[hx];
+            __syncwarp();
+            if (lane == 0) tab[hx] = (uint16_t)sIndex;
+            __syncwarp();
+            uint32_t mlx = 0;
+            if (cand != (uint32_t)sIndex) mlx = pw_extend(base, sIndex, (int32_t)cand, 0, matchLimit, lane);
+            if (mlx >= 4u) {
+                if (lane == 0) rec2[nrec] = rec_pack((uint32_t)sIndex, mlx, (uint32_t)sIndex - cand);
+                ++nrec;
+                sIndex += (int32_t)mlx;
+                smc = 67u;
+            } else {
+                sIndex += (int32_t)(smc >> 6);
+                ++smc;
+            }
+            continue;
+        }
+        if (smc <= kPwRingSmc && sIndex < rlimit) {
+            // ---- ring step: the next 32 probe positions of the skip schedule
+            const uint32_t bs = skip_sum(smc);
+            const int32_t p = sIndex + (int32_t)(skip_sum(smc + lane) - bs);
+            const bool valid = p < rlimit;
+            if (pub != (uint32_t)sIndex) { pub = (uint32_t)sIndex; if (lane == 0) ctl->w_pos = pub; }
+            const uint64_t *slot = ring + ((uint32_t)p & (kPwRing - 1));
+            const uint32_t want = (((uint32_t)p >> 5) + 1u) & 0xFFFu;
+            uint64_t e;
+            for (;;) {
+                e = pw_lds64(slot);
+                const bool ready = !valid || (((uint32_t)e >> 20) == want);
+                if (__all_sync(FULL, ready)) break;
+                __nanosleep(20);
+            }
+            const uint32_t lo = (uint32_t)e, seen = (uint32_t)(e >> 32);
+            const uint32_t h = lo & 0x3FFFu, ml = (lo >> 14) & 63u;
+            const uint32_t cur = tab[h];                                       // :54 (state before this step)
+            const uint32_t claim = __ballot_sync(FULL, valid && ml != 0u);
+            const uint32_t f = claim ? (uint32_t)__ffs(claim) - 1u : 32u;
+            const bool active = valid && lane <= f;
+            const uint32_t tag = (uint32_t)p & 0xFFFFu;
+            __syncwarp();                                                      // every lane holds its `cur` before any slot changes
+            if (active) tab[h] = (uint16_t)tag;                                 // :55
+            __syncwarp();
+            const uint32_t r = active ? (uint32_t)tab[h] : tag;
+            const uint32_t bad = __ballot_sync(FULL, active && (r != tag || cur != seen));
+            if (!bad) {
+                if (claim) {
+                    // lanes below f: misses; lane f: the match (:71, :143-174)
+                    const int32_t pf = sIndex + (int32_t)(skip_sum(smc + f) - bs);
+                    const uint32_t curf = __shfl_sync(FULL, cur, f);
+                    uint32_t mlf = __shfl_sync(FULL, ml, f);
+                    if (mlf == 32u) mlf = pw_extend(base, pf, (int32_t)curf, 32, matchLimit, lane);
+                    if (lane == 0) rec2[nrec] = rec_pack((uint32_t)pf, mlf, (uint32_t)pf - curf);
+                    ++nrec;
+                    sIndex = pf + (int32_t)mlf;
+                    smc = 67u;
+                } else {
+                    const uint32_t nv = (uint32_t)__popc(__ballot_sync(FULL, valid));
+                    sIndex += (int32_t)(skip_sum(smc + nv) - bs);
+                    smc += nv;
+                }
+                continue;
+            }
+            // ---- cut: the lanes in front of the first same-slot pair / stale entry are plain misses
+            const uint32_t inv = (active && r != tag) ? min((uint32_t)p, r) : 0xFFFFFFFFu;      // lower position of the pair
+            const uint32_t cutpos = __reduce_min_sync(FULL, inv);
+            const uint32_t grp = __ballot_sync(FULL, active && (uint32_t)p <= cutpos);
+            const uint32_t stale = __ballot_sync(FULL, active && cur != seen);
+            const uint32_t c = min((uint32_t)__popc(grp), stale ? (uint32_t)__ffs(stale) - 1u : 32u);
+            if (active && lane >= c) tab[h] = (uint16_t)cur;                    // undo
+            __syncwarp();
+            if (active && lane < c) tab[h] = (uint16_t)tag;                     // (a kept lane may share its slot with an undone one)
+            __syncwarp();
+            if (c != 0u) {
+                sIndex += (int32_t)(skip_sum(smc + c) - bs);
+                smc += c;
+                continue;
+            }
+            // ---- the position at the head of the step is stale: probe it the slow way (one position, :50-71)
+            const uint32_t h0 = __shfl_sync(FULL, h, 0);
+            const uint32_t cand = tab[h0];
+            __syncwarp();
+            if (lane == 0) tab[h0] = (uint16_t)sIndex;
+            __syncwarp();
+            uint32_t ml0 = 0;
+            if (cand != (uint32_t)sIndex) ml0 = pw_extend(base, sIndex, (int32_t)cand, 0, matchLimit, lane);
+            if (ml0 >= 4u) {
+                if (lane == 0) rec2[nrec] = rec_pack((uint32_t)sIndex, ml0, (uint32_t)sIndex - cand);
+                ++nrec;
+                sIndex += (int32_t)ml0;
+                smc = 67u;
+            } else {
+                sIndex += (int32_t)(smc >> 6);
+                ++smc;
+            }
+            continue;
+        }
+
+        // ---- batch step (sparse schedule, block tail): the walker alone, from global memory; producers sleep
+        if (smc > kPwRingSmc && sIndex < rlimit) {
+            const uint32_t v = (uint32_t)sIndex | kPwSparse;
+            if (pub != v) { pub = v; if (lane == 0) ctl->w_pos = pub; }
+        }
+        const uint32_t base_sum = skip_sum(smc);
+        const int32_t p = sIndex + (int32_t)(skip_sum(smc + lane) - base_sum);
+        const bool valid = p < mflimit;
+        uint32_t seq = 0, h = 0x10000u + lane;
+        int32_t cand = -1;
+        if (valid) {
+            seq = S.ld32(p);
+            h = (seq * 2654435761u) >> 18;
+            cand = T.get(h);
+        }
+        const uint32_t same = __match_any_sync(FULL, h);
+        const uint32_t prev = same & lt;
+        const int j = prev ? 31 - __clz(prev) : (int)lane;
+        const int32_t pj = __shfl_sync(FULL, p, j);
+        const uint32_t sj = __shfl_sync(FULL, seq, j);
+        uint32_t cseq = sj;
+        if (prev) cand = pj;
+        const bool ok = valid && cand >= 0 && cand != p && (((uint32_t)(p - cand)) >> 16) == 0;
+        if (ok && !prev) cseq = S.ld32(cand);
+        const bool hit = ok && cseq == seq;
+        const uint32_t hits = __ballot_sync(FULL, hit);
+        const uint32_t vmask = __ballot_sync(FULL, valid);
+        const int hl = __ffs(hits) - 1;
+        const uint32_t commit = hits ? ((2u << hl) - 1u) : vmask;
+        if (((commit >> lane) & 1u) && ((same & commit) >> lane) == 1u) T.put(h, p);
+        __syncwarp();
+        if (!hits) {
+            if (vmask != FULL) break;                            // ran into mflimit: loop ends
+            sIndex += (int32_t)(skip_sum(smc + 32u) - base_sum);
+            smc += 32u;
+            continue;
+        }
+        const int32_t s0 = __shfl_sync(FULL, p, hl);
+        const int32_t m0 = __shfl_sync(FULL, cand, hl);
+        smc = 67;
+        const uint32_t ml = pw_extend(base, s0, m0, 4, matchLimit, lane);
+        if (lane == 0) rec2[nrec] = rec_pack((uint32_t)s0, ml, (uint32_t)(s0 - m0));
+        ++nrec;
+        sIndex = s0 + (int32_t)ml;
+    }
+    return nrec;
+}
+
+// Fresh independent blocks <= 64 KiB: the match finder as producer/walker teams.  Records as k_parse_fresh16.
+// CTA = kPwChains teams of (1 + kNP) warps; warp t of a team: 0 = walker, 1.. = producers.
+template <int kNP>
+__global__ void __launch_bounds__(kPwChains * (1 + kNP) * 32, 1)
+k_parse_pw(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ src_len,
+           uint32_t nblocks, uint64_t *__restrict__ rec_base, uint64_t rec_stride /* records per block */,
+           uint32_t *__restrict__ nrec_out, uint32_t *counter, uint32_t lead,
+           uint32_t full_ns /* a producer with a full ring sleeps this long: the ring buffers several windows */) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr uint32_t kTeam = (1 + kNP) * 32;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t chain = warp / (1 + kNP), role = warp % (1 + kNP);
+    const uint32_t tid = threadIdx.x - chain * kTeam;                          // thread index inside the team
+    uint8_t *const cb = smem + (size_t)chain * kPwChainBytes;
+    uint16_t *const tab = reinterpret_cast<uint16_t *>(cb);
+    uint64_t *const ring = reinterpret_cast<uint64_t *>(cb + kHashEntries * 2);
+    PwCtl *const ctl = reinterpret_cast<PwCtl *>(cb + kHashEntries * 2 + kPwRing * 8);
+    const uint32_t bar = 1u + chain;
+    // first block of a team: spread over the CTAs first, then over the teams of a CTA; later ones from the queue
+    uint32_t first = chain * gridDim.x + blockIdx.x;
+    const uint32_t qbase = gridDim.x * (uint32_t)kPwChains;
+    bool have_first = true;
+    for (;;) {
+        pw_bar(bar, kTeam);                                                    // everyone is done with the previous block
+        if (role == 0 && lane == 0) {
+            uint32_t b;
+            if (have_first) b = first; else b = qbase + atomicAdd(counter, 1u);
+            ctl->block = b < nblocks ? b : 0xFFFFFFFFu;
+            ctl->w_pos = 0u;
+        }
+        have_first = false;
+        pw_bar(bar, kTeam);
+        const uint32_t b = ctl->block;
+        if (b == 0xFFFFFFFFu) return;
+        const uint32_t len = src_len[b];
+        if (len > 65536u) {
+            if (role == 0 && lane == 0) nrec_out[b] = 0xFFFFFFFFu;
+            continue;
+        }
+        {   // empty table (bufferCompress.js:182 / :235), invalid ring
+            uint4 *z = reinterpret_cast<uint4 *>(cb);
+            for (uint32_t i = tid; i < (kHashEntries * 2 + kPwRing * 8) / 16; i += kTeam) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        pw_bar(bar, kTeam);
+        const uint8_t *base = src + src_off[b];
+        // windows whose loads stay inside the block: position 32k+31 reads its own bytes up to +39 and, for a candidate right
+        // below it, 16-byte granules up to +47
+        const uint32_t nwin = len >= 80u ? (len - 79u) / 32u + 1u : 0u;
+        if (role == 0) {
+            const uint32_t n = pw_walker(base, (int32_t)len, nwin, tab, ring, ctl, rec_base + (uint64_t)b * rec_stride, lane);
+            if (lane == 0) { nrec_out[b] = n; ctl->w_pos = kPwDone; }
+        } else {
+            pw_producer<kNP>(base, nwin, lead, role - 1u, tab, ring, ctl, lane, full_ns);
+        }
+    }
+}
+
+}  // namespace dlz4
