@@ -76,48 +76,111 @@ __device__ __forceinline__ uint32_t pw_extend(const uint8_t *__restrict__ base, 
     }
 }
 
-// ---- producer: window k (positions 32k .. 32k+31) of the block at `base`
-__device__ __forceinline__ void pw_produce(const uint8_t *__restrict__ base, const uint32_t k, const uint16_t *tab, uint64_t *ring,
-                                           const uint32_t lane) {
-    const uint32_t p = 32u * k + lane;
-    const uintptr_t ba = reinterpret_cast<uintptr_t>(base);
-    const uint32_t a = (uint32_t)(ba & 3u) + p;
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(ba & ~(uintptr_t)3) + (a >> 2);
-    const uint32_t sh = (a & 3u) * 8u;
-    uint32_t w[9];
+constexpr uint32_t kPwCap = 64u;              // producers pre-extend a match to this many bytes; the walker continues a longer one
+constexpr uint32_t kPwGenMask = 0x7FFu;       // ring entry: slot (14 bits) | match length (7) | window number + 1 (11); high word: entry seen
+
+// candidate bytes (three aligned 16-byte granules, `cs` = byte offset of the first wanted byte inside the first) against
+// the 32 bytes Sw[0..7]: number of equal leading bytes, 0..32.  Branch-free like wide_verify.
+__device__ __forceinline__ uint32_t pw_count32(const uint4 &q0, const uint4 &q1, const uint4 &q2, const uint32_t cs, const uint32_t *Sw) {
+    uint32_t v[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+    const bool s8 = (cs & 8u) != 0, s4 = (cs & 4u) != 0;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) w[i] = __ldg(wp + i);
-    uint32_t S[8];
+    for (int k = 0; k < 10; ++k) v[k] = s8 ? v[k + 2] : v[k];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) S[i] = __funnelshift_r(w[i], w[i + 1], sh);
-    const uint32_t h = (S[0] * 2654435761u) >> 18;                                   // :53
-    const uint32_t seen = *reinterpret_cast<const volatile uint16_t *>(tab + h);    // the slot as it is right now
-    const bool ok = seen != p;                                                       // :62 with the 16-bit table (Tab16: 0 = position 0)
-    const uint32_t la = ok ? seen : p;                                               // no candidate: read at the own address
-    const uint32_t cs = ((uint32_t)(ba & 15u) + la) & 15u;
-    const uint4 *cq = reinterpret_cast<const uint4 *>(base + la - cs);
-    const uint4 q0 = __ldg(cq), q1 = __ldg(cq + 1), q2 = __ldg(cq + 2);
-    const uint32_t v = wide_verify(q0, q1, q2, cs, S);                               // 0 or 4..32
-    const uint32_t ml = ok ? v : 0u;
-    const uint32_t lo = h | (ml << 14) | (((k + 1u) & 0xFFFu) << 20);
-    pw_sts64(ring + (p & (kPwRing - 1)), (uint64_t)lo | ((uint64_t)seen << 32));
+    for (int k = 0; k < 9; ++k) v[k] = s4 ? v[k + 1] : v[k];
+    const uint32_t csh = (cs & 3u) * 8u;
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = Sw[k] ^ __funnelshift_r(v[k], v[k + 1], csh);
+    const bool h4 = (x[0] | x[1] | x[2] | x[3]) == 0u;
+    const uint32_t y0 = h4 ? x[4] : x[0], y1 = h4 ? x[5] : x[1], y2 = h4 ? x[6] : x[2], y3 = h4 ? x[7] : x[3];
+    const bool h2 = (y0 | y1) == 0u;
+    const uint32_t z0 = h2 ? y2 : y0, z1 = h2 ? y3 : y1;
+    const bool h1 = z0 == 0u;
+    const uint32_t zz = h1 ? z1 : z0;
+    return (h4 ? 16u : 0u) + (h2 ? 8u : 0u) + (h1 ? 4u : 0u) + (zz ? ((uint32_t)(__ffs(zz) - 1) >> 3) : 4u);
 }
 
+// ---- producer: the windows k and k+1 (positions 32k .. 32k+63) of the block at `base`, two positions per lane -- two
+//      independent instruction streams, so the memory round trips (source words, table entry, candidate bytes) overlap.
+//      two == false: window k only (the last window of a block).
+__device__ __forceinline__ void pw_produce2(const uint8_t *__restrict__ base, const uint32_t k, const bool two, const uint16_t *tab,
+                                            uint64_t *ring, const uint32_t lane) {
+    const uint32_t pa = 32u * k + lane, pb = pa + 32u;
+    const uintptr_t ba = reinterpret_cast<uintptr_t>(base);
+    const uint32_t a = (uint32_t)(ba & 3u) + pa;
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(ba & ~(uintptr_t)3) + (a >> 2);
+    const uint32_t sh = (a & 3u) * 8u;
+    uint32_t w[17];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) w[i] = __ldg(wp + i);
+#pragma unroll
+    for (int i = 9; i < 17; ++i) w[i] = two ? __ldg(wp + i) : 0u;
+    uint32_t S[16];                                                             // bytes pa .. pa+63 (pb = pa + 32)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) S[i] = __funnelshift_r(w[i], w[i + 1], sh);
+    const uint32_t ha = (S[0] * 2654435761u) >> 18, hb = (S[8] * 2654435761u) >> 18;   // :53
+    const uint32_t seena = *reinterpret_cast<const volatile uint16_t *>(tab + ha);     // the slots as they are right now
+    const uint32_t seenb = *reinterpret_cast<const volatile uint16_t *>(tab + hb);
+    const bool oka = seena != pa, okb = two && seenb != pb;                      // :62 with the 16-bit table (Tab16: 0 = position 0)
+    const uint32_t la = oka ? seena : pa, lb = okb ? seenb : pa;                // no candidate: read at an own address
+    const uint32_t csa = ((uint32_t)(ba & 15u) + la) & 15u, csb = ((uint32_t)(ba & 15u) + lb) & 15u;
+    const uint4 *cqa = reinterpret_cast<const uint4 *>(base + la - csa), *cqb = reinterpret_cast<const uint4 *>(base + lb - csb);
+    const uint4 qa0 = __ldg(cqa), qa1 = __ldg(cqa + 1), qa2 = __ldg(cqa + 2);
+    const uint4 qb0 = __ldg(cqb), qb1 = __ldg(cqb + 1), qb2 = __ldg(cqb + 2);
+    const uint32_t va = wide_verify(qa0, qa1, qa2, csa, S), vb = wide_verify(qb0, qb1, qb2, csb, S + 8);     // 0 or 4..32
+    uint32_t mla = oka ? va : 0u, mlb = okb ? vb : 0u;
+    if (__any_sync(FULL, mla == 32u || mlb == 32u)) {
+        // second stage for the positions whose 32 bytes all matched: bytes 32..63 (:147-150 continued)
+        if (mla == 32u) {
+            const uint4 q3 = __ldg(cqa + 3), q4 = __ldg(cqa + 4);
+            mla += two ? pw_count32(qa2, q3, q4, csa, S + 8) : 0u;               // (one window only: no bytes behind +32 loaded; stays 32,
+        }                                                                        //  fixed below)
+        if (mlb == 32u) {
+            uint32_t w2[9], S2[8];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) w2[i] = __ldg(wp + 16 + i);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) S2[i] = __funnelshift_r(w2[i], w2[i + 1], sh);
+            const uint4 q3 = __ldg(cqb + 3), q4 = __ldg(cqb + 4);
+            mlb += pw_count32(qb2, q3, q4, csb, S2);
+        }
+    }
+    if (!two && mla == 32u) {
+        // last window of the block, produced alone: its bytes 32..63 come from a direct load
+        uint32_t w2[9], S2[8];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w2[i] = __ldg(wp + 8 + i);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) S2[i] = __funnelshift_r(w2[i], w2[i + 1], sh);
+        const uint4 q3 = __ldg(cqa + 3), q4 = __ldg(cqa + 4);
+        mla += pw_count32(qa2, q3, q4, csa, S2);
+    }
+    const uint32_t loa = ha | (mla << 14) | (((k + 1u) & kPwGenMask) << 21);
+    pw_sts64(ring + (pa & (kPwRing - 1)), (uint64_t)loa | ((uint64_t)seena << 32));
+    if (two) {
+        const uint32_t lob = hb | (mlb << 14) | (((k + 2u) & kPwGenMask) << 21);
+        pw_sts64(ring + (pb & (kPwRing - 1)), (uint64_t)lob | ((uint64_t)seenb << 32));
+    }
+}
+
+// Producer j of kNP takes the window pairs (2j, 2j+1), (2j + 2 kNP, ...), ... -- skipping those the walker has left behind -- and
+// stays at most `lead` windows ahead of the walker's window.
 template <int kNP>
 __device__ __forceinline__ void pw_producer(const uint8_t *__restrict__ base, const uint32_t nwin, const uint32_t lead,
                                             const uint32_t j, const uint16_t *tab, uint64_t *ring, PwCtl *ctl, const uint32_t lane,
                                             const uint32_t full_ns) {
-    uint32_t k = j;
+    uint32_t k = 2u * j;
     for (;;) {
         const uint32_t wpos = ctl->w_pos;
         if (wpos & kPwDone) break;
         if (wpos & kPwSparse) { __nanosleep(256); continue; }
         const uint32_t wk = wpos >> 5;
-        if (k < wk) k = wk + ((j + (uint32_t)kNP - wk % (uint32_t)kNP) % (uint32_t)kNP);      // first window >= wk of this warp's class
+        while (k + 1u < wk) k += 2u * (uint32_t)kNP;
         if (k >= nwin) { __nanosleep(1024); continue; }
-        if (k >= wk + lead) { __nanosleep(full_ns); continue; }
-        pw_produce(base, k, tab, ring, lane);
-        k += (uint32_t)kNP;
+        if (k + 1u >= wk + lead) { __nanosleep(full_ns); continue; }
+        pw_produce2(base, k, k + 1u < nwin, tab, ring, lane);
+        k += 2u * (uint32_t)kNP;
     }
 }
 
@@ -149,19 +212,19 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
             if ((s ^ pub) >> 5) { pub = s; if (lane == 0) ctl->w_pos = s; }
             const uint32_t p = s + lane;
             const uint64_t *slot = ring + (p & (kPwRing - 1));
-            const uint32_t want = ((p >> 5) + 1u) & 0xFFFu;
+            const uint32_t want = ((p >> 5) + 1u) & kPwGenMask;
             uint64_t e;
             for (;;) {
                 e = pw_lds64(slot);
-                if (__all_sync(FULL, ((uint32_t)e >> 20) == want)) break;
+                if (__all_sync(FULL, ((uint32_t)e >> 21) == want)) break;
                 __nanosleep(32);
             }
             const uint32_t lo = (uint32_t)e, seen = (uint32_t)(e >> 32);
-            const uint32_t h = lo & 0x3FFFu, ml = (lo >> 14) & 63u;
+            const uint32_t h = lo & 0x3FFFu, ml = (lo >> 14) & 127u;
             const uint32_t cur = tab[h];                                       // :54 (state before this step)
             // reach: n = where the walk from this lane stands (>= 32: left the step; a pre-extension that hit its cap of 32
             // ends the walk at that position, n = 64), m = positions visited so far
-            uint32_t n = ml == 32u ? 64u : lane + (ml ? ml : 1u);
+            uint32_t n = ml == kPwCap ? 255u : lane + (ml ? ml : 1u);
             uint32_t m = 1u << lane;
 #pragma unroll
             for (int r = 0; r < 5; ++r) {
@@ -180,12 +243,12 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
             if (!bad) {
                 const uint32_t HM = PM & claim;                                // the matches, in order
                 const uint32_t nh = (uint32_t)__popc(HM);
-                if (((HM >> lane) & 1u) && ml != 32u) rec2[nrec + (uint32_t)__popc(HM & lt)] = rec_pack(p, ml, p - cur);
-                if (exitp == 64u) {
+                if (((HM >> lane) & 1u) && ml != kPwCap) rec2[nrec + (uint32_t)__popc(HM & lt)] = rec_pack(p, ml, p - cur);
+                if (exitp == 255u) {
                     // the walk ended at a match of 32 or more bytes (the last probed position): its real length (:147-150)
                     const uint32_t c = 31u - (uint32_t)__clz(PM);
                     const uint32_t pc = s + c, curc = __shfl_sync(FULL, cur, c);
-                    const uint32_t mlx = pw_extend(base, (int32_t)pc, (int32_t)curc, 32, matchLimit, lane);
+                    const uint32_t mlx = pw_extend(base, (int32_t)pc, (int32_t)curc, (int32_t)kPwCap, matchLimit, lane);
                     if (lane == 0) rec2[nrec + nh - 1u] = rec_pack(pc, mlx, pc - curc);
                     sIndex = (int32_t)(pc + mlx);
                     smc = 67u;
@@ -241,16 +304,16 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
             const bool valid = p < rlimit;
             if (pub != (uint32_t)sIndex) { pub = (uint32_t)sIndex; if (lane == 0) ctl->w_pos = pub; }
             const uint64_t *slot = ring + ((uint32_t)p & (kPwRing - 1));
-            const uint32_t want = (((uint32_t)p >> 5) + 1u) & 0xFFFu;
+            const uint32_t want = (((uint32_t)p >> 5) + 1u) & kPwGenMask;
             uint64_t e;
             for (;;) {
                 e = pw_lds64(slot);
-                const bool ready = !valid || (((uint32_t)e >> 20) == want);
+                const bool ready = !valid || (((uint32_t)e >> 21) == want);
                 if (__all_sync(FULL, ready)) break;
                 __nanosleep(20);
             }
             const uint32_t lo = (uint32_t)e, seen = (uint32_t)(e >> 32);
-            const uint32_t h = lo & 0x3FFFu, ml = (lo >> 14) & 63u;
+            const uint32_t h = lo & 0x3FFFu, ml = (lo >> 14) & 127u;
             const uint32_t cur = tab[h];                                       // :54 (state before this step)
             const uint32_t claim = __ballot_sync(FULL, valid && ml != 0u);
             const uint32_t f = claim ? (uint32_t)__ffs(claim) - 1u : 32u;
@@ -267,7 +330,7 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
                     const int32_t pf = sIndex + (int32_t)(skip_sum(smc + f) - bs);
                     const uint32_t curf = __shfl_sync(FULL, cur, f);
                     uint32_t mlf = __shfl_sync(FULL, ml, f);
-                    if (mlf == 32u) mlf = pw_extend(base, pf, (int32_t)curf, 32, matchLimit, lane);
+                    if (mlf == kPwCap) mlf = pw_extend(base, pf, (int32_t)curf, (int32_t)kPwCap, matchLimit, lane);
                     if (lane == 0) rec2[nrec] = rec_pack((uint32_t)pf, mlf, (uint32_t)pf - curf);
                     ++nrec;
                     sIndex = pf + (int32_t)mlf;
@@ -407,9 +470,9 @@ k_parse_pw(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off
         }
         pw_bar(bar, kTeam);
         const uint8_t *base = src + src_off[b];
-        // windows whose loads stay inside the block: position 32k+31 reads its own bytes up to +39 and, for a candidate right
-        // below it, 16-byte granules up to +47
-        const uint32_t nwin = len >= 80u ? (len - 79u) / 32u + 1u : 0u;
+        // windows whose loads stay inside the block: position 32k+31 reads its own bytes up to +71 and, for a candidate right
+        // below it, 16-byte granules up to +79
+        const uint32_t nwin = len >= 112u ? (len - 111u) / 32u + 1u : 0u;
         if (role == 0) {
             const uint32_t n = pw_walker(base, (int32_t)len, nwin, tab, ring, ctl, rec_base + (uint64_t)b * rec_stride, lane);
             if (lane == 0) { nrec_out[b] = n; ctl->w_pos = kPwDone; }

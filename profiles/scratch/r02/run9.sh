@@ -1,0 +1,15 @@
+set -x
+cd /root/repo
+timeout 600 python -m pytest tests/test_gpu_blocks.py -x -q -m gpu > gpurun_out/r02_pw_tests.txt 2>&1
+tail -3 gpurun_out/r02_pw_tests.txt
+grep -q passed gpurun_out/r02_pw_tests.txt || exit 1
+rm -f gpurun_out/r02_pw_kbench4.txt
+for cfg in "DLZ4_PW=2 DLZ4_PW_LEAD=6 DLZ4_PW_SLEEP=200" "DLZ4_PW=2 DLZ4_PW_LEAD=5 DLZ4_PW_SLEEP=200" "DLZ4_PW=2 DLZ4_PW_LEAD=8 DLZ4_PW_SLEEP=200" "DLZ4_PW=3 DLZ4_PW_LEAD=6 DLZ4_PW_SLEEP=200" ; do
+  echo "== $cfg" >> gpurun_out/r02_pw_kbench4.txt
+  env $cfg timeout 300 python divortio-lz4_b200/tools/kbench.py 1024 65536 log,mixed,zero,rand >> gpurun_out/r02_pw_kbench4.txt 2>&1
+done
+cat gpurun_out/r02_pw_kbench4.txt
+export DLZ4_PW=2 DLZ4_PW_LEAD=6 DLZ4_PW_SLEEP=200
+python divortio-lz4_b200/tools/prof_one.py log 1024 > gpurun_out/r02_prof_plain.log 2>&1 &&
+ncu --set full --import-source on --clock-control none -k regex:k_parse_pw -s 1 -c 1 -o gpurun_out/r02_pw4_log1024 -f python divortio-lz4_b200/tools/prof_one.py log 1024 > gpurun_out/r02_ncu_pw.log 2>&1
+tail -3 gpurun_out/r02_ncu_pw.log
