@@ -47,9 +47,10 @@ struct dlz4_ctx {
     int32_t *d_table = nullptr;         // int32[16384] scratch table
     int wide = 1;                       // shared-memory-table chains use the 64-position window (dlz4_wide.cuh); 0: A/B runs
     int split = 1;                      // fresh blocks <= 64 KiB: match finder (k_parse_pw / k_parse_fresh16) + encoder (k_encode_blocks); 0: A/B runs
-    int pw = 3;                         // producers per chain of the match finder (k_parse_pw<2|3>); 0: one warp per chain (k_parse_fresh16)
-    int pw_sleep = 400;                 // ns a producer sleeps when its ring is full
-    int pw_lead = 6;                    // windows a producer may run ahead of the walker (3..8)
+    int pw = 2;                         // producers per chain of the match finder (k_parse_pw<2|3>); 0: one warp per chain (k_parse_fresh16)
+    int pw_fused = 0;                   // 1: the encoder is a fourth kind of warp inside k_parse_pw (measured slower: it delays the next block)
+    int pw_sleep = 200;                 // ns a producer sleeps when its ring is full
+    int pw_lead = 7;                    // windows a producer may run ahead of the walker (3..8)
     Buf rec;                            // match records of the split path: kGtabRegions regions (one per work-queue counter)
     uint32_t *d_nrec = nullptr;         // matches per block (split path), kGtabRegions regions of kMaxSplitBlocks
     int hybrid = 1;                     // 64 KiB fresh blocks: hybrid kernel (L2-resident tables) instead of the 7-warp one
@@ -168,13 +169,24 @@ int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, 
         if (ctx->pw) {
             // teams spread over the SMs first (a small batch uses one chain per SM), six teams per CTA at most
             const int grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count);
+            const uint32_t lead = (uint32_t)ctx->pw_lead, ns = (uint32_t)ctx->pw_sleep;
+            const size_t sm = (size_t)kPwChains * kPwChainBytes;
+            if (ctx->pw_fused) {
+                // walker, producers and encoder of a chain in one kernel
+                if (ctx->pw == 2)
+                    k_parse_pw<2, true><<<grid, kPwChains * 4 * 32, sm, st>>>(src, src_off, src_len, n, recs, rstride, nrec, counter, lead, ns, dst, dst_off, comp_len);
+                else
+                    k_parse_pw<3, true><<<grid, kPwChains * 5 * 32, sm, st>>>(src, src_off, src_len, n, recs, rstride, nrec, counter, lead, ns, dst, dst_off, comp_len);
+                ctx->launches++;
+                CK(cudaGetLastError());
+                return DLZ4_OK;
+            }
             if (ctx->pw == 2)
-                k_parse_pw<2><<<grid, kPwChains * 3 * 32, kPwChains * kPwChainBytes, st>>>(src, src_off, src_len, n, recs, rstride, nrec,
-                                                                                         counter, (uint32_t)ctx->pw_lead, (uint32_t)ctx->pw_sleep);
+                k_parse_pw<2, false><<<grid, kPwChains * 3 * 32, sm, st>>>(src, src_off, src_len, n, recs, rstride, nrec, counter, lead, ns, nullptr, nullptr, nullptr);
             else
-                k_parse_pw<3><<<grid, kPwChains * 4 * 32, kPwChains * kPwChainBytes, st>>>(src, src_off, src_len, n, recs, rstride, nrec,
-                                                                                         counter, (uint32_t)ctx->pw_lead, (uint32_t)ctx->pw_sleep);
-        } else {
+                k_parse_pw<3, false><<<grid, kPwChains * 4 * 32, sm, st>>>(src, src_off, src_len, n, recs, rstride, nrec, counter, lead, ns, nullptr, nullptr, nullptr);
+        } else
+        {
             const int grid = (int)std::min<uint64_t>((n + kWarpsFresh16 - 1) / kWarpsFresh16, (uint64_t)ctx->sm_count);
             k_parse_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * kHashEntries * 2, st>>>(
                 src, src_off, src_len, n, recs, rstride, nrec, counter);
@@ -630,6 +642,7 @@ int dlz4_init(int device, dlz4_ctx **out) {
     if (const char *e = getenv("DLZ4_WIDE")) ctx->wide = atoi(e) != 0;
     if (const char *e = getenv("DLZ4_SPLIT")) ctx->split = atoi(e) != 0;
     if (const char *e = getenv("DLZ4_PW")) ctx->pw = std::max(0, std::min(3, atoi(e)));
+    if (const char *e = getenv("DLZ4_PW_FUSED")) ctx->pw_fused = atoi(e) != 0;
     if (const char *e = getenv("DLZ4_PW_SLEEP")) ctx->pw_sleep = std::max(0, atoi(e));
     if (const char *e = getenv("DLZ4_PW_LEAD")) ctx->pw_lead = std::max(3, std::min(8, atoi(e)));
     if (const char *e = getenv("DLZ4_HYBRID")) ctx->hybrid = atoi(e) != 0;      // 0: the 7-warp shared-memory-only kernel (A/B runs)
@@ -638,8 +651,10 @@ int dlz4_init(int device, dlz4_ctx **out) {
     CK(cudaMalloc(&ctx->d_gtabs, (size_t)kGtabRegions * ctx->hy_grid * kHyGlWarps * kHashEntries * 2));
     CK(cudaMalloc(&ctx->d_nrec, (size_t)kGtabRegions * kMaxSplitBlocks * 4));
     CK(cudaFuncSetAttribute(k_parse_fresh16<kWarpsFresh16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpsFresh16 * kHashEntries * 2));
-    CK(cudaFuncSetAttribute(k_parse_pw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwChains * kPwChainBytes));
-    CK(cudaFuncSetAttribute(k_parse_pw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwChains * kPwChainBytes));
+    CK(cudaFuncSetAttribute(k_parse_pw<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwChains * kPwChainBytes));
+    CK(cudaFuncSetAttribute(k_parse_pw<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwChains * kPwChainBytes));
+    CK(cudaFuncSetAttribute(k_parse_pw<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwChains * kPwChainBytes));
+    CK(cudaFuncSetAttribute(k_parse_pw<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwChains * kPwChainBytes));
     CK(cudaFuncSetAttribute(k_compress_fresh16h, cudaFuncAttributeMaxDynamicSharedMemorySize, kHySmemBytes));
     CK(cudaFuncSetAttribute(k_compress_overlay, cudaFuncAttributeMaxDynamicSharedMemorySize, kHySmemBytes));
     CK(cudaFuncSetAttribute(k_compress_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, kSegSmemBytes));

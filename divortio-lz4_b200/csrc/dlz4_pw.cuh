@@ -42,6 +42,7 @@ constexpr uint32_t kPwDone = 0x80000000u, kPwSparse = 0x40000000u;
 struct PwCtl {                                // one per chain, in shared memory
     volatile uint32_t w_pos;                  // walker's position (block-relative) | kPwSparse | kPwDone
     volatile uint32_t block;                  // block index of the team, 0xFFFFFFFF: no more work
+    volatile uint32_t nrec_pub;               // records the walker has written so far | kPwDone once the block is parsed (encoder warp)
 };
 
 __device__ __forceinline__ void pw_bar(uint32_t id, uint32_t nthreads) {
@@ -57,22 +58,69 @@ __device__ __forceinline__ void pw_sts64(uint64_t *p, uint64_t v) {
 }
 
 // common prefix of base[s0 + eb ..] and base[m0 + eb ..] from byte eb on, bounded by matchLimit (:147-150); all lanes.
+// First 128 bytes four at a time per lane (most matches end there); a match that is still running is compared 16 bytes
+// per lane from a 16-byte-aligned source address on, 2 KiB per memory round trip (zero runs, periodic data).
 __device__ __forceinline__ uint32_t pw_extend(const uint8_t *__restrict__ base, int32_t s0, int32_t m0, int32_t eb,
                                               int32_t matchLimit, uint32_t lane) {
-    for (;; eb += 256) {
-        const int32_t q0 = s0 + eb + 4 * (int32_t)lane, q1 = q0 + 128;
-        int32_t nv0 = matchLimit - q0, nv1 = matchLimit - q1;
-        nv0 = nv0 > 4 ? 4 : nv0; nv1 = nv1 > 4 ? 4 : nv1;
-        int32_t eq0 = 0, eq1 = 0;
-        uint32_t x0 = 0, x1 = 0;
-        if (nv0 > 0) x0 = ld32u(base + q0) ^ ld32u(base + (m0 - s0) + q0);
-        if (nv1 > 0) x1 = ld32u(base + q1) ^ ld32u(base + (m0 - s0) + q1);
-        if (nv0 > 0) { eq0 = x0 ? ((__ffs(x0) - 1) >> 3) : 4; eq0 = eq0 < nv0 ? eq0 : nv0; }
-        if (nv1 > 0) { eq1 = x1 ? ((__ffs(x1) - 1) >> 3) : 4; eq1 = eq1 < nv1 ? eq1 : nv1; }
-        const uint32_t stop0 = __ballot_sync(FULL, eq0 < 4);
-        if (stop0) { const int l = __ffs(stop0) - 1; return (uint32_t)(eb + 4 * l + __shfl_sync(FULL, eq0, l)); }
-        const uint32_t stop1 = __ballot_sync(FULL, eq1 < 4);
-        if (stop1) { const int l = __ffs(stop1) - 1; return (uint32_t)(eb + 128 + 4 * l + __shfl_sync(FULL, eq1, l)); }
+    const int32_t back = s0 - m0;
+    auto round4 = [&](int32_t e0, uint32_t &res) -> bool {                     // 128 bytes from e0; true: the match ends in them
+        const int32_t q = s0 + e0 + 4 * (int32_t)lane;
+        int32_t nv = matchLimit - q;
+        nv = nv > 4 ? 4 : nv;
+        int32_t eq = 0;
+        if (nv > 0) {
+            const uint32_t x = ld32u(base + q) ^ ld32u(base + q - back);
+            const int32_t e = x ? ((__ffs(x) - 1) >> 3) : 4;
+            eq = e < nv ? e : nv;
+        }
+        const uint32_t stop = __ballot_sync(FULL, eq < 4);
+        if (!stop) return false;
+        const int l = __ffs(stop) - 1;
+        res = (uint32_t)(e0 + 4 * l + __shfl_sync(FULL, eq, l));
+        return true;
+    };
+    uint32_t res = 0;
+    if (round4(eb, res)) return res;
+    eb += 128;
+    // up to the next 16-byte boundary of the source address (at most one more round of 128 covers it)
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(base + s0 + eb) & 15u);
+    if (mis) {
+        if (round4(eb, res)) return res;
+        eb += 128 - (int32_t)mis;                                                // bytes [eb, eb + 128) are equal; resume aligned inside them
+        eb -= 112;                                                               // (eb + 128 - mis) - 112: first aligned address behind the old eb
+    }
+    // aligned phase: lane compares bytes [q, q+16), q = s0 + eb + 16 lane (+ 512 u); candidate bytes from two aligned granules
+    const uint8_t *cb = base + s0 + eb - back;
+    const uint32_t cmis = (uint32_t)(reinterpret_cast<uintptr_t>(cb) & 15u);
+    const uint32_t wsel = cmis >> 2, bsh = (cmis & 3u) * 8u;
+    for (;; eb += 2048) {
+        uint32_t eqb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int32_t q = s0 + eb + 512 * u + 16 * (int32_t)lane;
+            int32_t nv = matchLimit - q;
+            nv = nv > 16 ? 16 : nv;
+            eqb[u] = 0;
+            if (nv > 0) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4 *>(base + q));
+                const uint4 *cp = reinterpret_cast<const uint4 *>(base + q - back - (int32_t)cmis);
+                const uint4 c0 = __ldg(cp), c1 = __ldg(cp + 1);
+                uint32_t v[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                uint32_t t[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) t[i] = wsel == 0 ? v[i] : wsel == 1 ? v[i + 1] : wsel == 2 ? v[i + 2] : v[i + 3];
+                const uint32_t x0 = a.x ^ __funnelshift_r(t[0], t[1], bsh), x1 = a.y ^ __funnelshift_r(t[1], t[2], bsh);
+                const uint32_t x2 = a.z ^ __funnelshift_r(t[2], t[3], bsh), x3 = a.w ^ __funnelshift_r(t[3], t[4], bsh);
+                uint32_t e = x0 ? ((uint32_t)(__ffs(x0) - 1) >> 3) : x1 ? 4u + ((uint32_t)(__ffs(x1) - 1) >> 3)
+                           : x2 ? 8u + ((uint32_t)(__ffs(x2) - 1) >> 3) : x3 ? 12u + ((uint32_t)(__ffs(x3) - 1) >> 3) : 16u;
+                eqb[u] = e < (uint32_t)nv ? e : (uint32_t)nv;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t stop = __ballot_sync(FULL, eqb[u] < 16u);
+            if (stop) { const int l = __ffs(stop) - 1; return (uint32_t)(eb + 512 * u + 16 * l) + __shfl_sync(FULL, eqb[u], l); }
+        }
     }
 }
 
@@ -186,8 +234,10 @@ __device__ __forceinline__ void pw_producer(const uint8_t *__restrict__ base, co
 
 // ---- walker: the serial loop.  Returns the number of records written.
 __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, const int32_t len, const uint32_t nwin, uint16_t *tab,
-                                              const uint64_t *ring, PwCtl *ctl, uint64_t *__restrict__ rec, const uint32_t lane) {
+                                              const uint64_t *ring, PwCtl *ctl, uint64_t *__restrict__ rec, const uint32_t lane,
+                                              const bool publish_records) {
     const uint32_t lt = (1u << lane) - 1u;
+    uint32_t rpub = 0;                                                          // what ctl->nrec_pub holds
     const int32_t sEnd = len;
     const int32_t mflimit = sEnd - 12;                                          // blockCompress.js:34
     const int32_t matchLimit = sEnd - 5;                                        // :35
@@ -202,6 +252,13 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
     uint2 *const rec2 = reinterpret_cast<uint2 *>(rec);
 
     while (sIndex < mflimit) {                                                  // :48
+        if (publish_records && ((nrec ^ rpub) >> 5)) {
+            // another 32 records: hand them to the encoder warp (the records are plain global stores of several lanes)
+            __threadfence_block();
+            __syncwarp();
+            rpub = nrec;
+            if (lane == 0) ctl->nrec_pub = nrec;
+        }
         if (smc <= 96u && sIndex + 32 <= rlimit) {
             // ---- path step: while searchMatchCount stays below 128 the schedule steps by 1 (:66-67), so the parse inside the
             //      next 32 positions is a walk over the producers' match lengths: from a hit to the position behind its match,
@@ -425,18 +482,89 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
     return nrec;
 }
 
-// Fresh independent blocks <= 64 KiB: the match finder as producer/walker teams.  Records as k_parse_fresh16.
-// CTA = kPwChains teams of (1 + kNP) warps; warp t of a team: 0 = walker, 1.. = producers.
-template <int kNP>
-__global__ void __launch_bounds__(kPwChains * (1 + kNP) * 32, 1)
+// ---- encoder warp: the block's bytes from the walker's records, 32 sequences per step, while the parse is still running
+//      (blockCompress.js:75-174 per match, :179-230 for the final literals; the loop body of k_encode_blocks)
+__device__ __forceinline__ uint32_t pw_encoder(const uint8_t *__restrict__ in, const uint32_t len, const uint64_t *rec, PwCtl *ctl,
+                                               uint8_t *__restrict__ out, const uint32_t lane) {
+    uint32_t D = 0, prev_end = 0, r0 = 0;                // output offset; end of the previous match (= mAnchor, :174); next record
+    for (;;) {
+        uint32_t pub = 0;
+        if (lane == 0) pub = ctl->nrec_pub;
+        pub = __shfl_sync(FULL, pub, 0);
+        uint32_t cnt = (pub & ~kPwDone) - r0;
+        if (cnt < 32u && !(pub & kPwDone)) { __nanosleep(512); continue; }
+        if (cnt == 0u) break;
+        cnt = cnt < 32u ? cnt : 32u;
+        const bool have = lane < cnt;
+        const uint2 rc = have ? __ldcg(reinterpret_cast<const uint2 *>(rec) + r0 + lane) : make_uint2(0u, 0u);
+        const uint32_t pos = rc.x & 0xFFFFu, ml = rc.y, offset = rc.x >> 16;
+        const uint32_t end = pos + ml;
+        uint32_t pe = __shfl_up_sync(FULL, end, 1);
+        if (lane == 0) pe = prev_end;
+        const uint32_t lit = have ? pos - pe : 0u;                                   // :74 litLen
+        const uint32_t code = ml - 4u;                                               // :160
+        const uint32_t litx = lit >= 15u ? 1u + (lit - 15u) / 255u : 0u;
+        const uint32_t mlx = have && code >= 15u ? 1u + (code - 15u) / 255u : 0u;
+        const uint32_t size = have ? 3u + litx + lit + mlx : 0u;
+        uint32_t incl = size;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+        uint32_t d = D + incl - size;                        // this sequence's token
+        if (have) {
+            out[d++] = (uint8_t)(((lit < 15u ? lit : 15u) << 4) | (code < 15u ? code : 15u));   // :78-90, :161-170
+            if (lit >= 15u) {
+                uint32_t rest = lit - 15u;
+                while (rest >= 255u) { out[d++] = 255; rest -= 255u; }
+                out[d++] = (uint8_t)rest;
+            }
+        }
+        // literals (:92-140): short runs by their own lane, long ones by the whole warp
+        const uint32_t lits_at = d;
+        const bool longrun = have && lit > 24u;
+        if (have && !longrun) {
+            const uint8_t *sp = in + pe;
+            for (uint32_t k = 0; k < lit; ++k) out[d + k] = sp[k];
+        }
+        for (uint32_t mm = __ballot_sync(FULL, longrun); mm; mm &= mm - 1u) {
+            const int l = __ffs(mm) - 1;
+            const uint32_t o_ = __shfl_sync(FULL, lits_at, l), p_ = __shfl_sync(FULL, pe, l), n_ = __shfl_sync(FULL, lit, l);
+            warp_copy(out + o_, in + p_, n_, lane);
+        }
+        if (have) {
+            d += lit;
+            out[d] = (uint8_t)offset;                        // :156-157
+            out[d + 1] = (uint8_t)(offset >> 8);
+            d += 2;
+            if (code >= 15u) {
+                uint32_t rest = code - 15u;
+                while (rest >= 255u) { out[d++] = 255; rest -= 255u; }
+                out[d] = (uint8_t)rest;
+            }
+        }
+        D += __shfl_sync(FULL, incl, 31);
+        prev_end = __shfl_sync(FULL, end, cnt - 1u);
+        r0 += cnt;
+    }
+    __syncwarp();
+    uint8_t *e = emit_literals(out + D, SrcFlat{in}, (int32_t)prev_end, len - prev_end, 0u, lane);       // :179-230
+    return (uint32_t)(e - out);
+}
+
+// Fresh independent blocks <= 64 KiB as producer/walker teams.  CTA = kPwChains teams; warp t of a team: 0 = walker,
+// 1..kNP = producers, and with kEncode one more, the encoder (then the kernel is the whole compressor and writes dst / comp_len;
+// without it only the match records and their number, for k_encode_blocks).
+template <int kNP, bool kEncode>
+__global__ void __launch_bounds__(kPwChains * (1 + kNP + (kEncode ? 1 : 0)) * 32, 1)
 k_parse_pw(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ src_len,
            uint32_t nblocks, uint64_t *__restrict__ rec_base, uint64_t rec_stride /* records per block */,
            uint32_t *__restrict__ nrec_out, uint32_t *counter, uint32_t lead,
-           uint32_t full_ns /* a producer with a full ring sleeps this long: the ring buffers several windows */) {
+           uint32_t full_ns /* a producer with a full ring sleeps this long: the ring buffers several windows */,
+           uint8_t *__restrict__ dst, const uint64_t *__restrict__ dst_off, uint32_t *__restrict__ comp_len) {
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr uint32_t kTeam = (1 + kNP) * 32;
+    constexpr uint32_t kRoles = 1 + kNP + (kEncode ? 1 : 0);
+    constexpr uint32_t kTeam = kRoles * 32;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    const uint32_t chain = warp / (1 + kNP), role = warp % (1 + kNP);
+    const uint32_t chain = warp / kRoles, role = warp % kRoles;
     const uint32_t tid = threadIdx.x - chain * kTeam;                          // thread index inside the team
     uint8_t *const cb = smem + (size_t)chain * kPwChainBytes;
     uint16_t *const tab = reinterpret_cast<uint16_t *>(cb);
@@ -454,6 +582,7 @@ k_parse_pw(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off
             if (have_first) b = first; else b = qbase + atomicAdd(counter, 1u);
             ctl->block = b < nblocks ? b : 0xFFFFFFFFu;
             ctl->w_pos = 0u;
+            ctl->nrec_pub = 0u;
         }
         have_first = false;
         pw_bar(bar, kTeam);
@@ -461,7 +590,7 @@ k_parse_pw(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off
         if (b == 0xFFFFFFFFu) return;
         const uint32_t len = src_len[b];
         if (len > 65536u) {
-            if (role == 0 && lane == 0) nrec_out[b] = 0xFFFFFFFFu;
+            if (role == 0 && lane == 0) { if (kEncode) comp_len[b] = 0xFFFFFFFFu; else nrec_out[b] = 0xFFFFFFFFu; }
             continue;
         }
         {   // empty table (bufferCompress.js:182 / :235), invalid ring
@@ -470,14 +599,22 @@ k_parse_pw(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off
         }
         pw_bar(bar, kTeam);
         const uint8_t *base = src + src_off[b];
+        uint64_t *const rec = rec_base + (uint64_t)b * rec_stride;
         // windows whose loads stay inside the block: position 32k+31 reads its own bytes up to +71 and, for a candidate right
         // below it, 16-byte granules up to +79
         const uint32_t nwin = len >= 112u ? (len - 111u) / 32u + 1u : 0u;
         if (role == 0) {
-            const uint32_t n = pw_walker(base, (int32_t)len, nwin, tab, ring, ctl, rec_base + (uint64_t)b * rec_stride, lane);
-            if (lane == 0) { nrec_out[b] = n; ctl->w_pos = kPwDone; }
-        } else {
+            const uint32_t n = pw_walker(base, (int32_t)len, nwin, tab, ring, ctl, rec, lane, kEncode);
+            if (kEncode) { __threadfence_block(); __syncwarp(); }
+            if (lane == 0) {
+                if (kEncode) ctl->nrec_pub = n | kPwDone; else nrec_out[b] = n;
+                ctl->w_pos = kPwDone;
+            }
+        } else if (role <= (uint32_t)kNP) {
             pw_producer<kNP>(base, nwin, lead, role - 1u, tab, ring, ctl, lane, full_ns);
+        } else {
+            const uint32_t c = pw_encoder(base, len, rec, ctl, dst + dst_off[b], lane);
+            if (lane == 0) comp_len[b] = c;
         }
     }
 }

@@ -1,0 +1,11 @@
+set -x
+cd /root/repo
+timeout 600 python -m pytest tests/test_gpu_blocks.py -x -q -m gpu > gpurun_out/r02_pw_tests.txt 2>&1
+tail -3 gpurun_out/r02_pw_tests.txt
+grep -q passed gpurun_out/r02_pw_tests.txt || exit 1
+rm -f gpurun_out/r02_pw_kbench6.txt
+for cfg in "DLZ4_PW=2 DLZ4_PW_LEAD=8" "DLZ4_PW=2 DLZ4_PW_LEAD=7" "DLZ4_PW=2 DLZ4_PW_LEAD=6" "DLZ4_SPLIT=0"; do
+  echo "== $cfg" >> gpurun_out/r02_pw_kbench6.txt
+  env $cfg timeout 300 python divortio-lz4_b200/tools/kbench.py 1024 65536 log,mixed,zero,rand,bench >> gpurun_out/r02_pw_kbench6.txt 2>&1
+done
+cat gpurun_out/r02_pw_kbench6.txt
