@@ -85,6 +85,7 @@ def lib():
         "dlz4_last_error": (C.c_char_p, [vp]),
         "dlz4_launch_count": (u64, [vp]),
         "dlz4_last_kernel_ms": (C.c_float, [vp]),
+        "dlz4_kernel_probe": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "dlz4_segment_stats": (None, [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "dlz4_pinned_alloc": (vp, [u64]),
         "dlz4_pinned_free": (None, [vp]),
@@ -129,7 +130,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = [
-    "dlz4_init", "dlz4_shutdown", "dlz4_strerror", "dlz4_last_error", "dlz4_launch_count", "dlz4_last_kernel_ms", "dlz4_segment_stats",
+    "dlz4_init", "dlz4_shutdown", "dlz4_strerror", "dlz4_last_error", "dlz4_launch_count", "dlz4_last_kernel_ms", "dlz4_kernel_probe", "dlz4_segment_stats",
     "dlz4_pinned_alloc", "dlz4_pinned_free", "dlz4_host_register", "dlz4_host_unregister", "dlz4_compress_bound", "dlz4_frame_bound", "dlz4_shard_range",
     "dlz4_compress_blocks_dev", "dlz4_compress_blocks", "dlz4_decompress_blocks_dev", "dlz4_decompress_blocks",
     "dlz4_compress_block", "dlz4_decompress_block", "dlz4_xxh32_batch_dev", "dlz4_xxh32_stream_dev", "dlz4_xxh32",
@@ -206,6 +207,13 @@ class Context(object):
     @property
     def last_kernel_ms(self):
         return float(lib().dlz4_last_kernel_ms(self._h))
+
+    def kernel_probe(self, enable=True, read=False):
+        """Measurement aid (dlz4_kernel_probe): time the match finder and the encoder of fresh-block batches separately.
+        read=True returns (finder_ms, encoder_ms) of the most recent probed batch."""
+        a, b = C.c_float(0), C.c_float(0)
+        self.check(lib().dlz4_kernel_probe(self._h, int(bool(enable)), C.byref(a) if read else None, C.byref(b) if read else None))
+        return (a.value, b.value) if read else None
 
     @property
     def segment_stats(self):

@@ -50,7 +50,7 @@ struct dlz4_ctx {
     int pw = 2;                         // producers per chain of the match finder (k_parse_pw<2|3>); 0: one warp per chain (k_parse_fresh16)
     int pw_fused = 0;                   // 1: the encoder is a fourth kind of warp inside k_parse_pw (measured slower: it delays the next block)
     int pw_sleep = 200;                 // ns a producer sleeps when its ring is full
-    int pw_lead = 7;                    // windows a producer may run ahead of the walker (3..8)
+    int pw_lead = 7;                    // windows a producer may run ahead of the walker (3..kPwWin - 1)
     Buf rec;                            // match records of the split path: kGtabRegions regions (one per work-queue counter)
     uint32_t *d_nrec = nullptr;         // matches per block (split path), kGtabRegions regions of kMaxSplitBlocks
     int hybrid = 1;                     // 64 KiB fresh blocks: hybrid kernel (L2-resident tables) instead of the 7-warp one
@@ -65,6 +65,8 @@ struct dlz4_ctx {
     uint32_t seg_jobs = 0, seg_reruns = 0, seg_rounds = 0;   // last segment-parallel call: segments, re-run segments, rounds
     uint64_t launches = 0;
     float last_ms = 0.f;
+    int probe = 0;                      // dlz4_kernel_probe: time the match finder and the encoder of the next batch separately
+    cudaEvent_t evq[3] = {};            // before the match finder, between the two kernels, behind the encoder
     // what the last frame-body / frame-range call left resident on the device (sharded frames): the rank's input
     // slice, its packed frame body, the decoded bytes of its block range -- read by dlz4_frame_body_fetch and by the
     // content-checksum relay dlz4_xxh32_update_resident
@@ -166,6 +168,7 @@ int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, 
         const size_t per_region = ((ctx->rec.cap - 256) / kGtabRegions) & ~(size_t)255;
         uint64_t *recs = (uint64_t *)((uint8_t *)ctx->rec.p + region * per_region);
         uint32_t *nrec = ctx->d_nrec + region * (size_t)kMaxSplitBlocks;
+        if (ctx->probe) CK(cudaEventRecord(ctx->evq[0], st));
         if (ctx->pw) {
             // teams spread over the SMs first (a small batch uses one chain per SM), six teams per CTA at most
             const int grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count);
@@ -191,10 +194,12 @@ int launch_compress(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, 
             k_parse_fresh16<kWarpsFresh16><<<grid, kWarpsFresh16 * 32, kWarpsFresh16 * kHashEntries * 2, st>>>(
                 src, src_off, src_len, n, recs, rstride, nrec, counter);
         }
+        if (ctx->probe) CK(cudaEventRecord(ctx->evq[1], st));
         CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
         const int egrid = (int)std::min<uint64_t>((n + kWarpsDecode - 1) / kWarpsDecode, (uint64_t)ctx->sm_count * 8);
         k_encode_blocks<kWarpsDecode><<<egrid, kWarpsDecode * 32, 0, st>>>(src, src_off, src_len, n, recs, rstride, nrec, dst, dst_off,
                                                                             comp_len, counter);
+        if (ctx->probe) CK(cudaEventRecord(ctx->evq[2], st));
         ctx->launches++;
     } else if (max_len <= 65536 && prefix_len == 0 && init_table == nullptr && ctx->hybrid) {
         // one table region per work-queue counter: kernels of different pipeline lanes run concurrently
@@ -620,6 +625,7 @@ int dlz4_init(int device, dlz4_ctx **out) {
     for (cudaEvent_t &e : ctx->evp) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaEventCreate(&ctx->ev0));
     CK(cudaEventCreate(&ctx->ev1));
+    for (cudaEvent_t &e : ctx->evq) CK(cudaEventCreate(&e));
     CK(cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     for (cudaStream_t &l : ctx->lanes) CK(cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking));
@@ -644,7 +650,7 @@ int dlz4_init(int device, dlz4_ctx **out) {
     if (const char *e = getenv("DLZ4_PW")) ctx->pw = std::max(0, std::min(3, atoi(e)));
     if (const char *e = getenv("DLZ4_PW_FUSED")) ctx->pw_fused = atoi(e) != 0;
     if (const char *e = getenv("DLZ4_PW_SLEEP")) ctx->pw_sleep = std::max(0, atoi(e));
-    if (const char *e = getenv("DLZ4_PW_LEAD")) ctx->pw_lead = std::max(3, std::min(8, atoi(e)));
+    if (const char *e = getenv("DLZ4_PW_LEAD")) ctx->pw_lead = std::max(3, std::min(kPwWin - 1, atoi(e)));
     if (const char *e = getenv("DLZ4_HYBRID")) ctx->hybrid = atoi(e) != 0;      // 0: the 7-warp shared-memory-only kernel (A/B runs)
     ctx->hy_grid = ctx->sm_count * kHyCtasPerSm;
     if (const char *e = getenv("DLZ4_HY_ACTIVE")) ctx->hy_active = std::max(0, std::min(kHyWarps, atoi(e)));
@@ -683,6 +689,7 @@ void dlz4_shutdown(dlz4_ctx *ctx) {
     if (ctx->rec.p) cudaFree(ctx->rec.p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->evq) if (e) cudaEventDestroy(e);
     if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (cudaEvent_t e : ctx->evp) if (e) cudaEventDestroy(e);
@@ -716,6 +723,18 @@ const char *dlz4_strerror(int status) {
 const char *dlz4_last_error(const dlz4_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 uint64_t dlz4_launch_count(const dlz4_ctx *ctx) { return ctx ? ctx->launches : 0; }
 float dlz4_last_kernel_ms(const dlz4_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
+int dlz4_kernel_probe(dlz4_ctx *ctx, int enable, float *finder_ms, float *encoder_ms) {
+    if (!ctx) return DLZ4_E_INVALID_ARG;
+    if (finder_ms || encoder_ms) {
+        // the most recent probed batch of fresh blocks <= 64 KiB (match finder k_parse_pw, then encoder k_encode_blocks)
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaEventSynchronize(ctx->evq[2]));
+        if (finder_ms) CK(cudaEventElapsedTime(finder_ms, ctx->evq[0], ctx->evq[1]));
+        if (encoder_ms) CK(cudaEventElapsedTime(encoder_ms, ctx->evq[1], ctx->evq[2]));
+    }
+    ctx->probe = enable != 0;
+    return DLZ4_OK;
+}
 void dlz4_segment_stats(const dlz4_ctx *ctx, uint32_t *segments, uint32_t *reruns, uint32_t *rounds) {
     if (segments) *segments = ctx ? ctx->seg_jobs : 0;
     if (reruns) *reruns = ctx ? ctx->seg_reruns : 0;

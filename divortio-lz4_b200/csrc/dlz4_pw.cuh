@@ -32,12 +32,15 @@
 
 namespace dlz4 {
 
-constexpr int kPwChains = 6;                  // chains (teams) per CTA: 6 x (32 KiB table + 2 KiB ring) of 227 KiB
-constexpr int kPwRing = 256;                  // ring entries (positions) per chain: 8 windows
+constexpr int kPwChains = 6;                  // chains (teams) per CTA: 6 x (32 KiB table + 5.25 KiB ring) of 227 KiB
+constexpr int kPwWin = 14;                    // windows of 32 positions in a chain's ring (what fits beside six tables)
+constexpr int kPwRingBytes = kPwWin * 32 * 12; // a window's entries: three arrays of 32 words (x, y, z below)
 constexpr int kPwCtl = 64;                    // control bytes per chain
-constexpr int kPwChainBytes = kHashEntries * 2 + kPwRing * 8 + kPwCtl;
+constexpr int kPwChainBytes = kHashEntries * 2 + kPwRingBytes + kPwCtl;
 constexpr uint32_t kPwRingSmc = 160u;         // the walker uses the ring while searchMatchCount <= this (steps of 1 and 2)
 constexpr uint32_t kPwDone = 0x80000000u, kPwSparse = 0x40000000u;
+constexpr bool kPwPrefetch = true;            // producers prefetch the second stage's lines and the next window pair's source lines
+constexpr uint32_t kPwCap = 64u;              // producers pre-extend a match to this many bytes; the walker continues a longer one
 
 struct PwCtl {                                // one per chain, in shared memory
     volatile uint32_t w_pos;                  // walker's position (block-relative) | kPwSparse | kPwDone
@@ -48,13 +51,35 @@ struct PwCtl {                                // one per chain, in shared memory
 __device__ __forceinline__ void pw_bar(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ uint64_t pw_lds64(const uint64_t *p) {
-    uint64_t v;
-    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+__device__ __forceinline__ uint32_t pw_lds(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
     return v;
 }
-__device__ __forceinline__ void pw_sts64(uint64_t *p, uint64_t v) {
-    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "l"(v) : "memory");
+__device__ __forceinline__ void pw_sts(uint32_t *p, const uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void pw_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// ring slot of position p: the words x, y, z of its entry are at slot[0], slot[32], slot[64]
+__device__ __forceinline__ uint32_t pw_slot(const uint32_t p) {
+    const uint32_t w = p >> 5;                                                  // < 2048
+    const uint32_t ws = w - (uint32_t)kPwWin * ((w * 74899u) >> 20);            // w mod 14
+    return ws * 96u + (p & 31u);
+}
+// The walk of the serial loop through one aligned window of 32 positions, from every entry position at once (pointer
+// doubling, all lanes): lane i holds the match length ml of position i (0: miss, kPwCap: 64 or more bytes -- the walk ends
+// there, the walker measures the match).  Returns the set of positions the walk from position i probes (bit j = position j)
+// and, in `exitp`, where it leaves the window: 32..94 window-relative, or 255 for a walk that ended at a capped match.
+__device__ __forceinline__ uint32_t pw_resolve(const uint32_t ml, const uint32_t lane, uint32_t &exitp) {
+    uint32_t n = ml == kPwCap ? 255u : lane + (ml ? ml : 1u);
+    uint32_t m = 1u << lane;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const uint32_t mj = __shfl_sync(FULL, m, n), nj = __shfl_sync(FULL, n, n);      // (source lane = n mod 32)
+        if (n < 32u) { m |= mj; n = nj; }
+    }
+    exitp = n;
+    return m;
 }
 
 // common prefix of base[s0 + eb ..] and base[m0 + eb ..] from byte eb on, bounded by matchLimit (:147-150); all lanes.
@@ -124,8 +149,7 @@ __device__ __forceinline__ uint32_t pw_extend(const uint8_t *__restrict__ base, 
     }
 }
 
-constexpr uint32_t kPwCap = 64u;              // producers pre-extend a match to this many bytes; the walker continues a longer one
-constexpr uint32_t kPwGenMask = 0x7FFu;       // ring entry: slot (14 bits) | match length (7) | window number + 1 (11); high word: entry seen
+constexpr uint32_t kPwGenMask = 0x7FFu;       // ring entry: x = slot (14 bits) | match length (7) | window number + 1 (11); y = entry seen | exit << 16; z = probed set (pw_resolve)
 
 // candidate bytes (three aligned 16-byte granules, `cs` = byte offset of the first wanted byte inside the first) against
 // the 32 bytes Sw[0..7]: number of equal leading bytes, 0..32.  Branch-free like wide_verify.
@@ -153,7 +177,7 @@ __device__ __forceinline__ uint32_t pw_count32(const uint4 &q0, const uint4 &q1,
 //      independent instruction streams, so the memory round trips (source words, table entry, candidate bytes) overlap.
 //      two == false: window k only (the last window of a block).
 __device__ __forceinline__ void pw_produce2(const uint8_t *__restrict__ base, const uint32_t k, const bool two, const uint16_t *tab,
-                                            uint64_t *ring, const uint32_t lane) {
+                                            uint32_t *ring, const uint32_t lane) {
     const uint32_t pa = 32u * k + lane, pb = pa + 32u;
     const uintptr_t ba = reinterpret_cast<uintptr_t>(base);
     const uint32_t a = (uint32_t)(ba & 3u) + pa;
@@ -176,6 +200,11 @@ __device__ __forceinline__ void pw_produce2(const uint8_t *__restrict__ base, co
     const uint4 *cqa = reinterpret_cast<const uint4 *>(base + la - csa), *cqb = reinterpret_cast<const uint4 *>(base + lb - csb);
     const uint4 qa0 = __ldg(cqa), qa1 = __ldg(cqa + 1), qa2 = __ldg(cqa + 2);
     const uint4 qb0 = __ldg(cqb), qb1 = __ldg(cqb + 1), qb2 = __ldg(cqb + 2);
+    if (kPwPrefetch) {
+        // what the second stage reads if 32 bytes match (granules 3, 4 and the source words behind +64): start the round trip now
+        pw_prefetch(cqa + 4);
+        if (two) { pw_prefetch(cqb + 4); pw_prefetch(wp + 24); }
+    }
     const uint32_t va = wide_verify(qa0, qa1, qa2, csa, S), vb = wide_verify(qb0, qb1, qb2, csb, S + 8);     // 0 or 4..32
     uint32_t mla = oka ? va : 0u, mlb = okb ? vb : 0u;
     if (__any_sync(FULL, mla == 32u || mlb == 32u)) {
@@ -204,37 +233,49 @@ __device__ __forceinline__ void pw_produce2(const uint8_t *__restrict__ base, co
         const uint4 q3 = __ldg(cqa + 3), q4 = __ldg(cqa + 4);
         mla += pw_count32(qa2, q3, q4, csa, S2);
     }
+    uint32_t exa, exb;
+    const uint32_t pma = pw_resolve(mla, lane, exa), pmb = pw_resolve(mlb, lane, exb);
     const uint32_t loa = ha | (mla << 14) | (((k + 1u) & kPwGenMask) << 21);
-    pw_sts64(ring + (pa & (kPwRing - 1)), (uint64_t)loa | ((uint64_t)seena << 32));
+    // y and z first, then x with the window number: a reader that sees the number sees the rest
+    uint32_t *const sa = ring + pw_slot(pa), *const sb = ring + pw_slot(pb);
+    pw_sts(sa + 32, seena | (exa << 16));
+    pw_sts(sa + 64, pma);
     if (two) {
-        const uint32_t lob = hb | (mlb << 14) | (((k + 2u) & kPwGenMask) << 21);
-        pw_sts64(ring + (pb & (kPwRing - 1)), (uint64_t)lob | ((uint64_t)seenb << 32));
+        pw_sts(sb + 32, seenb | (exb << 16));
+        pw_sts(sb + 64, pmb);
     }
+    __threadfence_block();
+    pw_sts(sa, loa);
+    if (two) pw_sts(sb, hb | (mlb << 14) | (((k + 2u) & kPwGenMask) << 21));
 }
 
 // Producer j of kNP takes the window pairs (2j, 2j+1), (2j + 2 kNP, ...), ... -- skipping those the walker has left behind -- and
 // stays at most `lead` windows ahead of the walker's window.
 template <int kNP>
 __device__ __forceinline__ void pw_producer(const uint8_t *__restrict__ base, const uint32_t nwin, const uint32_t lead,
-                                            const uint32_t j, const uint16_t *tab, uint64_t *ring, PwCtl *ctl, const uint32_t lane,
+                                            const uint32_t j, const uint16_t *tab, uint32_t *ring, PwCtl *ctl, const uint32_t lane,
                                             const uint32_t full_ns) {
     uint32_t k = 2u * j;
+    PT_DECL
     for (;;) {
         const uint32_t wpos = ctl->w_pos;
         if (wpos & kPwDone) break;
-        if (wpos & kPwSparse) { __nanosleep(256); continue; }
+        if (wpos & kPwSparse) { __nanosleep(256); PT_MARK(8) continue; }
         const uint32_t wk = wpos >> 5;
         while (k + 1u < wk) k += 2u * (uint32_t)kNP;
-        if (k >= nwin) { __nanosleep(1024); continue; }
-        if (k + 1u >= wk + lead) { __nanosleep(full_ns); continue; }
+        if (k >= nwin) { __nanosleep(1024); PT_MARK(8) continue; }
+        if (k + 1u >= wk + lead) { __nanosleep(full_ns); PT_MARK(7) continue; }
+        if (kPwPrefetch && lane < 2u && k + 2u * (uint32_t)kNP < nwin) pw_prefetch(base + 32u * (k + 2u * (uint32_t)kNP) + 128u * lane);
         pw_produce2(base, k, k + 1u < nwin, tab, ring, lane);
+        PT_MARK(6) PT_COUNT(13, 1)
         k += 2u * (uint32_t)kNP;
     }
+    PT_FLUSH
 }
 
 // ---- walker: the serial loop.  Returns the number of records written.
 __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, const int32_t len, const uint32_t nwin, uint16_t *tab,
-                                              const uint64_t *ring, PwCtl *ctl, uint64_t *__restrict__ rec, const uint32_t lane,
+                                              const uint32_t *ring, PwCtl *ctl, uint64_t *__restrict__ rec, const uint32_t lane,
                                               const bool publish_records) {
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t rpub = 0;                                                          // what ctl->nrec_pub holds
@@ -250,6 +291,7 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
     const SrcFlat S{base};
     Tab16 T{tab, 0};
     uint2 *const rec2 = reinterpret_cast<uint2 *>(rec);
+    PT_DECL
 
     while (sIndex < mflimit) {                                                  // :48
         if (publish_records && ((nrec ^ rpub) >> 5)) {
@@ -259,36 +301,33 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
             rpub = nrec;
             if (lane == 0) ctl->nrec_pub = nrec;
         }
-        if (smc <= 96u && sIndex + 32 <= rlimit) {
-            // ---- path step: while searchMatchCount stays below 128 the schedule steps by 1 (:66-67), so the parse inside the
-            //      next 32 positions is a walk over the producers' match lengths: from a hit to the position behind its match,
-            //      from a miss to the next position.  Every lane computes the positions reachable from its own by pointer
-            //      doubling; lane 0's set is the set of PROBED positions.  Those lanes validate (slot unchanged since the
-            //      producer looked, no two of them in one slot) and insert themselves; the hits among them are the records.
-            const uint32_t s = (uint32_t)sIndex;
-            if ((s ^ pub) >> 5) { pub = s; if (lane == 0) ctl->w_pos = s; }
-            const uint32_t p = s + lane;
-            const uint64_t *slot = ring + (p & (kPwRing - 1));
+        if (smc <= 96u && (sIndex | 31) < rlimit) {
+            // ---- path step: while searchMatchCount stays below 128 the schedule steps by 1 (:66-67), so the parse inside an
+            //      aligned window of 32 positions is a walk over the producers' match lengths: from a hit to the position
+            //      behind its match, from a miss to the next position.  The PRODUCER of the window has already resolved that
+            //      walk from every possible entry position (pw_resolve); the walker reads the walk that starts at its own
+            //      position -- the set PM of PROBED positions and where the walk leaves the window -- from that position's
+            //      ring entry.  The probed lanes validate (slot unchanged since the producer looked, no two of them in one
+            //      slot) and insert themselves; the hits among them are the records.
+            const uint32_t s = (uint32_t)sIndex, wbase = s & ~31u, sl = s & 31u;
+            if (pub != wbase) { pub = wbase; if (lane == 0) ctl->w_pos = wbase; }
+            const uint32_t p = wbase + lane;
+            const uint32_t *slot = ring + pw_slot(p);
             const uint32_t want = ((p >> 5) + 1u) & kPwGenMask;
-            uint64_t e;
+            uint32_t ex;
             for (;;) {
-                e = pw_lds64(slot);
-                if (__all_sync(FULL, ((uint32_t)e >> 21) == want)) break;
+                ex = pw_lds(slot);
+                if (__all_sync(FULL, (ex >> 21) == want)) break;
                 __nanosleep(32);
+                PT_COUNT(15, 1)
             }
-            const uint32_t lo = (uint32_t)e, seen = (uint32_t)(e >> 32);
-            const uint32_t h = lo & 0x3FFFu, ml = (lo >> 14) & 127u;
+            PT_MARK(1)
+            const uint32_t ey = pw_lds(slot + 32);
+            const uint32_t PM = pw_lds(slot + 64 + sl - lane), exitp = pw_lds(slot + 32 + sl - lane) >> 16;     // entry of position s
+            const uint32_t seen = ey & 0xFFFFu;
+            const uint32_t h = ex & 0x3FFFu, ml = (ex >> 14) & 127u;
             const uint32_t cur = tab[h];                                       // :54 (state before this step)
-            // reach: n = where the walk from this lane stands (>= 32: left the step; a pre-extension that hit its cap of 32
-            // ends the walk at that position, n = 64), m = positions visited so far
-            uint32_t n = ml == kPwCap ? 255u : lane + (ml ? ml : 1u);
-            uint32_t m = 1u << lane;
-#pragma unroll
-            for (int r = 0; r < 5; ++r) {
-                const uint32_t mj = __shfl_sync(FULL, m, n), nj = __shfl_sync(FULL, n, n);      // (source lane = n mod 32)
-                if (n < 32u) { m |= mj; n = nj; }
-            }
-            const uint32_t PM = __shfl_sync(FULL, m, 0), exitp = __shfl_sync(FULL, n, 0);
+            const uint32_t claim = __ballot_sync(FULL, ml != 0u);
             const bool probed = (PM >> lane) & 1u;
             const uint32_t tag = p & 0xFFFFu;
             __syncwarp();                                                      // every lane holds its `cur` before any slot changes
@@ -296,7 +335,6 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
             __syncwarp();
             const uint32_t r = probed ? (uint32_t)tab[h] : tag;
             const uint32_t bad = __ballot_sync(FULL, probed && (r != tag || cur != seen));
-            const uint32_t claim = __ballot_sync(FULL, ml != 0u);
             if (!bad) {
                 const uint32_t HM = PM & claim;                                // the matches, in order
                 const uint32_t nh = (uint32_t)__popc(HM);
@@ -304,17 +342,18 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
                 if (exitp == 255u) {
                     // the walk ended at a match of 32 or more bytes (the last probed position): its real length (:147-150)
                     const uint32_t c = 31u - (uint32_t)__clz(PM);
-                    const uint32_t pc = s + c, curc = __shfl_sync(FULL, cur, c);
+                    const uint32_t pc = wbase + c, curc = __shfl_sync(FULL, cur, c);
                     const uint32_t mlx = pw_extend(base, (int32_t)pc, (int32_t)curc, (int32_t)kPwCap, matchLimit, lane);
                     if (lane == 0) rec2[nrec + nh - 1u] = rec_pack(pc, mlx, pc - curc);
                     sIndex = (int32_t)(pc + mlx);
                     smc = 67u;
                 } else {
-                    sIndex = (int32_t)(s + exitp);
+                    sIndex = (int32_t)(wbase + exitp);
                     if (HM) smc = 67u + (uint32_t)__popc(PM & ~((2u << (31 - __clz(HM))) - 1u));      // misses behind the last match
                     else smc += (uint32_t)__popc(PM);
                 }
                 nrec += nh;
+                PT_MARK(0) PT_COUNT(9, 1)
                 continue;
             }
             // ---- a same-slot pair or a stale entry among the probed positions: the probed positions in front of the first
@@ -323,7 +362,7 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
             const uint32_t inv = (probed && r != tag) ? min(tag, r) : 0xFFFFFFFFu;              // lower position of a pair
             const uint32_t cutpos = __reduce_min_sync(FULL, inv);
             const uint32_t stale = __ballot_sync(FULL, probed && cur != seen);
-            const uint32_t Bl = min(cutpos == 0xFFFFFFFFu ? 32u : ((cutpos - s) & 0xFFFFu) + 1u, stale ? (uint32_t)__ffs(stale) - 1u : 32u);
+            const uint32_t Bl = min(cutpos == 0xFFFFFFFFu ? 32u : ((cutpos - wbase) & 0xFFFFu) + 1u, stale ? (uint32_t)__ffs(stale) - 1u : 32u);
             const uint32_t below = (1u << Bl) - 1u;                            // Bl <= 31
             if (probed && lane >= Bl) tab[h] = (uint16_t)cur;                   // undo
             __syncwarp();
@@ -334,9 +373,9 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
             nrec += (uint32_t)__popc(HMk);
             if (HMk) smc = 67u + (uint32_t)__popc(keep & ~((2u << (31 - __clz(HMk))) - 1u));
             else smc += (uint32_t)__popc(keep);
-            sIndex = (int32_t)(s + (uint32_t)__ffs(PM & ~below) - 1u);
+            sIndex = (int32_t)(wbase + (uint32_t)__ffs(PM & ~below) - 1u);
             // one position, :50-71
-            const uint32_t hx = __shfl_sync(FULL, h, (uint32_t)sIndex - s);
+            const uint32_t hx = __shfl_sync(FULL, h, (uint32_t)sIndex - wbase);
             const uint32_t cand = tab[hx];
             __syncwarp();
             if (lane == 0) tab[hx] = (uint16_t)sIndex;
@@ -352,6 +391,7 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
                 sIndex += (int32_t)(smc >> 6);
                 ++smc;
             }
+            PT_MARK(4) PT_COUNT(10, 1)
             continue;
         }
         if (smc <= kPwRingSmc && sIndex < rlimit) {
@@ -360,16 +400,16 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
             const int32_t p = sIndex + (int32_t)(skip_sum(smc + lane) - bs);
             const bool valid = p < rlimit;
             if (pub != (uint32_t)sIndex) { pub = (uint32_t)sIndex; if (lane == 0) ctl->w_pos = pub; }
-            const uint64_t *slot = ring + ((uint32_t)p & (kPwRing - 1));
+            const uint32_t *slot = ring + pw_slot((uint32_t)p);
             const uint32_t want = (((uint32_t)p >> 5) + 1u) & kPwGenMask;
-            uint64_t e;
+            uint32_t lo;
             for (;;) {
-                e = pw_lds64(slot);
-                const bool ready = !valid || (((uint32_t)e >> 21) == want);
+                lo = pw_lds(slot);
+                const bool ready = !valid || ((lo >> 21) == want);
                 if (__all_sync(FULL, ready)) break;
                 __nanosleep(20);
             }
-            const uint32_t lo = (uint32_t)e, seen = (uint32_t)(e >> 32);
+            const uint32_t seen = pw_lds(slot + 32) & 0xFFFFu;
             const uint32_t h = lo & 0x3FFFu, ml = (lo >> 14) & 127u;
             const uint32_t cur = tab[h];                                       // :54 (state before this step)
             const uint32_t claim = __ballot_sync(FULL, valid && ml != 0u);
@@ -397,6 +437,7 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
                     sIndex += (int32_t)(skip_sum(smc + nv) - bs);
                     smc += nv;
                 }
+                PT_MARK(2) PT_COUNT(11, 1)
                 continue;
             }
             // ---- cut: the lanes in front of the first same-slot pair / stale entry are plain misses
@@ -412,6 +453,7 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
             if (c != 0u) {
                 sIndex += (int32_t)(skip_sum(smc + c) - bs);
                 smc += c;
+                PT_MARK(2) PT_COUNT(11, 1)
                 continue;
             }
             // ---- the position at the head of the step is stale: probe it the slow way (one position, :50-71)
@@ -431,6 +473,7 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
                 sIndex += (int32_t)(smc >> 6);
                 ++smc;
             }
+            PT_MARK(2) PT_COUNT(11, 1)
             continue;
         }
 
@@ -469,6 +512,7 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
             if (vmask != FULL) break;                            // ran into mflimit: loop ends
             sIndex += (int32_t)(skip_sum(smc + 32u) - base_sum);
             smc += 32u;
+            PT_MARK(3) PT_COUNT(12, 1)
             continue;
         }
         const int32_t s0 = __shfl_sync(FULL, p, hl);
@@ -478,7 +522,10 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
         if (lane == 0) rec2[nrec] = rec_pack((uint32_t)s0, ml, (uint32_t)(s0 - m0));
         ++nrec;
         sIndex = s0 + (int32_t)ml;
+        PT_MARK(3) PT_COUNT(12, 1)
     }
+    PT_MARK(5)
+    PT_FLUSH
     return nrec;
 }
 
@@ -568,8 +615,8 @@ k_parse_pw(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off
     const uint32_t tid = threadIdx.x - chain * kTeam;                          // thread index inside the team
     uint8_t *const cb = smem + (size_t)chain * kPwChainBytes;
     uint16_t *const tab = reinterpret_cast<uint16_t *>(cb);
-    uint64_t *const ring = reinterpret_cast<uint64_t *>(cb + kHashEntries * 2);
-    PwCtl *const ctl = reinterpret_cast<PwCtl *>(cb + kHashEntries * 2 + kPwRing * 8);
+    uint32_t *const ring = reinterpret_cast<uint32_t *>(cb + kHashEntries * 2);
+    PwCtl *const ctl = reinterpret_cast<PwCtl *>(cb + kHashEntries * 2 + kPwRingBytes);
     const uint32_t bar = 1u + chain;
     // first block of a team: spread over the CTAs first, then over the teams of a CTA; later ones from the queue
     uint32_t first = chain * gridDim.x + blockIdx.x;
@@ -595,7 +642,7 @@ k_parse_pw(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off
         }
         {   // empty table (bufferCompress.js:182 / :235), invalid ring
             uint4 *z = reinterpret_cast<uint4 *>(cb);
-            for (uint32_t i = tid; i < (kHashEntries * 2 + kPwRing * 8) / 16; i += kTeam) z[i] = make_uint4(0, 0, 0, 0);
+            for (uint32_t i = tid; i < (kHashEntries * 2 + kPwRingBytes) / 16; i += kTeam) z[i] = make_uint4(0, 0, 0, 0);
         }
         pw_bar(bar, kTeam);
         const uint8_t *base = src + src_off[b];

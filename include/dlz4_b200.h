@@ -64,6 +64,10 @@ const char *dlz4_last_error(const dlz4_ctx *ctx);
 uint64_t dlz4_launch_count(const dlz4_ctx *ctx);
 /* Device time in ms of the most recent host-pointer call's kernel section (CUDA events). */
 float dlz4_last_kernel_ms(const dlz4_ctx *ctx);
+/* Measurement aid (bench.py "roofline"): with enable != 0 the next batches of fresh blocks <= 64 KiB record CUDA events
+ * around the match finder (k_parse_pw) and the encoder (k_encode_blocks) on the stream they run on.  finder_ms /
+ * encoder_ms (nullable) receive the durations of the most recent probed batch (the call waits for it). */
+int dlz4_kernel_probe(dlz4_ctx *ctx, int enable, float *finder_ms, float *encoder_ms);
 /* Segment-parallel compression (linked-block chains, bufferCompress.js:182,219,234, and independent blocks > 64 KiB): how
  * many segments the most recent frame call used, how many of them had to be re-run because the speculative start state
  * differed from the serial parse's, and in how many rounds.  The output bytes are those of the serial loop either way. */

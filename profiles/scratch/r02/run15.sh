@@ -1,0 +1,14 @@
+set -x
+cd /root/repo
+timeout 600 python -m pytest tests/test_gpu_blocks.py -x -q -m gpu > gpurun_out/r02_pw_tests.txt 2>&1
+tail -3 gpurun_out/r02_pw_tests.txt
+grep -q passed gpurun_out/r02_pw_tests.txt || exit 1
+rm -f gpurun_out/r02_pw_kbench9.txt
+for cfg in "DLZ4_PW=2 DLZ4_PW_LEAD=12" "DLZ4_PW=3 DLZ4_PW_LEAD=12" "DLZ4_PW=3 DLZ4_PW_LEAD=13 DLZ4_PW_SLEEP=400" "DLZ4_PW=3 DLZ4_PW_LEAD=10"; do
+  echo "== $cfg" >> gpurun_out/r02_pw_kbench9.txt
+  env $cfg timeout 300 python divortio-lz4_b200/tools/kbench.py 1024 65536 log,mixed >> gpurun_out/r02_pw_kbench9.txt 2>&1
+done
+cat gpurun_out/r02_pw_kbench9.txt
+DLZ4_LIB=divortio-lz4_b200/csrc/libdlz4_b200_prof.so timeout 300 python divortio-lz4_b200/tools/pw_phases.py log 1024 > gpurun_out/r02_pw_phases3.txt 2>&1
+DLZ4_PW=3 DLZ4_LIB=divortio-lz4_b200/csrc/libdlz4_b200_prof.so timeout 300 python divortio-lz4_b200/tools/pw_phases.py log 1024 >> gpurun_out/r02_pw_phases3.txt 2>&1
+cat gpurun_out/r02_pw_phases3.txt
