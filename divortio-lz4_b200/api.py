@@ -103,6 +103,8 @@ def lib():
         "dlz4_xxh32_batch_dev": (C.c_int, [vp, vp, vp, vp, u32, u32, vp, vp]),
         "dlz4_xxh32_stream_dev": (C.c_int, [vp, vp, u64, u32, vp, vp]),
         "dlz4_xxh32": (C.c_int, [vp, vp, u64, u32, C.POINTER(u32)]),
+        "dlz4_xxh32_async": (C.c_int, [vp, C.c_int, vp, u64, u32]),
+        "dlz4_xxh32_wait": (C.c_int, [vp, C.c_int, C.POINTER(u32)]),
         "dlz4_xxh32_batch": (C.c_int, [vp, vp, u64, vp, vp, u32, u32, vp]),
         "dlz4_frame_compress": (C.c_int, [vp, vp, u64, vp, u64, C.POINTER(FrameOpts), vp, u64, C.POINTER(u64)]),
         "dlz4_frame_info": (C.c_int, [vp, u64, C.POINTER(FrameInfo)]),
@@ -133,7 +135,7 @@ EXPORTED_SYMBOLS = [
     "dlz4_init", "dlz4_shutdown", "dlz4_strerror", "dlz4_last_error", "dlz4_launch_count", "dlz4_last_kernel_ms", "dlz4_kernel_probe", "dlz4_segment_stats",
     "dlz4_pinned_alloc", "dlz4_pinned_free", "dlz4_host_register", "dlz4_host_unregister", "dlz4_compress_bound", "dlz4_frame_bound", "dlz4_shard_range",
     "dlz4_compress_blocks_dev", "dlz4_compress_blocks", "dlz4_decompress_blocks_dev", "dlz4_decompress_blocks",
-    "dlz4_compress_block", "dlz4_decompress_block", "dlz4_xxh32_batch_dev", "dlz4_xxh32_stream_dev", "dlz4_xxh32",
+    "dlz4_compress_block", "dlz4_decompress_block", "dlz4_xxh32_batch_dev", "dlz4_xxh32_stream_dev", "dlz4_xxh32", "dlz4_xxh32_async", "dlz4_xxh32_wait",
     "dlz4_xxh32_batch", "dlz4_frame_compress", "dlz4_frame_info", "dlz4_frame_decompress", "dlz4_frame_pack_dev", "dlz4_frames_decompress", "dlz4_frames_info", "dlz4_frame_decompress_ex", "dlz4_xxh32_reset", "dlz4_xxh32_update", "dlz4_xxh32_digest",
     "dlz4_chain_compress", "dlz4_frame_body_compress", "dlz4_frame_body_fetch", "dlz4_frame_header", "dlz4_frame_decompress_range",
     "dlz4_xxh32_update_resident",

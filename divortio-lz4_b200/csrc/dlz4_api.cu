@@ -5,7 +5,12 @@
 #include "dlz4_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -26,6 +31,77 @@ struct Buf {
     void *p = nullptr;
     size_t cap = 0;
 };
+
+// Host threads for copies between ordinary (pageable) caller memory and the page-locked staging ring: the reference's
+// callers own plain Uint8Arrays (bufferCompress.js:100), and one thread's memcpy -- or the driver's own staging inside
+// cudaMemcpyAsync -- moves 5-6 GB/s where the PCIe link takes 55.
+class CopyPool {
+  public:
+    explicit CopyPool(int threads) {
+        for (int i = 0; i < threads; ++i) workers_.emplace_back([this] { run(); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+        cv_.notify_all();
+        for (std::thread &t : workers_) t.join();
+    }
+    // memcpy(dst, src, n) cut into pieces over the workers and the caller
+    void copy(void *dst, const void *src, size_t n) {
+        const size_t piece = 1u << 20;
+        const size_t parts = (n + piece - 1) / piece;
+        if (parts <= 1 || workers_.empty()) { memcpy(dst, src, n); return; }
+        {
+            std::lock_guard<std::mutex> g(m_);
+            dst_ = (uint8_t *)dst; src_ = (const uint8_t *)src; n_ = n; piece_ = piece; parts_ = parts;
+            next_.store(0); done_ = 0; ++gen_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> g(m_);
+        cv_done_.wait(g, [&] { return done_ == parts_; });
+    }
+
+  private:
+    void work() {
+        size_t mine = 0;
+        for (;;) {
+            const size_t i = next_.fetch_add(1);
+            if (i >= parts_) break;
+            const size_t o = i * piece_;
+            memcpy(dst_ + o, src_ + o, std::min(piece_, n_ - o));
+            ++mine;
+        }
+        if (mine) {
+            std::lock_guard<std::mutex> g(m_);
+            done_ += mine;
+            if (done_ == parts_) cv_done_.notify_all();
+        }
+    }
+    void run() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, cv_done_;
+    bool stop_ = false;
+    uint64_t gen_ = 0;
+    uint8_t *dst_ = nullptr;
+    const uint8_t *src_ = nullptr;
+    size_t n_ = 0, piece_ = 0, parts_ = 0, done_ = 0;
+    std::atomic<size_t> next_{0};
+};
+constexpr int kSumSlots = 32;                  // concurrent whole-stream checksums (dlz4_xxh32_async)
+constexpr int kStageSlots = 4;                 // page-locked staging ring for pageable caller buffers
+constexpr size_t kStageBytes = 16u << 20;
 
 }  // namespace
 
@@ -65,6 +141,13 @@ struct dlz4_ctx {
     uint32_t seg_jobs = 0, seg_reruns = 0, seg_rounds = 0;   // last segment-parallel call: segments, re-run segments, rounds
     uint64_t launches = 0;
     float last_ms = 0.f;
+    CopyPool *pool = nullptr;           // host copy threads (pageable caller buffers), created on first use
+    int copy_threads = 0;               // 0: min(8, hardware threads / 2)
+    uint8_t *stage[kStageSlots] = {};   // page-locked staging ring
+    cudaEvent_t stage_ev[kStageSlots] = {};
+    bool stage_busy[kStageSlots] = {};
+    cudaStream_t sum_stream[kSumSlots] = {};   // dlz4_xxh32_async: one serial chain per slot, each on its own stream
+    uint32_t *h_sum = nullptr;          // their results (page-locked, written by the kernels)
     int probe = 0;                      // dlz4_kernel_probe: time the match finder and the encoder of the next batch separately
     cudaEvent_t evq[3] = {};            // before the match finder, between the two kernels, behind the encoder
     // what the last frame-body / frame-range call left resident on the device (sharded frames): the rank's input
@@ -114,6 +197,73 @@ int reserve_pinned(dlz4_ctx *ctx, Buf &b, size_t bytes) {
 }
 
 inline cudaStream_t pick(dlz4_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+// Ordinary host memory (neither cudaMallocHost nor cudaHostRegister)?
+bool is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+int stage_init(dlz4_ctx *ctx) {
+    if (ctx->stage[0]) return DLZ4_OK;
+    for (int i = 0; i < kStageSlots; ++i) {
+        CK(cudaMallocHost((void **)&ctx->stage[i], kStageBytes));
+        CK(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+        ctx->stage_busy[i] = false;
+    }
+    int t = ctx->copy_threads;
+    if (t <= 0) t = (int)std::min<unsigned>(8u, std::max(2u, std::thread::hardware_concurrency() / 2));
+    ctx->pool = new CopyPool(t - 1);             // the calling thread copies too
+    return DLZ4_OK;
+}
+
+// Host -> device on stream `s`.  Page-locked source: one asynchronous copy.  Pageable source of some size: pieces go through
+// the staging ring (host threads copy a piece into a page-locked slot, the slot is sent asynchronously, the next piece is
+// copied meanwhile); returns when the last piece is queued -- the caller's memory is no longer read after that.
+int h2d(dlz4_ctx *ctx, void *d, const void *h, size_t n, cudaStream_t s, int pageable /* -1: ask the driver */ = -1) {
+    if (!n) return DLZ4_OK;
+    if (pageable < 0) pageable = n >= (4u << 20) && is_pageable(h);
+    if (!pageable || n < (4u << 20)) { CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); return DLZ4_OK; }
+    CKS(stage_init(ctx));
+    int slot = 0;
+    for (size_t o = 0; o < n; o += kStageBytes, slot = (slot + 1) % kStageSlots) {
+        const size_t len = std::min(kStageBytes, n - o);
+        if (ctx->stage_busy[slot]) CK(cudaEventSynchronize(ctx->stage_ev[slot]));
+        ctx->pool->copy(ctx->stage[slot], (const uint8_t *)h + o, len);
+        CK(cudaMemcpyAsync((uint8_t *)d + o, ctx->stage[slot], len, cudaMemcpyHostToDevice, s));
+        CK(cudaEventRecord(ctx->stage_ev[slot], s));
+        ctx->stage_busy[slot] = true;
+    }
+    return DLZ4_OK;
+}
+
+// Device -> host on stream `s`.  Page-locked destination: one asynchronous copy (the caller synchronises).  Pageable
+// destination: the pieces arrive in the staging ring and host threads copy them out while the next ones are in flight;
+// returns when the caller's memory holds the bytes.
+int d2h(dlz4_ctx *ctx, void *h, const void *d, size_t n, cudaStream_t s, int pageable = -1) {
+    if (!n) return DLZ4_OK;
+    if (pageable < 0) pageable = n >= (4u << 20) && is_pageable(h);
+    if (!pageable || n < (4u << 20)) { CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); return DLZ4_OK; }
+    CKS(stage_init(ctx));
+    for (int i = 0; i < kStageSlots; ++i)
+        if (ctx->stage_busy[i]) { CK(cudaEventSynchronize(ctx->stage_ev[i])); ctx->stage_busy[i] = false; }
+    const size_t pieces = (n + kStageBytes - 1) / kStageBytes;
+    auto issue = [&](size_t i) -> int {
+        const size_t o = i * kStageBytes, len = std::min(kStageBytes, n - o);
+        CK(cudaMemcpyAsync(ctx->stage[i % kStageSlots], (const uint8_t *)d + o, len, cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(ctx->stage_ev[i % kStageSlots], s));
+        return DLZ4_OK;
+    };
+    for (size_t i = 0; i < std::min<size_t>(pieces, kStageSlots); ++i) CKS(issue(i));
+    for (size_t i = 0; i < pieces; ++i) {
+        const size_t o = i * kStageBytes, len = std::min(kStageBytes, n - o);
+        CK(cudaEventSynchronize(ctx->stage_ev[i % kStageSlots]));
+        ctx->pool->copy((uint8_t *)h + o, ctx->stage[i % kStageSlots], len);
+        if (i + kStageSlots < pieces) CKS(issue(i + kStageSlots));
+    }
+    return DLZ4_OK;
+}
 
 // host xxh32 for the <= 14 header bytes only (FLG..dictID -> HC byte, bufferCompress.js:177-178)
 uint32_t header_xxh32(const uint8_t *p, size_t len) {
@@ -287,7 +437,7 @@ int launch_xxh32_batch(dlz4_ctx *ctx, const uint8_t *base, const uint64_t *off, 
 }
 
 int launch_xxh32_stream(dlz4_ctx *ctx, const uint8_t *data, uint64_t len, uint32_t seed, uint32_t *out, cudaStream_t st) {
-    k_xxh32_stream<<<1, 32, 0, st>>>(data, len, seed, out, nullptr, nullptr);
+    k_xxh32_stream<1><<<1, 32, 0, st>>>(data, len, seed, out, nullptr, nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
     return DLZ4_OK;
@@ -584,7 +734,7 @@ int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, uint64_t frame_span, 
         if (ship && base_h[b1] > base_h[b0]) {
             CK(cudaEventRecord(ctx->evp[u], st));
             CK(cudaStreamWaitEvent(ctx->copy_out, ctx->evp[u], 0));
-            CK(cudaMemcpyAsync(host_out + base_h[b0], d_out + base_h[b0], base_h[b1] - base_h[b0], cudaMemcpyDeviceToHost, ctx->copy_out));
+            CKS(d2h(ctx, host_out + base_h[b0], d_out + base_h[b0], base_h[b1] - base_h[b0], ctx->copy_out));
         }
     }
 
@@ -631,6 +781,7 @@ int dlz4_init(int device, dlz4_ctx **out) {
     for (cudaStream_t &l : ctx->lanes) CK(cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking));
     if (const char *e = getenv("DLZ4_CHUNK_MIB")) ctx->chunk_bytes = (uint64_t)std::max(1, atoi(e)) << 20;
     if (const char *e = getenv("DLZ4_LANES")) ctx->n_lanes = std::min(4, std::max(1, atoi(e)));
+    if (const char *e = getenv("DLZ4_COPY_THREADS")) ctx->copy_threads = std::min(64, std::max(1, atoi(e)));
     CK(cudaMalloc(&ctx->d_counter, 64));
     CK(cudaMalloc(&ctx->d_land, kLandFlags * 4));
     CK(cudaMallocHost(&ctx->h_one, 64));
@@ -687,6 +838,13 @@ void dlz4_shutdown(dlz4_ctx *ctx) {
     if (ctx->d_gtabs) cudaFree(ctx->d_gtabs);
     if (ctx->d_nrec) cudaFree(ctx->d_nrec);
     if (ctx->rec.p) cudaFree(ctx->rec.p);
+    delete ctx->pool;
+    for (cudaStream_t s : ctx->sum_stream) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    if (ctx->h_sum) cudaFreeHost(ctx->h_sum);
+    for (int i = 0; i < kStageSlots; ++i) {
+        if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+    }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->evq) if (e) cudaEventDestroy(e);
@@ -774,7 +932,7 @@ void dlz4_pinned_free(void *p) { if (p) cudaFreeHost(p); }
 // stays usable, just pageable).
 int dlz4_host_register(void *p, uint64_t bytes) {
     if (!p || !bytes) return DLZ4_E_INVALID_ARG;
-    return cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable) == cudaSuccess ? DLZ4_OK : (cudaGetLastError(), DLZ4_E_CUDA);
+    return cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess ? DLZ4_OK : (cudaGetLastError(), DLZ4_E_CUDA);
 }
 int dlz4_host_unregister(void *p) {
     if (!p) return DLZ4_E_INVALID_ARG;
@@ -873,24 +1031,25 @@ static int compress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t sr
     for (uint32_t l = 1; l < nl; ++l) CK(cudaStreamWaitEvent(sks[l], ctx->ev_fork, 0));   // descriptors visible to every lane
 
     uint64_t host_pos = 0;
+    const int src_pg = src_bytes >= (4u << 20) && is_pageable(src), dst_pg = dst_bytes >= (4u << 20) && is_pageable(dst);
     auto drain = [&](uint32_t c) -> int {          // chunk c's kernels are done: ship its packed bytes
         CK(cudaEventSynchronize(ctx->evp[64 + c]));
         const uint64_t tot = h_tot[c];
         if (host_pos + tot > dst_bytes) return DLZ4_E_OUTPUT_TOO_SMALL;
-        if (tot) CK(cudaMemcpyAsync(dst + host_pos, d_pack + (uint64_t)cb[c] * (stride + 16), tot, cudaMemcpyDeviceToHost, so));
+        CKS(d2h(ctx, dst + host_pos, d_pack + (uint64_t)cb[c] * (stride + 16), tot, so, dst_pg));
         host_pos += tot;
         return DLZ4_OK;
     };
     // everything is enqueued up front (the host only blocks in drain(), which needs each chunk's packed size to place it):
-    // all H2D copies on the copy-in stream, then every chunk's kernels on its lane, gated by the chunk's copy event
-    for (uint32_t c = 0; c < nc; ++c) {
-        const uint32_t b0 = cb[c], b1 = cb[c + 1];
-        const uint64_t lo = src_off[b0], hi = src_off[b1 - 1] + src_len[b1 - 1];
-        if (hi > lo) CK(cudaMemcpyAsync(d_src + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, si));
-        CK(cudaEventRecord(ctx->evp[c], si));
-    }
+    // a chunk's H2D copy on the copy-in stream (a pageable source through the staging ring: the host copies chunk c + 1 while
+    // chunk c's kernels run), then its kernels on its lane, gated by the chunk's copy event
     for (uint32_t c = 0; c < nc; ++c) {
         const uint32_t b0 = cb[c], b1 = cb[c + 1], m = b1 - b0;
+        {
+            const uint64_t lo = src_off[b0], hi = src_off[b1 - 1] + src_len[b1 - 1];
+            if (hi > lo) CKS(h2d(ctx, d_src + lo, src + lo, hi - lo, si, src_pg));
+            CK(cudaEventRecord(ctx->evp[c], si));
+        }
         // chunks rotate over the compute streams (own work-queue counter and L2-table region each): the next chunks' CTAs
         // take over SM slots as the previous chunk's last blocks drain
         sk = sks[c % nl];
@@ -1031,6 +1190,7 @@ static int decompress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t 
         if (acc >= want || i + 1 == n) { cb.push_back(i + 1); acc = 0; }
     }
     const uint32_t nc = (uint32_t)cb.size() - 1;
+    const int src_pg = src_bytes >= (4u << 20) && is_pageable(src), dst_pg = dst_bytes >= (4u << 20) && is_pageable(dst);
     if (dict_len) CK(cudaMemcpyAsync(d_dict, dict, dict_len, cudaMemcpyHostToDevice, sk));
     if (stored_in) CK(cudaMemcpyAsync(d_stored, stored_in, n, cudaMemcpyHostToDevice, sk));
     CK(cudaMemcpyAsync(d_soff, soff.data(), (size_t)n * 8, cudaMemcpyHostToDevice, sk));
@@ -1045,7 +1205,7 @@ static int decompress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t 
     for (uint32_t c = 0; c < nc; ++c) {
         const uint32_t b0 = cb[c], b1 = cb[c + 1], m = b1 - b0;
         const uint64_t s_lo = soff[b0], s_hi = soff[b1 - 1] + src_len[b1 - 1];
-        if (s_hi > s_lo) CK(cudaMemcpyAsync(d_src + s_lo, src + s_lo, s_hi - s_lo, cudaMemcpyHostToDevice, si));
+        if (s_hi > s_lo) CKS(h2d(ctx, d_src + s_lo, src + s_lo, s_hi - s_lo, si, src_pg));
         CK(cudaEventRecord(ctx->evp[c], si));
         cudaStream_t sc = sks[c % lanes_used];
         CK(cudaStreamWaitEvent(sc, ctx->evp[c], 0));
@@ -1053,12 +1213,22 @@ static int decompress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t 
                               hist_mode == DLZ4_HIST_FRAME, stored_in ? d_stored + b0 : nullptr, d_olen + b0, d_status + b0, sc,
                               ctx->d_counter + 1 + (c % lanes_used)));
         CK(cudaEventRecord(ctx->evp[64 + c], sc));
+        if (dst_pg) continue;                                             // copied out below, chunk by chunk, once everything is queued
         CK(cudaStreamWaitEvent(so, ctx->evp[64 + c], 0));
         const uint64_t lo = dst_off[b0], hi = dst_off[b1 - 1] + dst_cap[b1 - 1];
         if (hi > lo) CK(cudaMemcpyAsync(dst + lo, d_dst + lo, hi - lo, cudaMemcpyDeviceToHost, so));
     }
     for (uint32_t l = 1; l < lanes_used; ++l) { CK(cudaEventRecord(ctx->ev_side, sks[l])); CK(cudaStreamWaitEvent(sk, ctx->ev_side, 0)); }
     CK(cudaEventRecord(ctx->ev1, sk));
+    if (dst_pg) {
+        // pageable destination: through the staging ring (a direct copy would block the host inside the loop above)
+        for (uint32_t c = 0; c < nc; ++c) {
+            const uint32_t b0 = cb[c], b1 = cb[c + 1];
+            CK(cudaStreamWaitEvent(so, ctx->evp[64 + c], 0));
+            const uint64_t lo = dst_off[b0], hi = dst_off[b1 - 1] + dst_cap[b1 - 1];
+            if (hi > lo) CKS(d2h(ctx, dst + lo, d_dst + lo, hi - lo, so, 1));
+        }
+    }
     CK(cudaMemcpyAsync(out_len, d_olen, (size_t)n * 4, cudaMemcpyDeviceToHost, sk));
     CK(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, sk));
     CK(cudaStreamSynchronize(sk));
@@ -1228,6 +1398,45 @@ int dlz4_xxh32_stream_dev(dlz4_ctx *ctx, const uint8_t *data, uint64_t len, uint
     return launch_xxh32_stream(ctx, data, len, seed, out, pick(ctx, stream));
 }
 
+// Whole-stream checksums of independent streams (the content checksums of the frames of a multi-frame job) are independent
+// serial chains: each runs as its own single-warp kernel on its own stream, beside the block kernels, and reads its bytes where
+// they already are -- device memory, or the caller's PAGE-LOCKED host memory directly over PCIe (no second upload).
+int dlz4_xxh32_async(dlz4_ctx *ctx, int slot, const uint8_t *data, uint64_t len, uint32_t seed) {
+    if (!ctx || slot < 0 || slot >= kSumSlots || (len && !data)) return DLZ4_E_INVALID_ARG;
+    if (len >= 0x80000000ull) return DLZ4_E_TOO_LARGE;       // xxhash32.js:23 len|0
+    CK(cudaSetDevice(ctx->device));
+    const uint8_t *dptr = data;
+    bool on_host = false;
+    if (len) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, data) != cudaSuccess) { cudaGetLastError(); return DLZ4_E_INVALID_ARG; }
+        if (a.type == cudaMemoryTypeUnregistered) return DLZ4_E_INVALID_ARG;      // pageable: the caller uses dlz4_xxh32 / _update
+        if (a.type == cudaMemoryTypeHost) {
+            void *dp = nullptr;
+            if (cudaHostGetDevicePointer(&dp, (void *)data, 0) != cudaSuccess) { cudaGetLastError(); return DLZ4_E_INVALID_ARG; }
+            dptr = (const uint8_t *)dp;
+            on_host = true;
+        }
+    }
+    if (!ctx->h_sum) CK(cudaHostAlloc((void **)&ctx->h_sum, kSumSlots * sizeof(uint32_t), cudaHostAllocMapped));
+    if (!ctx->sum_stream[slot]) CK(cudaStreamCreateWithFlags(&ctx->sum_stream[slot], cudaStreamNonBlocking));
+    void *res = nullptr;
+    CK(cudaHostGetDevicePointer(&res, ctx->h_sum + slot, 0));
+    if (on_host) k_xxh32_stream<3><<<1, 32, 0, ctx->sum_stream[slot]>>>(dptr, len, seed, (uint32_t *)res, nullptr, nullptr);
+    else k_xxh32_stream<1><<<1, 32, 0, ctx->sum_stream[slot]>>>(dptr, len, seed, (uint32_t *)res, nullptr, nullptr);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DLZ4_OK;
+}
+
+int dlz4_xxh32_wait(dlz4_ctx *ctx, int slot, uint32_t *out) {
+    if (!ctx || slot < 0 || slot >= kSumSlots || !out || !ctx->sum_stream[slot] || !ctx->h_sum) return DLZ4_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->sum_stream[slot]));
+    *out = ctx->h_sum[slot];
+    return DLZ4_OK;
+}
+
 int dlz4_xxh32(dlz4_ctx *ctx, const uint8_t *data, uint64_t len, uint32_t seed, uint32_t *out) {
     if (!ctx || !out) return DLZ4_E_INVALID_ARG;
     if (len >= 0x80000000ull) return DLZ4_E_TOO_LARGE;       // xxhash32.js:23 len|0
@@ -1346,12 +1555,12 @@ static int frame_body(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len, c
         CK(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_fork, 0));
         const uint64_t chunk = 1ull << kLandShift;
         for (uint64_t c = 0, o = 0; o < input_len; ++c, o += chunk) {
-            CK(cudaMemcpyAsync(d_in + o, input + o, (size_t)std::min<uint64_t>(chunk, input_len - o), cudaMemcpyHostToDevice, ctx->copy_in));
+            CKS(h2d(ctx, d_in + o, input + o, (size_t)std::min<uint64_t>(chunk, input_len - o), ctx->copy_in));
             CK(cudaMemcpyAsync(ctx->d_land + c, ctx->h_one, 4, cudaMemcpyHostToDevice, ctx->copy_in));
         }
         CK(cudaEventRecord(ctx->evp[0], ctx->copy_in));                 // whole input in memory
     } else if (input_len) {
-        CK(cudaMemcpyAsync(d_in, input, input_len, cudaMemcpyHostToDevice, st));
+        CKS(h2d(ctx, d_in, input, input_len, st));
     }
     if (dwin) CK(cudaMemcpyAsync(d_work, dictionary + (dict_len - dwin), dwin, cudaMemcpyHostToDevice, st));
 
@@ -1483,7 +1692,7 @@ int dlz4_frame_compress(dlz4_ctx *ctx, const uint8_t *input, uint64_t input_len,
     put(hdr, hp);
     if (seg_len) {
         if (pos < output_cap)
-            CK(cudaMemcpyAsync(output + pos, ctx->seg.p, (size_t)std::min<uint64_t>(seg_len, output_cap - pos), cudaMemcpyDeviceToHost, st));
+            CKS(d2h(ctx, output + pos, ctx->seg.p, (size_t)std::min<uint64_t>(seg_len, output_cap - pos), st));
         pos += seg_len;
     }
     uint8_t foot[8] = {0, 0, 0, 0, 0, 0, 0, 0};                           // EndMark (:244)
@@ -1517,7 +1726,7 @@ int dlz4_frame_body_fetch(dlz4_ctx *ctx, uint8_t *dst, uint64_t dst_cap) {
     if (!ctx || (ctx->res_body_len && !dst)) return DLZ4_E_INVALID_ARG;
     if (ctx->res_body_len > dst_cap) return DLZ4_E_OUTPUT_TOO_SMALL;
     CK(cudaSetDevice(ctx->device));
-    if (ctx->res_body_len) CK(cudaMemcpyAsync(dst, ctx->seg.p, ctx->res_body_len, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->res_body_len) CKS(d2h(ctx, dst, ctx->seg.p, ctx->res_body_len, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return DLZ4_OK;
 }
@@ -1533,7 +1742,7 @@ int dlz4_xxh32_update_resident(dlz4_ctx *ctx, dlz4_xxh32_state *s, int which) {
     const uint64_t body = len & ~15ull;
     if (body) {
         CK(cudaMemcpyAsync(ctx->d_hash + 4, s->v, 16, cudaMemcpyHostToDevice, st));
-        k_xxh32_stream<<<1, 32, 0, st>>>(d, body, s->seed, nullptr, ctx->d_hash + 4, ctx->d_hash + 8);
+        k_xxh32_stream<1><<<1, 32, 0, st>>>(d, body, s->seed, nullptr, ctx->d_hash + 4, ctx->d_hash + 8);
         ctx->launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(s->v, ctx->d_hash + 8, 16, cudaMemcpyDeviceToHost, st));
@@ -1775,14 +1984,14 @@ static int frame_decompress_impl(dlz4_ctx *ctx, const uint8_t *frame_in, uint64_
             const bool last = i + 1 == n;
             const uint64_t end = last ? frame_len : blocks[i + 1].off;           // (runs into the next block's size word: harmless)
             if (last || end - begin >= target) {
-                CK(cudaMemcpyAsync(d_frame + begin, frame + begin, end - begin, cudaMemcpyHostToDevice, ctx->copy_in));
+                CKS(h2d(ctx, d_frame + begin, frame + begin, end - begin, ctx->copy_in));
                 CK(cudaEventRecord(ctx->evp[kJdGroupEvent + groups.size() - 1], ctx->copy_in));
                 groups.push_back(i + 1);
                 begin = end;
             }
         }
     } else {
-        CK(cudaMemcpyAsync(d_frame, frame, frame_len, cudaMemcpyHostToDevice, st));
+        CKS(h2d(ctx, d_frame, frame, frame_len, st));
     }
     if (dwin) CK(cudaMemcpyAsync(d_dict, dictionary + (dict_len - dwin), dwin, cudaMemcpyHostToDevice, st));
 
@@ -1894,7 +2103,7 @@ static int frame_decompress_impl(dlz4_ctx *ctx, const uint8_t *frame_in, uint64_
     *output_len = total;
     if (total > output_cap) return DLZ4_E_OUTPUT_TOO_SMALL;
     if (block_out_len && n) CK(cudaMemcpyAsync(block_out_len, d_olen, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    if (total && !shipped) CK(cudaMemcpyAsync(output, d_out, total, cudaMemcpyDeviceToHost, st));
+    if (total && !shipped) CKS(d2h(ctx, output, d_out, total, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     ctx->res_out = d_out; ctx->res_out_len = total;
@@ -1939,7 +2148,7 @@ int dlz4_xxh32_update(dlz4_ctx *ctx, dlz4_xxh32_state *s, const uint8_t *data, u
     if (s->memsize) CK(cudaMemcpyAsync(d, s->mem, s->memsize, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d + s->memsize, data, from_data, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_hash + 4, s->v, 16, cudaMemcpyHostToDevice, st));
-    k_xxh32_stream<<<1, 32, 0, st>>>(d, body, s->seed, nullptr, ctx->d_hash + 4, ctx->d_hash + 8);
+    k_xxh32_stream<1><<<1, 32, 0, st>>>(d, body, s->seed, nullptr, ctx->d_hash + 4, ctx->d_hash + 8);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(s->v, ctx->d_hash + 8, 16, cudaMemcpyDeviceToHost, st));

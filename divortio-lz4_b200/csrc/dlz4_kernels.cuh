@@ -2160,6 +2160,9 @@ k_xxh32_batch(const uint8_t *__restrict__ base, const uint64_t *__restrict__ off
 
 // One hash over one long buffer: a single quad is the whole parallelism the algorithm has.  The other 28
 // lanes of the warp stage the stream through shared memory so the four chain lanes never wait on HBM.
+// kAhead: chunks of 4 KiB held in registers ahead of the chain -- 1 for device memory, 3 for page-locked HOST memory read
+// over PCIe (the content checksum of a frame whose bytes the caller already holds in pinned memory: ~2 us per round trip).
+template <int kAhead>
 __global__ void __launch_bounds__(32)
 k_xxh32_stream(const uint8_t *__restrict__ data, uint64_t len, uint32_t seed, uint32_t *out,
                const uint32_t *__restrict__ acc_in /* nullable: resume from 4 accumulators */,
@@ -2174,19 +2177,29 @@ k_xxh32_stream(const uint8_t *__restrict__ data, uint64_t len, uint32_t seed, ui
     if (aligned) {
         const uint4 *g = reinterpret_cast<const uint4 *>(data);
         const uint64_t nchunks = nstripes >> 8;                  // 256 stripes per chunk
-        uint4 r[8];
-        if (nchunks) {
+        uint4 r[kAhead][8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) r[u] = g[u * 32 + lane];
+        for (int j = 0; j < kAhead; ++j) {
+            if ((uint64_t)j < nchunks) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[j][u] = g[j * 256 + u * 32 + lane];
+            }
         }
         for (uint64_t c = 0; c < nchunks; ++c) {
+            // staged as x * P2 (:36-39's multiply, done here by all 32 lanes): the four chain lanes are left with a load and
+            // the two dependent multiply-adds per stripe
             uint4 *b4 = reinterpret_cast<uint4 *>(buf[c & 1]);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) b4[u * 32 + lane] = r[u];
-            if (c + 1 < nchunks) {
-                const uint4 *gn = g + (c + 1) * 256;
+            for (int u = 0; u < 8; ++u) b4[u * 32 + lane] = make_uint4(r[0][u].x * P32_2, r[0][u].y * P32_2, r[0][u].z * P32_2, r[0][u].w * P32_2);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) r[u] = gn[u * 32 + lane];
+            for (int j = 0; j + 1 < kAhead; ++j) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[j][u] = r[j + 1][u];
+            }
+            if (c + kAhead < nchunks) {
+                const uint4 *gn = g + (c + kAhead) * 256;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[kAhead - 1][u] = gn[u * 32 + lane];
             }
             __syncwarp();
             if (lane < 4) {
@@ -2195,10 +2208,10 @@ k_xxh32_stream(const uint8_t *__restrict__ data, uint64_t len, uint32_t seed, ui
                 // second multiply-add run side by side, two dependent operations per stripe.
                 const uint32_t *w = buf[c & 1] + lane;
                 constexpr uint32_t K1 = P32_1 << 13;
-                uint32_t a = v + w[0] * P32_2;
+                uint32_t a = v + w[0];
 #pragma unroll 16
                 for (int t = 1; t < 256; ++t) {
-                    const uint32_t y = w[t * 4] * P32_2;
+                    const uint32_t y = w[t * 4];
                     uint32_t c;                                 // fixed association (nvcc would re-order the sum into three links)
                     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(c) : "r"(a), "r"(K1), "r"(y));
                     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(a >> 19), "r"(P32_1), "r"(c));

@@ -14,10 +14,14 @@ One process per GPU, one `dlz4_ctx` each.  Independent blocks shard with no data
               whose inner blocks are not full, and every linked-block frame, is decoded whole by one rank (frames rotate over
               the ranks).  Ranks exchange decoded lengths and statuses (integers) per frame.
 
-The whole-stream content checksum is one serial chain (xxhash32.js:34-57, four non-associative accumulators): "replicas
-only".  It runs as a RELAY over the bytes already resident on each GPU -- rank r receives the 16-byte accumulator state
-from rank r-1, runs the stripe loop over its resident piece, passes the state on (dlz4_xxh32_update_resident) -- so nothing is
-uploaded twice, and it is timed separately from the block work.
+The whole-stream content checksum is one serial chain PER FRAME (xxhash32.js:34-57, four non-associative accumulators):
+"replicas only" inside a frame, but the chains of different frames are independent.  When the bytes to hash sit in
+page-locked host memory (the shared mappings of a multi-rank job, dlz4_pinned_alloc buffers) frame k's chain is started
+asynchronously on rank k mod world (dlz4_xxh32_async: a single-warp kernel on its own stream that reads the host bytes in
+place over PCIe) and runs beside the block work of that and the following frames; the digests are collected at the end.
+Otherwise (pageable buffers, more frames in flight than slots) it runs as a RELAY over the bytes already resident on each
+GPU -- rank r receives the 16-byte accumulator state from rank r-1, runs the stripe loop over its resident piece, passes the
+state on (dlz4_xxh32_update_resident) -- so nothing is uploaded twice.  Either way it is timed separately from the block work.
 
 `data`, `frames` and `out` are numpy uint8 arrays every rank can address: the same page-locked shared mapping in a multi-process
 run (`SharedBuffer`), plain arrays in a single process.  Communication goes through a small `comm` object (torch.distributed
@@ -245,6 +249,20 @@ class GpuBackend(object):
     def state_digest(self, state):
         return int(api.lib().dlz4_xxh32_digest(C.byref(state)))
 
+    SUM_SLOTS = 32
+
+    def sum_async(self, slot, piece):
+        """Starts xxh32(piece) in `slot` (dlz4_xxh32_async); False when the bytes are not page-locked (caller falls back)."""
+        st = api.lib().dlz4_xxh32_async(self.ctx.handle, int(slot), api._ptr(piece), piece.size, 0)
+        if st == api.E_CUDA:
+            self.ctx.check(st)
+        return st == 0
+
+    def sum_wait(self, slot):
+        h = C.c_uint32()
+        self.ctx.check(api.lib().dlz4_xxh32_wait(self.ctx.handle, int(slot), C.byref(h)))
+        return int(h.value)
+
     def decompress_range(self, frame, first, count, out, verify_block_checksums=False):
         """-> (status, decoded bytes, per-block decoded lengths)."""
         n = C.c_uint64()
@@ -280,7 +298,20 @@ def compress_sharded(data, out, max_block_size=4194304, content_checksum=False, 
     bs, frames = plan(data.size, max_block_size, world, frame_max)
     pos = 0
     t_blocks = t_sum = 0.0
-    for lo, hi, nblocks, ranks in frames:
+    # content checksums: frame k's chain on rank k mod world, started now, collected behind the block loop
+    async_sum = {}                                 # frame index -> slot (on its owner)
+    use_async = 0
+    if content_checksum and hasattr(backend, "sum_async") and len(frames) <= backend.SUM_SLOTS * world:
+        ok = 1
+        for k, (lo, hi, _, _) in enumerate(frames):
+            if k % world == rank:
+                if ok and backend.sum_async(k // world, data[lo:hi]):
+                    async_sum[k] = k // world
+                else:
+                    ok = 0
+        use_async = int(all(v[0] for v in comm.all_gather_ints([ok])))     # all or nothing: every rank takes the same path
+    sum_at = {}                                    # frame index -> position of its checksum in `out`
+    for k, (lo, hi, nblocks, ranks) in enumerate(frames):
         t0 = time.perf_counter()
         first, count, blo, bhi = ranks[rank]
         body_len = backend.body_compress(data[blo:bhi], bs, block_checksum) if count else 0
@@ -298,7 +329,9 @@ def compress_sharded(data, out, max_block_size=4194304, content_checksum=False, 
             out[pos:body_pos] = np.frombuffer(header, dtype=np.uint8)
             out[body_pos + total_body:body_pos + total_body + 4] = 0              # EndMark (bufferCompress.js:244)
         t1 = time.perf_counter()
-        if content_checksum:                                                      # :248-252, serial: relay in rank order
+        if content_checksum and use_async:
+            sum_at[k] = end - 4
+        elif content_checksum:                                                    # :248-252, serial: relay in rank order
             state = backend.state_new() if rank == 0 else _state_from(comm.recv_bytes(STATE_BYTES, rank - 1))
             if count:
                 backend.state_update_input(state)
@@ -311,10 +344,20 @@ def compress_sharded(data, out, max_block_size=4194304, content_checksum=False, 
         t_blocks += t1 - t0
         t_sum += t2 - t1
         pos = end
+    t2 = time.perf_counter()
+    if use_async:
+        for k, slot in async_sum.items():
+            h = backend.sum_wait(slot)
+            out[sum_at[k]:sum_at[k] + 4] = np.frombuffer(int(h).to_bytes(4, "little"), dtype=np.uint8)
+    elif async_sum:
+        for slot in async_sum.values():            # started but not used (another rank could not): let them finish
+            backend.sum_wait(slot)
+    t_sum += time.perf_counter() - t2
     comm.barrier()
     if timings is not None:
         timings["blocks"] = t_blocks
         timings["checksum"] = t_sum
+        timings["checksum_mode"] = "one chain per frame, asynchronous, from page-locked host memory" if use_async else "relay over resident bytes"
     return pos
 
 
@@ -348,7 +391,16 @@ def decompress_sharded(frames, out, verify_checksum=True, verify_block_checksums
     rank, world = comm.rank, comm.world
     base = 0
     t_blocks = t_sum = 0.0
-    for k, (fpos, info) in enumerate(list_frames(f)):
+    flist = list_frames(f)
+    # content checksums of different frames are independent chains: asynchronous, on the frame's owner, over the decoded bytes
+    # where they land in (page-locked) `out`; verified behind the frame loop
+    use_async = int(verify_checksum and hasattr(backend, "sum_async") and len(flist) <= backend.SUM_SLOTS * world
+                    and out.size >= 16 and backend.sum_async(0, out[:16]))
+    if use_async:
+        backend.sum_wait(0)
+    use_async = int(all(v[0] for v in comm.all_gather_ints([use_async])))
+    pending = []                                   # (slot, expected digest) on this rank
+    for k, (fpos, info) in enumerate(flist):
         t0 = time.perf_counter()
         fr = f[fpos:fpos + int(info.frame_bytes)]
         n, B = int(info.nblocks), int(info.block_max_size)
@@ -377,7 +429,12 @@ def decompress_sharded(frames, out, verify_checksum=True, verify_block_checksums
             raise api.LZ4Error(bad[0], api.lib().dlz4_strerror(bad[0]).decode())
         total = sum(r[1] for r in res)
         t1 = time.perf_counter()
-        if info.has_content_checksum and verify_checksum:                         # bufferDecompress.js:213-217, serial relay
+        if info.has_content_checksum and verify_checksum and use_async:
+            if rank == owner:
+                if not backend.sum_async(k // world, out[base:base + total]):
+                    raise RuntimeError("dlz4_xxh32_async refused a buffer it accepted before")
+                pending.append((k // world, int.from_bytes(fr[fr.size - 4:].tobytes(), "little")))
+        elif info.has_content_checksum and verify_checksum:                       # bufferDecompress.js:213-217, serial relay
             order = list(range(world)) if sharded else [owner]
             ok = 1
             if rank in order:
@@ -395,10 +452,17 @@ def decompress_sharded(frames, out, verify_checksum=True, verify_block_checksums
         t_blocks += t1 - t0
         t_sum += t2 - t1
         base += total
+    t2 = time.perf_counter()
+    if use_async:
+        ok = int(all(backend.sum_wait(slot) == want for slot, want in pending))
+        if not all(r[0] for r in comm.all_gather_ints([ok])):
+            raise api.LZ4Error(api.E_CONTENT_CHECKSUM, "LZ4: Content Checksum Error")
+    t_sum += time.perf_counter() - t2
     comm.barrier()
     if timings is not None:
         timings["blocks"] = t_blocks
         timings["checksum"] = t_sum
+        timings["checksum_mode"] = "one chain per frame, asynchronous, from page-locked host memory" if use_async else "relay over resident bytes"
     return base
 
 

@@ -146,6 +146,12 @@ int dlz4_xxh32_batch_dev(dlz4_ctx *ctx, const uint8_t *base, const uint64_t *off
                          uint32_t seed, uint32_t *out, void *stream);
 int dlz4_xxh32_stream_dev(dlz4_ctx *ctx, const uint8_t *data, uint64_t len, uint32_t seed, uint32_t *out, void *stream);
 int dlz4_xxh32(dlz4_ctx *ctx, const uint8_t *data, uint64_t len, uint32_t seed, uint32_t *out);
+/* The same hash started asynchronously in one of 32 slots, each a serial chain on its own stream (xxhash32.js:34-57 is one
+ * chain per stream; the content checksums of DIFFERENT frames, bufferCompress.js:248-252, are independent).  data: a device
+ * pointer or PAGE-LOCKED host memory (dlz4_pinned_alloc / dlz4_host_register), which the kernel reads in place over PCIe;
+ * pageable memory is refused with DLZ4_E_INVALID_ARG.  dlz4_xxh32_wait blocks until the slot's hash is there. */
+int dlz4_xxh32_async(dlz4_ctx *ctx, int slot, const uint8_t *data, uint64_t len, uint32_t seed);
+int dlz4_xxh32_wait(dlz4_ctx *ctx, int slot, uint32_t *out);
 int dlz4_xxh32_batch(dlz4_ctx *ctx, const uint8_t *base, uint64_t base_bytes, const uint64_t *off,
                      const uint32_t *len, uint32_t n, uint32_t seed, uint32_t *out);
 

@@ -69,7 +69,7 @@ def test_config3_shape_4m_blocks_block_and_content_checksums(env):
     assert got_n == n and np.array_equal(back[:n], host)
 
 
-def _run_thread_ranks(dl, world, host, out, back, bs, cc, bc, frame_max=None):
+def _run_thread_ranks(dl, world, host, out, back, bs, cc, bc, frame_max=None, modes=None):
     """compress_sharded + decompress_sharded with `world` ranks emulated by threads (own dlz4_ctx each) on this GPU."""
     import threading
     from divortio_lz4_b200 import sharded
@@ -81,9 +81,12 @@ def _run_thread_ranks(dl, world, host, out, back, bs, cc, bc, frame_max=None):
         try:
             be = sharded.GpuBackend(dl.Context(0))
             kw = {} if frame_max is None else {"frame_max": frame_max}
-            t = sharded.compress_sharded(host, out, bs, cc, True, bc, comm=comms[r], backend=be, **kw)
-            g = sharded.decompress_sharded(out[:t], back, True, bc, comm=comms[r], backend=be)
+            tm1, tm2 = {}, {}
+            t = sharded.compress_sharded(host, out, bs, cc, True, bc, comm=comms[r], backend=be, timings=tm1, **kw)
+            g = sharded.decompress_sharded(out[:t], back, True, bc, comm=comms[r], backend=be, timings=tm2)
             res[r] = (t, g)
+            if modes is not None:
+                modes.append((tm1["checksum_mode"], tm2["checksum_mode"]))
         except Exception as e:  # noqa: BLE001
             err.append(e)
             comms[r].s.bar.abort()
@@ -116,6 +119,54 @@ def test_sharded_multi_frame_and_ragged_world_sizes(env):
         assert got_n == n and np.array_equal(back[:n], host)
         # any frame reader decodes the concatenation as one stream
         assert dl.decompressFrames(out[:total])[0] == host.tobytes()
+
+
+def test_sharded_frames_in_page_locked_buffers_hash_one_chain_per_frame(env):
+    """With page-locked host buffers the content checksum of every frame is its own asynchronous chain (dlz4_xxh32_async, read
+    in place over PCIe) instead of the rank-to-rank relay; same bytes either way.  Also the slots on their own: device memory,
+    page-locked memory, pageable memory refused, a corrupted checksum detected."""
+    import ctypes as C
+    dl, corpus, dev, torch, ctx = env
+    from divortio_lz4_b200 import api, sharded
+    n = 70 * 1024 * 1024 + 333
+    fm = 16 << 20
+    host = corpus.mixed(17, n)
+    want = b"".join(oracle.compress_buffer(host[lo:hi], None, 65536, True, True, True, None, True) for lo, hi in sharded.frame_spans(n, fm))
+    out = np.zeros(len(want) + 4096, dtype=np.uint8)
+    back = np.zeros(n + 64, dtype=np.uint8)
+    bufs = (host, out, back)
+    assert all(api.host_register(b) for b in bufs)
+    try:
+        modes = []
+        total, got_n = _run_thread_ranks(dl, 2, host, out, back, 65536, True, True, frame_max=fm, modes=modes)
+        assert bytes(out[:total].tobytes()) == want
+        assert got_n == n and np.array_equal(back[:n], host)
+        assert all(m[0].startswith("one chain per frame") and m[1].startswith("one chain per frame") for m in modes), modes
+        # the slots directly
+        L = dl.lib()
+        h = C.c_uint32()
+        for slot, lo, ln in ((0, 0, n), (5, 12345, 1 << 20), (31, 7, 15), (2, 100, 0)):
+            assert L.dlz4_xxh32_async(ctx.handle, slot, api._ptr(host[lo:]), ln, 0) == 0
+        for slot, lo, ln in ((0, 0, n), (5, 12345, 1 << 20), (31, 7, 15), (2, 100, 0)):
+            assert L.dlz4_xxh32_wait(ctx.handle, slot, C.byref(h)) == 0
+            assert h.value == oracle.xxh32(host[lo:lo + ln]), (slot, lo, ln)
+        d = torch.from_numpy(host[:1 << 22]).to(torch.device("cuda", ctx.device))
+        assert L.dlz4_xxh32_async(ctx.handle, 1, d.data_ptr() + 3, (1 << 22) - 3, 9) == 0
+        assert L.dlz4_xxh32_wait(ctx.handle, 1, C.byref(h)) == 0 and h.value == oracle.xxh32(host[3:1 << 22], 9)
+        assert L.dlz4_xxh32_async(ctx.handle, 1, api._ptr(np.zeros(1 << 20, dtype=np.uint8)), 1 << 20, 0) == 20      # pageable: DLZ4_E_INVALID_ARG
+        # a wrong content checksum is still found (every rank raises)
+        bad = out[:total].copy()
+        bad[total - 1] ^= 0x55
+        assert api.host_register(bad)
+        try:
+            with pytest.raises(Exception) as ei:
+                sharded.decompress_sharded(bad, back, True, False, comm=sharded.LocalComm(), backend=sharded.GpuBackend(ctx))
+            assert "Content Checksum Error" in str(ei.value)
+        finally:
+            api.host_unregister(bad)
+    finally:
+        for b in bufs:
+            api.host_unregister(b)
 
 
 def _two_gpu_worker(rank, world, port, tag, q):
