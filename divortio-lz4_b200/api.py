@@ -489,5 +489,15 @@ class _LZ4(object):
         from .worker import LZ4Worker
         return LZ4Worker.decompress(data, options)
 
+    @staticmethod
+    def compressWorkerStream(readable, writable, options=None):    # src/lz4.js:58 (LZ4Worker.compressStream)
+        from .worker import LZ4Worker
+        return LZ4Worker.compressStream(readable, writable, options)
+
+    @staticmethod
+    def decompressWorkerStream(readable, writable, options=None):  # src/lz4.js:59
+        from .worker import LZ4Worker
+        return LZ4Worker.decompressStream(readable, writable, options)
+
 
 LZ4 = _LZ4()

@@ -141,6 +141,9 @@ struct dlz4_ctx {
     uint32_t seg_jobs = 0, seg_reruns = 0, seg_rounds = 0;   // last segment-parallel call: segments, re-run segments, rounds
     uint64_t launches = 0;
     float last_ms = 0.f;
+    // measurement knobs, read from the environment ONCE in dlz4_init (A/B runs; none changes an output byte).  -1 / 0 = automatic
+    int64_t k_seg_kib = -1, k_seg_warm_kib = -1, k_seg_unit_kib = -1;
+    int k_seg_group = -1, k_seg_no_chase = 0, k_jd_unit_mib = 0, k_jd_serial_scan = 0, k_jd_no_overlap = 0, k_debug = 0;
     CopyPool *pool = nullptr;           // host copy threads (pageable caller buffers), created on first use
     int copy_threads = 0;               // 0: min(8, hardware threads / 2)
     uint8_t *stage[kStageSlots] = {};   // page-locked staging ring
@@ -462,9 +465,9 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
         if (fit <= (320 << 10)) S = std::max(S, fit);
         else while (S < total / 2048) S <<= 1;
     }
-    if (const char *e = getenv("DLZ4_SEG_KIB")) S = (int64_t)std::max(64, atoi(e)) << 10;
+    if (ctx->k_seg_kib >= 0) S = std::max<int64_t>(64, ctx->k_seg_kib) << 10;
     int64_t W = 512 << 10;
-    if (const char *e = getenv("DLZ4_SEG_WARM_KIB")) W = (int64_t)std::max(0, atoi(e)) << 10;
+    if (ctx->k_seg_warm_kib >= 0) W = ctx->k_seg_warm_kib << 10;
     if (!linked && S > B) S = B;
     // Groups: the chains on shared-memory tables (one per CTA) run about 1.5 times as fast as those on L2 tables when the
     // device is full, so once there are more segments than such slots, G consecutive segments form a group that one
@@ -475,13 +478,13 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
     // re-runs S bytes only.
     const int64_t slots = (int64_t)ctx->sm_count * kSegCtasPerSm;
     int64_t G = (total + S - 1) / S > slots ? std::max<int64_t>(2, (W + 3 * S) / (2 * S)) : 0;
-    if (const char *e = getenv("DLZ4_SEG_GROUP")) G = std::max(0, atoi(e));
+    if (ctx->k_seg_group >= 0) G = ctx->k_seg_group;
     if (G < 2) G = 0;
     // Verification unit U <= S: a warp's stretch of S bytes is itself a run of S/U segments (kSegCont / kSegMore), so that a
     // failed speculation re-runs U bytes, not S: the re-run converges to the speculative run's state within the unit and
     // the next member's snapshot then verifies (DLZ4_SEG_UNIT_KIB, 0 = S)
     int64_t U = S % (128 << 10) == 0 ? (128 << 10) : S % (64 << 10) == 0 ? (64 << 10) : S;
-    if (const char *e = getenv("DLZ4_SEG_UNIT_KIB")) { const int64_t u = (int64_t)atoi(e) << 10; U = u > 0 && S % u == 0 ? u : S; }
+    if (ctx->k_seg_unit_kib >= 0) { const int64_t u = ctx->k_seg_unit_kib << 10; U = u > 0 && S % u == 0 ? u : S; }
     const int64_t gs = S / U;
     std::vector<SegJob> jobs;
     std::vector<uint32_t> heads, singles;                  // first-launch queues (job indices)
@@ -594,7 +597,7 @@ int compress_segmented(dlz4_ctx *ctx, const uint8_t *d_work, int64_t start, int6
             for (uint32_t j : list) jobs[j].flags |= kSegRerun;
             CK(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nj * sizeof(SegJob), cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(d_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, st));
-            CKS(launch(d_list, (uint32_t)list.size(), nullptr, 0, 0, getenv("DLZ4_SEG_NO_CHASE") ? nullptr : d_bad));
+            CKS(launch(d_list, (uint32_t)list.size(), nullptr, 0, 0, ctx->k_seg_no_chase ? nullptr : d_bad));
             uint32_t chased = 0;
             CK(cudaMemcpyAsync(&chased, counter + 2, 4, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));                                // `list` / `jobs` are reused next round
@@ -627,7 +630,7 @@ int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, uint64_t frame_span, 
     // 16 MiB units; 32 MiB for frames of half a GiB and more (fewer launches; the first unit ships later, which only a long
     // frame can afford: 1 GiB 40.2 -> 38.2 ms, 128 MiB 5.8 -> 6.0 ms)
     uint32_t unit_bytes = (uint64_t)n * B >= (512ull << 20) ? 32u << 20 : 16u << 20;
-    if (const char *e = getenv("DLZ4_JD_UNIT_MIB")) unit_bytes = (uint32_t)std::max(1, atoi(e)) << 20;
+    if (ctx->k_jd_unit_mib > 0) unit_bytes = (uint32_t)ctx->k_jd_unit_mib << 20;
     const uint32_t per_unit = std::max<uint32_t>(1u, unit_bytes / B);
     const uint32_t nunits = (n + per_unit - 1) / per_unit;
     int rounds = 1;
@@ -640,7 +643,7 @@ int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, uint64_t frame_span, 
     const size_t o_todo = carve((size_t)nunits * (rounds + 2) * 4);
     const size_t ntiles = ((size_t)per_unit * B + kJdTile - 1) / kJdTile, o_tile = carve(ntiles);
     // chunked (parallel) token scan for blocks > 64 KiB: per-byte next/advance, per-byte chunk exits, run and slow-token lists
-    const bool chunked = B > 65536 && !getenv("DLZ4_JD_SERIAL_SCAN");
+    const bool chunked = B > 65536 && !ctx->k_jd_serial_scan;
     uint64_t fspan = 0;
     uint32_t max_slen = 0;
     std::vector<uint64_t> list_base(n + 1, 0);
@@ -691,7 +694,7 @@ int decompress_jump(dlz4_ctx *ctx, const uint8_t *d_frame, uint64_t frame_span, 
         k_jd_scan<<<scan_grid, 128, 0, st>>>(d_frame, d_soff, d_slen, d_stored, n, B, d_seq, d_sb, d_ns, d_olen, d_reach, d_status,
                                              ctx->d_counter, d_fb);
         ctx->launches += 5;
-        if (getenv("DLZ4_DEBUG")) {
+        if (ctx->k_debug) {
             std::vector<uint32_t> nr(n), nsl(n); std::vector<uint8_t> fb(n);
             CK(cudaMemcpyAsync(nr.data(), d_nr, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(nsl.data(), d_nsl, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
@@ -779,6 +782,16 @@ int dlz4_init(int device, dlz4_ctx **out) {
     CK(cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     for (cudaStream_t &l : ctx->lanes) CK(cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking));
+    // every environment knob is read here, once (the reference has no configuration surface: these exist for A/B measurements)
+    if (const char *e = getenv("DLZ4_SEG_KIB")) ctx->k_seg_kib = std::max(0, atoi(e));
+    if (const char *e = getenv("DLZ4_SEG_WARM_KIB")) ctx->k_seg_warm_kib = std::max(0, atoi(e));
+    if (const char *e = getenv("DLZ4_SEG_UNIT_KIB")) ctx->k_seg_unit_kib = std::max(0, atoi(e));
+    if (const char *e = getenv("DLZ4_SEG_GROUP")) ctx->k_seg_group = std::max(0, atoi(e));
+    ctx->k_seg_no_chase = getenv("DLZ4_SEG_NO_CHASE") != nullptr;
+    if (const char *e = getenv("DLZ4_JD_UNIT_MIB")) ctx->k_jd_unit_mib = std::max(1, atoi(e));
+    ctx->k_jd_serial_scan = getenv("DLZ4_JD_SERIAL_SCAN") != nullptr;
+    ctx->k_jd_no_overlap = getenv("DLZ4_JD_NO_OVERLAP") != nullptr;
+    ctx->k_debug = getenv("DLZ4_DEBUG") != nullptr;
     if (const char *e = getenv("DLZ4_CHUNK_MIB")) ctx->chunk_bytes = (uint64_t)std::max(1, atoi(e)) << 20;
     if (const char *e = getenv("DLZ4_LANES")) ctx->n_lanes = std::min(4, std::max(1, atoi(e)));
     if (const char *e = getenv("DLZ4_COPY_THREADS")) ctx->copy_threads = std::min(64, std::max(1, atoi(e)));
@@ -1240,13 +1253,64 @@ static int decompress_blocks_packed(dlz4_ctx *ctx, const uint8_t *src, uint64_t 
     return DLZ4_OK;
 }
 
+// Device-resident batch decode: one warp per block, or the jump decoder for few large blocks.
+static int decompress_dev_routed(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len, uint32_t nblocks,
+                                 uint8_t *dst, const uint64_t *dst_off, const uint32_t *dst_cap, const uint8_t *dict, uint32_t dict_len,
+                                 int hist_mode, uint32_t *out_len, uint8_t *status, cudaStream_t st) {
+    if (nblocks && nblocks <= 65536 && hist_mode != DLZ4_HIST_FRAME && !dict_len) {
+        // few large blocks: one warp per block decodes a 4 MiB block at ~40 MB/s.  If the batch is the usual one -- uniform blocks
+        // > 64 KiB tiling one output range -- the jump decoder takes it (token scan and pointer doubling in parallel inside
+        // every block).  The descriptors live on the device: read them back.
+        std::vector<uint64_t> so(nblocks), doff(nblocks);
+        std::vector<uint32_t> sl(nblocks), cap(nblocks);
+        CK(cudaMemcpyAsync(cap.data(), dst_cap, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(doff.data(), dst_off, (size_t)nblocks * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint64_t B = cap[0];
+        bool uniform = B > 65536 && B <= 4194304 && (B & (B - 1)) == 0;
+        for (uint32_t i = 0; uniform && i < nblocks; ++i)
+            uniform = doff[i] == doff[0] + (uint64_t)i * B && (cap[i] == B || (i + 1 == nblocks && cap[i] <= B && cap[i] > 0));
+        if (uniform) {
+            CK(cudaMemcpyAsync(so.data(), src_off, (size_t)nblocks * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(sl.data(), src_len, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            uint64_t span = 0;
+            for (uint32_t i = 0; i < nblocks; ++i) { span = std::max<uint64_t>(span, so[i] + sl[i]); uniform = uniform && sl[i] > 0; }
+            if (uniform && span < 0x7FFF0000ull) {
+                CKS(reserve(ctx, ctx->seg, (size_t)nblocks + 256));        // (meta holds the host variant's descriptors, aux the decoder's scratch)
+                uint8_t *d_stored = (uint8_t *)ctx->seg.p;
+                CK(cudaMemsetAsync(d_stored, 0, nblocks, st));
+                const uint64_t cap_total = (uint64_t)(nblocks - 1) * B + cap[nblocks - 1];
+                std::vector<uint8_t> status_h;
+                uint64_t total = 0;
+                CKS(decompress_jump(ctx, src, span, src_off, src_len, d_stored, sl, nblocks, (uint32_t)B, dst + doff[0], cap_total, nullptr, 0,
+                                    false, out_len, status, status_h, &total, st, nullptr, 0, nullptr));
+                bool clean = true;
+                for (uint32_t i = 0; i < nblocks; ++i) clean = clean && status_h[i] == 0;
+                if (clean) {
+                    // block i was written at the running sum of the decoded lengths: that is dst_off[i] only if every inner block is full
+                    std::vector<uint32_t> ol(nblocks);
+                    CK(cudaMemcpyAsync(ol.data(), out_len, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));
+                    for (uint32_t i = 0; clean && i + 1 < nblocks; ++i) clean = ol[i] == B;
+                    clean = clean && ol[nblocks - 1] <= cap[nblocks - 1];
+                }
+                if (clean) return DLZ4_OK;
+                // short inner blocks, or a block in error: one warp per block places and reports each on its own
+            }
+        }
+    }
+    return launch_decompress(ctx, src, src_off, src_len, nblocks, dst, dst_off, dst_cap, dict_len ? dict : nullptr, dict_len,
+                             hist_mode == DLZ4_HIST_FRAME, nullptr, out_len, status, st);
+}
+
 int dlz4_decompress_blocks_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len, uint32_t nblocks,
                                uint8_t *dst, const uint64_t *dst_off, const uint32_t *dst_cap, const uint8_t *dict, uint32_t dict_len,
                                int hist_mode, uint32_t *out_len, uint8_t *status, void *stream) {
     if (!ctx) return DLZ4_E_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
-    return launch_decompress(ctx, src, src_off, src_len, nblocks, dst, dst_off, dst_cap, dict_len ? dict : nullptr, dict_len,
-                             hist_mode == DLZ4_HIST_FRAME, nullptr, out_len, status, pick(ctx, stream));
+    return decompress_dev_routed(ctx, src, src_off, src_len, nblocks, dst, dst_off, dst_cap, dict, dict_len, hist_mode, out_len, status,
+                                 pick(ctx, stream));
 }
 
 int dlz4_decompress_blocks(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_bytes, const uint64_t *src_off, const uint32_t *src_len,
@@ -1280,19 +1344,19 @@ int dlz4_decompress_blocks(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_bytes
     uint64_t *d_soff = (uint64_t *)ctx->meta.p, *d_doff = d_soff + nblocks;
     uint32_t *d_slen = (uint32_t *)(d_doff + nblocks), *d_cap = d_slen + nblocks, *d_olen = d_cap + nblocks;
     uint8_t *d_status = (uint8_t *)(d_olen + nblocks);
-    CK(cudaMemcpyAsync(d_src, src, src_bytes, cudaMemcpyHostToDevice, st));
+    CKS(h2d(ctx, d_src, src, src_bytes, st));
     if (dict_len) CK(cudaMemcpyAsync(d_dict, dict, dict_len, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_soff, src_off, (size_t)nblocks * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_doff, dst_off, (size_t)nblocks * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_slen, src_len, (size_t)nblocks * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_cap, dst_cap, (size_t)nblocks * 4, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->ev0, st));
-    CKS(launch_decompress(ctx, d_src, d_soff, d_slen, nblocks, d_dst, d_doff, d_cap, dict_len ? d_dict : nullptr, dict_len,
-                          hist_mode == DLZ4_HIST_FRAME, nullptr, d_olen, d_status, st));
+    CKS(decompress_dev_routed(ctx, d_src, d_soff, d_slen, nblocks, d_dst, d_doff, d_cap, dict_len ? d_dict : nullptr, dict_len, hist_mode,
+                              d_olen, d_status, st));
     CK(cudaEventRecord(ctx->ev1, st));
     CK(cudaMemcpyAsync(out_len, d_olen, (size_t)nblocks * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(status, d_status, nblocks, cudaMemcpyDeviceToHost, st));
-    if (dst_bytes) CK(cudaMemcpyAsync(dst, d_dst, dst_bytes, cudaMemcpyDeviceToHost, st));
+    CKS(d2h(ctx, dst, d_dst, dst_bytes, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     for (uint32_t i = 0; i < nblocks; ++i)
@@ -1975,8 +2039,8 @@ static int frame_decompress_impl(dlz4_ctx *ctx, const uint8_t *frame_in, uint64_
     // of a group starts when it has landed (decompress_jump), the rest of the decoder waits for all of them through `st`.
     std::vector<uint32_t> groups;
     const bool jump_scan = n && frame_len >= ctx->jump_min_bytes && (!info.block_independence || (B > 65536 && n < 1024)) && B > 65536 &&
-                           !getenv("DLZ4_JD_SERIAL_SCAN");
-    if (jump_scan && frame_len >= (8ull << 20) && !((flags & 2u) && info.has_block_checksum) && !getenv("DLZ4_JD_NO_OVERLAP")) {
+                           !ctx->k_jd_serial_scan;
+    if (jump_scan && frame_len >= (8ull << 20) && !((flags & 2u) && info.has_block_checksum) && !ctx->k_jd_no_overlap) {
         const uint64_t target = std::max<uint64_t>(4ull << 20, (frame_len + 14) / 15);      // <= 16 groups
         uint64_t begin = 0;
         groups.push_back(0);

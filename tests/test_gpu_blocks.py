@@ -83,6 +83,53 @@ def test_compress_large_blocks_use_int32_table(dl, bs):
         assert np.array_equal(dst[int(doff[i]):int(doff[i]) + int(clen[i])], odst[int(odoff[i]):int(odoff[i]) + int(oclen[i])]), i
 
 
+@pytest.mark.parametrize("bs", [262144, 1048576, 4194304])
+def test_decompress_large_blocks_batch_api_jump_decoder_and_fallbacks(dl, bs):
+    """Few large blocks through the batch API: uniform batches take the jump decoder (host and device variants), ragged ones
+    (a short inner block, scattered destinations) and a malformed block take one warp per block; same bytes, same statuses."""
+    import torch
+    from divortio_lz4_b200 import corpus, device as dev
+    n = 5 * bs + 4321
+    data = corpus.mixed(bs + 1, n)
+    off = np.arange(0, n, bs, dtype=np.uint64)
+    ln = np.minimum(bs, n - off).astype(np.uint32)
+    dst, doff, clen = oracle.compress_blocks(data, off, ln)
+    out, olen, st = dl.decompress_blocks(dst, doff, clen, off, ln)
+    assert not st.any() and np.array_equal(olen, ln) and np.array_equal(out[:n], data)
+    # device variant
+    ctx = dl.default_context()
+    d = torch.device("cuda", ctx.device)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(d)
+    d_out = torch.zeros(n + 64, dtype=torch.uint8, device=d)
+    d_olen = torch.zeros(len(off), dtype=torch.int32, device=d)
+    d_st = torch.zeros(len(off), dtype=torch.uint8, device=d)
+    dev.decompress_blocks_dev(ctx, t(dst), t(doff.view(np.int64)), t(clen.view(np.int32)), d_out, t(off.view(np.int64)), t(ln.view(np.int32)), d_olen, d_st)
+    torch.cuda.synchronize()
+    assert int(d_st.max()) == 0 and np.array_equal(d_out[:n].cpu().numpy(), data)
+    # a short inner block: blocks 0..5 where block 2 holds only half a block of data, destinations still i * bs
+    pieces = [data[i * bs:(i + 1) * bs] for i in range(2)] + [data[2 * bs:2 * bs + bs // 2]] + [data[3 * bs:4 * bs]]
+    poff = np.zeros(len(pieces), dtype=np.uint64)
+    pl = np.array([p.size for p in pieces], dtype=np.uint32)
+    poff[1:] = np.cumsum(pl.astype(np.uint64))[:-1]
+    src = np.concatenate(pieces)
+    cdst, cdoff, cclen = oracle.compress_blocks(src, poff, pl)
+    where = np.arange(len(pieces), dtype=np.uint64) * bs
+    caps = np.full(len(pieces), bs, dtype=np.uint32)
+    out2, olen2, st2 = dl.decompress_blocks(cdst, cdoff, cclen, where, caps)
+    assert not st2.any() and np.array_equal(olen2, pl)
+    for i, p in enumerate(pieces):
+        assert np.array_equal(out2[int(where[i]):int(where[i]) + p.size], p), i
+    # a malformed block among good ones: its own status, the others decode
+    bad = dst.copy()
+    bad[int(doff[1]) + int(clen[1]) // 2:int(doff[1]) + int(clen[1])] = 0
+    out3, olen3, st3 = dl.decompress_blocks(bad, doff, clen, off, ln, check=False)
+    oo, ool, ost = oracle.decompress_blocks(bad, doff, clen, off, ln)
+    assert np.array_equal(st3.astype(np.int64), np.abs(ost.astype(np.int64)))      # the oracle reports -status
+    for i in range(len(off)):
+        if not ost[i]:
+            assert np.array_equal(out3[int(off[i]):int(off[i]) + int(ln[i])], data[int(off[i]):int(off[i]) + int(ln[i])]), i
+
+
 def test_compress_with_shared_prefix_three_table_modes(dl):
     """BASELINE config 4 at test size: 4 KiB JSON messages with a 64 KiB dictionary as shared prefix."""
     from divortio_lz4_b200 import corpus

@@ -19,7 +19,8 @@ def dl():
 
 
 class seg_env:
-    """DLZ4_SEG_KIB / DLZ4_SEG_WARM_KIB are read by every call."""
+    """DLZ4_SEG_KIB / DLZ4_SEG_WARM_KIB ... are read once, by dlz4_init: the default context is replaced by one created under
+    the wanted environment and dropped again on exit."""
 
     def __init__(self, seg_kib=None, warm_kib=None, group=None, unit_kib=None):
         self.new = {"DLZ4_SEG_KIB": seg_kib, "DLZ4_SEG_WARM_KIB": warm_kib, "DLZ4_SEG_GROUP": group, "DLZ4_SEG_UNIT_KIB": unit_kib}
@@ -31,6 +32,7 @@ class seg_env:
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = str(v)
+        self._fresh()
 
     def __exit__(self, *a):
         for k, v in self.old.items():
@@ -38,6 +40,12 @@ class seg_env:
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+        self._fresh()
+
+    @staticmethod
+    def _fresh():
+        from divortio_lz4_b200 import api
+        api._default.clear()                                    # (contexts other modules still hold stay alive)
 
 
 def _corpora(n):
