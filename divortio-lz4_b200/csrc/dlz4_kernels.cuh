@@ -39,6 +39,12 @@ __device__ unsigned long long g_phase[16];
 #define PT_USE(x)
 #endif
 
+#ifndef DLZ4_DEC_MINB
+#define DLZ4_DEC_MINB 6                 // resident CTAs of the block decoder per SM the register allocation is held to
+#endif
+#ifndef DLZ4_DEC_Q
+#define DLZ4_DEC_Q 2                    // sequences per step of the decoder's quick copy form
+#endif
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int kHashEntries = 16384;
 
@@ -1374,6 +1380,41 @@ __device__ uint32_t decompress_block_warp_v2(const uint8_t *__restrict__ in, con
         // ---- copies, in order
         const uint32_t pack = lit | (ml << 16);                  // both < 1024 here
         const bool anydict = kDict && __ballot_sync(FULL, dsrc != 0) != 0;
+        // ---- quick form: every sequence of the window is at most 32 bytes and its match source lies in front of the
+        //      window's own output (text: offsets of hundreds of bytes, sequences of ~15).  Then no copy of the window reads what
+        //      another one writes: two sequences per step, their loads issued together before the stores (the load-to-store
+        //      dependency of one sequence at a time was a third of the kernel's stall samples), two shuffles per sequence.
+        const uint32_t rel_o = myop - op;
+        const bool quick = adv <= 32u && offset >= rel_o + adv && dsrc == 0u;
+        if (good && !(good & ~__ballot_sync(FULL, quick))) {
+            const uint32_t pa = adv | (lit << 6) | ((litp - ip) << 12) | (rel_o << 18);      // 6 + 6 + 6 + 10 bits
+            uint8_t *const dw = ob + op + lane;
+            const uint8_t *const iw = in + ip + lane;
+            uint32_t m = good;
+            constexpr int kQ = DLZ4_DEC_Q;                                // sequences per step (4: 48 registers, fewer resident warps)
+            while (m) {
+                const uint8_t *sp[kQ];
+                uint8_t *dp[kQ];
+                bool pr[kQ];
+#pragma unroll
+                for (int u = 0; u < kQ; ++u) {
+                    const bool valid = m != 0u;
+                    const int l = valid ? __ffs(m) - 1 : 0;
+                    m &= m - 1u;
+                    const uint32_t a = __shfl_sync(FULL, pa, l), of = __shfl_sync(FULL, offset, l);
+                    const uint32_t tot = a & 63u, li = (a >> 6) & 63u;
+                    pr[u] = valid && lane < tot;
+                    dp[u] = dw + (a >> 18);
+                    sp[u] = lane < li ? iw + ((a >> 12) & 63u) : dp[u] - of;
+                }
+                uint8_t v[kQ];
+#pragma unroll
+                for (int u = 0; u < kQ; ++u) v[u] = pr[u] ? *sp[u] : (uint8_t)0;
+#pragma unroll
+                for (int u = 0; u < kQ; ++u) if (pr[u]) *dp[u] = v[u];
+            }
+            __syncwarp();
+        } else
         for (uint32_t m = good; m; m &= m - 1u) {
             const int l = __ffs(m) - 1;
             const uint32_t pk = __shfl_sync(FULL, pack, l), off_ = __shfl_sync(FULL, offset, l);
@@ -1435,7 +1476,7 @@ __device__ uint32_t decompress_block_warp_v2(const uint8_t *__restrict__ in, con
 // hist_frame != 0: block i's output array starts at dst[0] (history = dict ++ dst[0..dst_off[i]));
 // otherwise each block's array starts at its own dst_off[i].
 template <int WARPS, bool kDict>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, DLZ4_DEC_MINB)
 k_decompress_blocks(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
                     const uint32_t *__restrict__ src_len, uint32_t nblocks, uint8_t *dst,
                     const uint64_t *__restrict__ dst_off, const uint32_t *__restrict__ dst_cap,

@@ -145,3 +145,12 @@ def test_stateful_xxh32_digest_of_short_inputs_needs_no_device():
                 assert L.dlz4_xxh32_update(C.c_void_p(1), C.byref(s), arr.ctypes.data, 1) == 0
             assert L.dlz4_xxh32_digest(C.byref(s)) == oracle.xxh32(data, seed)
     assert L.dlz4_xxh32_digest(C.byref(s)) == oracle.xxh32(b"123456789012345", 7)
+
+
+def test_napi_addon_type_checks_against_the_header():
+    """addon/dlz4_napi.c (the binding INTEGRATION.md describes) compiles with -fsyntax-only -Wall -Wextra -Werror against
+    include/dlz4_b200.h and a hand-declared Node-API subset; every C-ABI entry point it calls exists with that signature."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["make", "-C", os.path.join(root, "addon"), "syntax"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
