@@ -73,3 +73,44 @@ def test_empty_and_tiny_streams():
     enc = RefEncoder(65536, True)
     f = b"".join(enc.add(b"abc") + enc.finish())
     assert oracle.decompress_buffer(f) == b"abc"
+
+
+# Header vectors derived by hand from the reference's writer (src/shared/lz4Encode.js:61-94: magic, FLG = version 1 << 6 |
+# blockIndependence 0x20 | contentChecksum 0x04 | dictId 0x01, BD = (bdId & 7) << 4, dictID little-endian, HC = second byte of
+# xxh32(FLG..dictID)) with the HC byte computed by the SYSTEM libxxhash (XXH32), not by the oracle; the first two are the
+# well-known headers every lz4 CLI file starts with.
+STREAM_HEADER_VECTORS = [
+    ((False, False, 7, None), "04224d184070df"),
+    ((True, True, 4, None), "04224d186440a7"),
+    ((True, False, 7, None), "04224d18607073"),
+    ((False, True, 5, None), "04224d184450e6"),
+    ((False, False, 7, 0x12345678), "04224d18417078563412d9"),
+    ((True, True, 6, 0xDEADBEEF), "04224d186560efbeaddecc"),
+]
+
+
+@pytest.mark.parametrize("args,want", STREAM_HEADER_VECTORS)
+def test_stream_header_bytes_match_hand_derived_vectors(args, want):
+    import jsref_stream
+    assert jsref_stream.create_frame_header(*args).hex() == want
+
+
+def test_stream_frames_with_a_dictionary_decode_in_liblz4():
+    """The dictId case end to end: a linked stream primed with a dictionary (lz4Encode.js:140-168) is decoded by liblz4's
+    LZ4F_decompress_usingDict (which also verifies the header checksum byte and the content checksum); the dictID field is
+    xxh32(dictionary) (lz4Encode.js:120)."""
+    import lz4f
+    if not lz4f.available():
+        pytest.skip("liblz4 not present")
+    rng = np.random.RandomState(5)
+    data = _data("log", 600000)
+    dic = _data("log", 150000)[20000:120000]
+    for indep in (False, True):
+        enc = RefEncoder(65536, indep, True, dic)
+        pieces = []
+        for c in _chunks(data, rng):
+            pieces += enc.add(c)
+        pieces += enc.finish()
+        frame = b"".join(pieces)
+        assert frame[4] & 0x01 and int.from_bytes(frame[6:10], "little") == oracle.xxh32(dic)
+        assert lz4f.decompress_frame(frame, len(data), dictionary=dic) == data
