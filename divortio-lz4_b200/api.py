@@ -117,6 +117,7 @@ def lib():
         "dlz4_xxh32_update": (C.c_int, [vp, C.POINTER(Xxh32State), vp, u64]),
         "dlz4_xxh32_digest": (u32, [C.POINTER(Xxh32State)]),
         "dlz4_chain_compress": (C.c_int, [vp, vp, u64, i32, i32, i32, vp, vp, u64, vp]),
+        "dlz4_stream_blocks": (C.c_int, [vp, vp, u64, vp, u64, i32, i32, i32, C.c_int, vp, vp, u64, C.POINTER(u64), vp]),
         "dlz4_frame_body_compress": (C.c_int, [vp, vp, u64, u32, C.c_int, C.POINTER(u64)]),
         "dlz4_frame_body_fetch": (C.c_int, [vp, vp, u64]),
         "dlz4_frame_header": (C.c_size_t, [C.POINTER(FrameOpts), u64, C.c_int, u32, vp]),
@@ -137,7 +138,7 @@ EXPORTED_SYMBOLS = [
     "dlz4_compress_blocks_dev", "dlz4_compress_blocks", "dlz4_decompress_blocks_dev", "dlz4_decompress_blocks",
     "dlz4_compress_block", "dlz4_decompress_block", "dlz4_xxh32_batch_dev", "dlz4_xxh32_stream_dev", "dlz4_xxh32", "dlz4_xxh32_async", "dlz4_xxh32_wait",
     "dlz4_xxh32_batch", "dlz4_frame_compress", "dlz4_frame_info", "dlz4_frame_decompress", "dlz4_frame_pack_dev", "dlz4_frames_decompress", "dlz4_frames_info", "dlz4_frame_decompress_ex", "dlz4_xxh32_reset", "dlz4_xxh32_update", "dlz4_xxh32_digest",
-    "dlz4_chain_compress", "dlz4_frame_body_compress", "dlz4_frame_body_fetch", "dlz4_frame_header", "dlz4_frame_decompress_range",
+    "dlz4_chain_compress", "dlz4_stream_blocks", "dlz4_frame_body_compress", "dlz4_frame_body_fetch", "dlz4_frame_header", "dlz4_frame_decompress_range",
     "dlz4_xxh32_update_resident",
 ]
 
@@ -449,6 +450,14 @@ class XXHash32(object):
         if b.size:
             self._ctx.check(lib().dlz4_xxh32_update(self._ctx.handle, C.byref(self._s), _ptr(b), b.size))
         return self
+
+    def update_resident(self, which):
+        """Continues over bytes the last frame / stream call left on the device (0: its input, 1: its decoded output) instead
+        of uploading them again; False when the state holds a partial stripe (the caller then updates from host bytes)."""
+        if self._s.memsize:
+            return False
+        self._ctx.check(lib().dlz4_xxh32_update_resident(self._ctx.handle, C.byref(self._s), int(which)))
+        return True
 
     def digest(self):
         return int(lib().dlz4_xxh32_digest(C.byref(self._s)))

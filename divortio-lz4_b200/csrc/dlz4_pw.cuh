@@ -315,6 +315,7 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
             const uint32_t *slot = ring + pw_slot(p);
             const uint32_t want = ((p >> 5) + 1u) & kPwGenMask;
             uint32_t ex;
+            PT_MARK(14)
             for (;;) {
                 ex = pw_lds(slot);
                 if (__all_sync(FULL, (ex >> 21) == want)) break;

@@ -88,22 +88,27 @@ class LZ4Encoder(object):
             self.hashTable = _jenkins_slots(self.buffer)
 
     # ---- add / finish ---------------------------------------------------------------------------------------------
+    # `buffer` holds what the reference's this.buffer holds BEFORE the chunk of the current add(): the window (dictSize bytes,
+    # at most 64 KiB) followed by the pending bytes of an incomplete block.  The new chunk is never appended to it: the C side
+    # joins the two pieces on the device (dlz4_stream_blocks), only the bytes behind the last full block are copied.
     def add(self, chunk):
         if self.isClosed:
             raise RuntimeError("Stream is closed")
         data = api.ensureBuffer(chunk)
         if data.size == 0:
             return []
-        if self.hasher:
-            self.hasher.update(data)
-        self.buffer = np.concatenate([self.buffer, data])
         results = []
         if not self.hasWrittenHeader:
             results.append(create_frame_header(self.blockIndependence, self.contentChecksum, self.bdId, self.dictId, self._ctx))
             self.hasWrittenHeader = True
-        full = (self.buffer.size - self.dictSize) // self.blockSize             # `while (buffer.length >= dictSize + blockSize)`
+        pending = self.buffer.size - self.dictSize
+        full = (pending + data.size) // self.blockSize                          # `while (buffer.length >= dictSize + blockSize)`
         if full:
-            results.extend(self._flush_blocks(full * self.blockSize))
+            take = full * self.blockSize - pending                              # bytes of `data` inside the full blocks
+            results.extend(self._flush_blocks(data[:take], full * self.blockSize))
+            data = data[take:]
+        if data.size:
+            self.buffer = np.concatenate([self.buffer, data])                    # < one block
         return results
 
     def finish(self):
@@ -115,48 +120,62 @@ class LZ4Encoder(object):
             frames.append(create_frame_header(self.blockIndependence, self.contentChecksum, self.bdId, self.dictId, self._ctx))
         rest = self.buffer.size - self.dictSize
         if rest > 0:
-            frames.extend(self._flush_blocks(rest))                              # full blocks, then the final short one
+            frames.extend(self._flush_blocks(np.zeros(0, dtype=np.uint8), rest))  # the final short block
         frames.append(_u32(0))
         if self.hasher:
             frames.append(_u32(self.hasher.digest()))
         return frames
 
-    # ---- _flushBlock over `total` pending bytes at once (:215-298) -------------------------------------------------
-    def _flush_blocks(self, total):
+    # ---- _flushBlock over `total` pending bytes at once (:215-298): working buffer = self.buffer ++ tail ---------------
+    def _flush_blocks(self, tail, total):
         bs = self.blockSize
         start = self.dictSize
+        head = self.buffer
         n = (total + bs - 1) // bs
-        lens = [min(bs, total - k * bs) for k in range(n)]
-        if self.blockIndependence:
-            # table cleared before every block (:240-242): fresh independent blocks, the dictionary prefix is never referenced
-            off = (np.arange(n, dtype=np.uint64) * bs) + np.uint64(start)
-            ln = np.array(lens, dtype=np.uint32)
-            dst, doff, clen = api.compress_blocks(self.buffer, off, ln, ctx=self._ctx)
-            comp = [dst[int(doff[k]):int(doff[k]) + int(clen[k])] for k in range(n)]
-            self.hashTable[:] = 0                                                # what the last block's fill(0) + parse leaves is not
-            self._table_stale = True                                             # observable: the next flush clears it again
+        cap = total + 8 * n + 64
+        body = np.empty(cap, dtype=np.uint8)
+        plen = np.zeros(n, dtype=np.uint32)
+        blen = C.c_uint64(0)
+        linked = not self.blockIndependence
+        if linked:
+            table = np.ascontiguousarray(self.hashTable, dtype=np.int32)
         else:
-            comp = api.chain_compress(self.buffer, start, total, bs, self.hashTable, ctx=self._ctx)
+            table = None
+        st = api.lib().dlz4_stream_blocks(self._ctx.handle, api._ptr(head), head.size, api._ptr(tail), tail.size, int(start), int(total),
+                                          int(bs), int(linked), api._ptr(table), api._ptr(body), cap, C.byref(blen), api._ptr(plen))
+        self._ctx.check(st)
+        if self.hasher:
+            # content checksum (:110, :181): bytes are flushed once and in order, so hashing every flush hashes the stream; the
+            # flushed bytes are still on the device
+            if not self.hasher.update_resident(0):
+                self.hasher.update(np.concatenate([head, tail])[start:start + total])
         out = []
+        mv = memoryview(body)
+        pos = 0
         for k in range(n):
-            raw = self.buffer[start + k * bs:start + k * bs + lens[k]]
-            c = comp[k]
-            if 0 < c.size < lens[k]:                                             # :263-273 stored-block rule
-                out.append(_u32(c.size) + c.tobytes())
-            else:
-                out.append(_u32(lens[k] | 0x80000000) + raw.tobytes())
+            e = pos + int(plen[k])
+            out.append(bytes(mv[pos:e]))                                         # [u32 size | stored bit][payload], :263-273
+            pos = e
         consumed_end = start + total
-        if not self.blockIndependence:
+        if linked:
             keep = min(consumed_end, MAX_WINDOW_SIZE)                             # :276-296 slide the window, rebase the table
             shift = consumed_end - keep
-            self.buffer = self.buffer[shift:].copy()
+            self.buffer = _tail_of(head, tail, consumed_end, keep)
             self.dictSize = keep
-            t = self.hashTable
-            self.hashTable = np.where(t > shift, t - shift, 0).astype(np.int32)
+            self.hashTable = np.where(table > shift, table - shift, 0).astype(np.int32)
         else:
-            self.buffer = self.buffer[consumed_end:].copy()
+            self.hashTable[:] = 0                                                # table cleared before every block (:240-242): what the
+            self.buffer = np.zeros(0, dtype=np.uint8)                            # last parse leaves is not observable
             self.dictSize = 0
         return out
+
+
+def _tail_of(head, tail, end, keep):
+    """The last `keep` bytes of (head ++ tail)[:end] as a new array."""
+    lo = end - keep
+    if lo >= head.size:
+        return tail[lo - head.size:end - head.size].copy()
+    return np.concatenate([head[lo:], tail[:end - head.size]])
 
 
 class _Pinned(object):
@@ -218,7 +237,7 @@ class LZ4Decoder(object):
                     raise api.LZ4Error(api.E_BAD_MAGIC, "LZ4: Invalid Magic Number")
                 del self.buffer[:4]
                 self.state = "header"
-                self.hasher = api.XXHash32(0, ctx=self._ctx) if self.verifyChecksum else None
+                self.hasher = None
             if self.state == "header":                                           # :134-178
                 if len(self.buffer) < 2:
                     break
@@ -241,6 +260,8 @@ class LZ4Decoder(object):
                     if actual != expected:
                         raise api.LZ4Error(api.E_DICT_OOB, "LZ4: Dictionary ID Mismatch. Header: 0x%x, Provided: 0x%x" % (expected, actual))
                 del self.buffer[:need]
+                # (the hasher only matters for a frame that carries a content checksum, :246-258)
+                self.hasher = api.XXHash32(0, ctx=self._ctx) if (self.verifyChecksum and self.hasContentChecksum) else None
                 self.state = "blocks"
             if self.state == "blocks":                                           # :181-243, every complete block at once
                 nblocks, pos, end_mark, body_end = 0, 0, False, 0
@@ -307,7 +328,8 @@ class LZ4Decoder(object):
             p += int(olen[k])
         decoded = out[:p]
         if self.hasher and p:
-            self.hasher.update(decoded)
+            if not self.hasher.update_resident(1):                                # the decoded bytes are still on the device
+                self.hasher.update(decoded)
         if not self.blockIndependence and p:                                     # _updateWindow, :278-304: the last 64 KiB
             if p >= MAX_WINDOW_SIZE:
                 self.window = decoded[p - MAX_WINDOW_SIZE:].copy()

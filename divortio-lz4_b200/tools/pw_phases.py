@@ -34,10 +34,10 @@ torch.cuda.synchronize()
 L.dlz4_phase_counters(cnt)
 v = list(cnt)
 print("%s %d MiB: %.2f ms (parse + encode)" % (kind, mib, e0.elapsed_time(e1)))
-wt = v[0] + v[1] + v[2] + v[3] + v[4] + v[5]
+wt = v[0] + v[1] + v[2] + v[3] + v[4] + v[5] + v[14]
 print("walker: %.0f cycles per block; path steps %d (%.1f B/step), cut steps %d, ring steps %d, batch steps %d, poll retries %d" %
       (wt / nblk, v[9], n / max(v[9], 1), v[10], v[11], v[12], v[15]))
-for i, nm in ((1, "path step: head + wait for ring entries"), (0, "path step: walk, insert, records"), (4, "cut steps (incl. slow probe)"),
+for i, nm in ((14, "path step: loop head, publish, slot address"), (1, "path step: poll / wait for ring entries"), (0, "path step: walk, insert, records"), (4, "cut steps (incl. slow probe)"),
               (2, "ring steps"), (3, "batch steps"), (5, "tail")):
     print("  %-44s %5.1f%%  %8.1f cycles per path step" % (nm, 100.0 * v[i] / max(wt, 1), v[i] / max(v[9], 1)))
 pt = v[6] + v[7] + v[8]

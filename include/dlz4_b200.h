@@ -225,6 +225,14 @@ uint32_t dlz4_xxh32_digest(const dlz4_xxh32_state *s);
  * the segment-parallel engine; the table returned is the serial loop's. */
 int dlz4_chain_compress(dlz4_ctx *ctx, const uint8_t *work, uint64_t work_len, int32_t start, int32_t total, int32_t block_size,
                         int32_t *table, uint8_t *dst, uint64_t dst_stride, uint32_t *comp_len);
+/* The same flush with the output already in frame-body form and the working buffer given as TWO host pieces that are joined
+ * on the device (head = 64 KiB window ++ pending bytes, tail = the caller's new chunk: no host-side concatenation).  Blocks of
+ * block_size tile [start, start + total) of head ++ tail.  linked != 0: one chain carrying `table` (in/out); linked == 0: fresh
+ * independent blocks (lz4Encode.js:240-242; table unused).  body <- [u32 size | stored bit][payload] per block with the
+ * stored-block rule of lz4Encode.js:263-273; piece_len[k] = length of block k's piece (4 + payload). */
+int dlz4_stream_blocks(dlz4_ctx *ctx, const uint8_t *head, uint64_t head_len, const uint8_t *tail, uint64_t tail_len, int32_t start,
+                       int32_t total, int32_t block_size, int linked, int32_t *table, uint8_t *body, uint64_t body_cap,
+                       uint64_t *body_len, uint32_t *piece_len);
 
 /* dlz4_frame_decompress that also reports every block's decoded length (block_out_len[nblocks], nullable): the stream
  * decoder hands out one chunk per block like LZ4Decoder.update (lz4Decode.js:206-245). */
