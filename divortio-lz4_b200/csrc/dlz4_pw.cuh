@@ -40,7 +40,10 @@ constexpr int kPwChainBytes = kHashEntries * 2 + kPwRingBytes + kPwCtl;
 constexpr uint32_t kPwRingSmc = 160u;         // the walker uses the ring while searchMatchCount <= this (steps of 1 and 2)
 constexpr uint32_t kPwDone = 0x80000000u, kPwSparse = 0x40000000u;
 constexpr bool kPwPrefetch = true;            // producers prefetch the second stage's lines and the next window pair's source lines
-constexpr uint32_t kPwCap = 64u;              // producers pre-extend a match to this many bytes; the walker continues a longer one
+#ifndef DLZ4_PW_CAP
+#define DLZ4_PW_CAP 32
+#endif
+constexpr uint32_t kPwCap = DLZ4_PW_CAP;              // producers pre-extend a match to this many bytes; the walker continues a longer one
 
 struct PwCtl {                                // one per chain, in shared memory
     volatile uint32_t w_pos;                  // walker's position (block-relative) | kPwSparse | kPwDone
@@ -207,7 +210,7 @@ __device__ __forceinline__ void pw_produce2(const uint8_t *__restrict__ base, co
     }
     const uint32_t va = wide_verify(qa0, qa1, qa2, csa, S), vb = wide_verify(qb0, qb1, qb2, csb, S + 8);     // 0 or 4..32
     uint32_t mla = oka ? va : 0u, mlb = okb ? vb : 0u;
-    if (__any_sync(FULL, mla == 32u || mlb == 32u)) {
+    if (kPwCap > 32u && __any_sync(FULL, mla == 32u || mlb == 32u)) {
         // second stage for the positions whose 32 bytes all matched: bytes 32..63 (:147-150 continued)
         if (mla == 32u) {
             const uint4 q3 = __ldg(cqa + 3), q4 = __ldg(cqa + 4);
@@ -223,7 +226,7 @@ __device__ __forceinline__ void pw_produce2(const uint8_t *__restrict__ base, co
             mlb += pw_count32(qb2, q3, q4, csb, S2);
         }
     }
-    if (!two && mla == 32u) {
+    if (kPwCap > 32u && !two && mla == 32u) {
         // last window of the block, produced alone: its bytes 32..63 come from a direct load
         uint32_t w2[9], S2[8];
 #pragma unroll
@@ -312,8 +315,8 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
             const uint32_t s = (uint32_t)sIndex, wbase = s & ~31u, sl = s & 31u;
             if (pub != wbase) { pub = wbase; if (lane == 0) ctl->w_pos = wbase; }
             const uint32_t p = wbase + lane;
-            const uint32_t *slot = ring + pw_slot(p);
             const uint32_t want = ((p >> 5) + 1u) & kPwGenMask;
+            const uint32_t *slot = ring + pw_slot(p);
             uint32_t ex;
             PT_MARK(14)
             for (;;) {
@@ -331,6 +334,8 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
             const uint32_t claim = __ballot_sync(FULL, ml != 0u);
             const bool probed = (PM >> lane) & 1u;
             const uint32_t tag = p & 0xFFFFu;
+            // two probed positions in one slot (the later one would find the earlier one's insert, not what its producer saw)
+            // show up when the tags are read back (match.any instead of the read-back: 920 against 500 cycles for this part)
             __syncwarp();                                                      // every lane holds its `cur` before any slot changes
             if (probed) tab[h] = (uint16_t)tag;                                 // :55
             __syncwarp();
