@@ -1,0 +1,2 @@
+cd /root/repo
+timeout 900 python -m pytest tests/test_gpu_blocks.py -x -q -m gpu -k fuzz 2>&1 | tail -12 | cut -c1-250

@@ -309,3 +309,54 @@ def test_packed_pipelined_host_path(dl):
     assert np.array_equal(oracle.xxh32_batch(dst, doff, clen), oracle.xxh32_batch(odst, odoff, oclen))
     out, olen, status = dl.decompress_blocks(dst, None, clen, off, ln)
     assert not status.any() and np.array_equal(olen, ln) and np.array_equal(out[:n], data)
+
+
+def _fuzz_block(rng, n):
+    """A block built from pieces that exercise different paths of the match finder: copies of earlier pieces at random distances
+    (short and long matches, same-slot pairs, stale table entries), runs, periodic patterns, text-like words, noise."""
+    words = [b"status=", b"GET ", b"/api/v1/", b"user", b"\n2026-10-", b"INFO ", b"error", b"=200 ", b"abcabc", b"    "]
+    out = bytearray()
+    while len(out) < n:
+        k = rng.randint(0, 8)
+        if k == 0 and len(out) > 8:                                  # copy of an earlier stretch
+            src = rng.randint(0, len(out) - 4)
+            ln = int(min(rng.choice([4, 5, 7, 12, 31, 32, 33, 63, 64, 65, 130, 300, 2000]), len(out) - src))
+            out += out[src:src + ln]
+        elif k == 1:                                                 # run
+            out += bytes([rng.randint(0, 256)]) * int(rng.choice([1, 3, 4, 5, 17, 64, 255, 256, 1000, 5000]))
+        elif k == 2:                                                 # periodic
+            p = rng.randint(1, 40)
+            unit = rng.bytes(p)
+            out += unit * int(rng.randint(1, 60))
+        elif k == 3:                                                 # noise
+            out += rng.bytes(int(rng.choice([1, 2, 3, 8, 40, 200, 3000])))
+        elif k == 4:                                                 # few-symbol noise (many hash collisions)
+            out += bytes(rng.randint(0, 3, size=int(rng.randint(4, 400))).astype(np.uint8))
+        else:                                                        # words
+            for _ in range(rng.randint(1, 12)):
+                out += words[rng.randint(0, len(words))]
+                if rng.randint(0, 3) == 0:
+                    out += str(rng.randint(0, 100000)).encode()
+    return bytes(out[:n])
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_compress_fuzz_random_structured_blocks_bit_exact(dl, seed):
+    """Differential fuzz of the producer/walker match finder against the oracle: 1500 random structured blocks of every length
+    class (empty, below the 13-byte minimum, around the window sizes 32 / 64 / 112, up to 64 KiB) in one batch, compressed bytes
+    compared one by one, then the batch decoded back."""
+    rng = np.random.RandomState(1000 + seed)
+    lens = [0, 1, 4, 5, 11, 12, 13, 14, 31, 32, 33, 63, 64, 65, 95, 96, 97, 111, 112, 113, 127, 128, 129, 143, 144, 145, 4095, 4096, 4097,
+            65535, 65536]
+    lens += [int(x) for x in rng.randint(0, 2000, size=600)] + [int(x) for x in rng.randint(2000, 65537, size=869)]
+    items = [_fuzz_block(rng, n) for n in lens]
+    buf, off, ln = _pack(items)
+    dst, doff, clen = dl.compress_blocks(buf, off, ln)
+    odst, odoff, oclen = oracle.compress_blocks(buf, off, ln)
+    bad = [i for i in range(len(items)) if clen[i] != oclen[i] or not np.array_equal(dst[int(doff[i]):int(doff[i]) + int(clen[i])],
+                                                                                       odst[int(odoff[i]):int(odoff[i]) + int(oclen[i])])]
+    assert not bad, ("blocks differ from the oracle", [(i, len(items[i])) for i in bad[:10]])
+    out, olen, status = dl.decompress_blocks(dst, doff, clen, off, ln)
+    assert not status.any() and np.array_equal(olen, ln)
+    for i in range(0, len(items), 37):
+        assert out[int(off[i]):int(off[i]) + int(ln[i])].tobytes() == items[i], i

@@ -234,3 +234,24 @@ def test_short_inner_blocks_decode_at_running_offsets(dl, with_size):
         assert dl.decompressBuffer(frame) == plain
         info = dl.frame_info(frame)
         assert info.nblocks == len(pieces)
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_frames_fuzz_random_structured_inputs(dl, seed):
+    """Differential fuzz of the frame paths (segment-parallel linked chains, large independent blocks, 64 KiB batches, dictionary
+    warm-up, jump decoder) on random structured inputs: frame bytes == oracle for random options, and back."""
+    from test_gpu_blocks import _fuzz_block
+    import lz4f
+    rng = np.random.RandomState(seed)
+    for case in range(5):
+        n = int(rng.randint(300000, 6000000))
+        data = np.frombuffer(_fuzz_block(rng, n), dtype=np.uint8)
+        bs = int(rng.choice([65536, 262144, 1048576, 4194304]))
+        indep, cc, bc = bool(rng.randint(0, 2)), bool(rng.randint(0, 2)), bool(rng.randint(0, 2))
+        dic = np.frombuffer(_fuzz_block(rng, int(rng.randint(100, 90000))), dtype=np.uint8) if rng.randint(0, 3) == 0 else None
+        want = oracle.compress_buffer(data, dic, bs, indep, cc, True, None, bc)
+        got = dl.compressBuffer(data, dic, bs, indep, cc, True, None, bc)
+        assert got == want, (seed, case, n, bs, indep, cc, bc, dic is not None)
+        assert dl.decompressBuffer(got, dic, True, bc) == data.tobytes(), (seed, case)
+        if lz4f.available() and dic is None:
+            assert lz4f.decompress_frame(got, n) == data.tobytes(), (seed, case)
