@@ -6,20 +6,22 @@
 // position is probed next) -- and the chain runs at the SUM of their latencies with the SM's issue slots 30 % used.  Here a
 // chain is a team of warps and the two halves overlap:
 //
-//   producers (kNP warps)   walk a FIXED grid of 32-position windows ahead of the parse.  For every position p of a window:
-//                           hash (:53), the table entry as it is at that moment, the candidate's bytes, verification and
-//                           pre-extension to 32 bytes (:63, :147-150).  Result: one 8-byte ring entry per position in shared
-//                           memory {slot, entry seen, match length against it, window number}.  Nothing a producer does
-//                           depends on the parse except the table entry it happened to read.
-//   walker (1 warp)         the serial loop itself, 32 upcoming probe positions per step (the skip schedule :66-67 makes them a
-//                           function of (sIndex, searchMatchCount)).  A lane takes its position's ring entry and the slot's
-//                           CURRENT value; if that equals the value the producer saw, the producer's match length is the
-//                           serial loop's (same candidate, same bytes).  The step ends at the first hit: lanes up to it tag
-//                           their slots (= the inserts of :55), the hit lane's match becomes a record.  Same-slot pairs among
-//                           the tagging lanes (read-back differs) and stale entries (slot changed since the producer looked)
-//                           cut the step in front of them; a stale position at the head of a step is probed the slow way,
-//                           from global memory.  Measured on log text (profiles/scratch/r02/pw_stats.c): 1.01 steps per
-//                           sequence, 3.3 % of the steps cut, 0.1-0.3 % of the probes stale with producers <= 128 positions ahead.
+//   producers (kNP warps)   walk a FIXED grid of 32-position windows ahead of the parse, two windows per iteration, two positions
+//                           per lane.  For every position p of a window: hash (:53), the table entry as it is at that
+//                           moment, the candidate's bytes, verification of the first 32 bytes (:63, :147-150).  Then the
+//                           producer RESOLVES THE SERIAL LOOP'S WALK through its window from every entry position at once
+//                           (pw_resolve, pointer doubling over next(i) = i + (match ? length : 1)): the set of positions the
+//                           loop probes if it arrives at p, and where it leaves the window.  One ring entry per position in
+//                           shared memory: x = {slot, match length, window number}, y = {entry seen, exit}, z = probed set.
+//                           Nothing a producer does depends on the parse except the table entry it happened to read.
+//   walker (1 warp)         the serial loop itself.  Per step it reads the entries of the window it stands in, takes the probed
+//                           set and the exit of its own position, and lets the probed lanes validate and insert themselves:
+//                           if every probed slot still holds what the producer saw, and no two probed positions share a slot
+//                           (tags read back), the producer's walk is the serial loop's -- the hits among the probed positions
+//                           are the records, the exit is the next position.  A same-slot pair or a stale entry cuts the step
+//                           in front of it; the position behind the cut is probed the slow way, from global memory.  Matches of
+//                           32 bytes and more end a walk and are measured by the walker (pw_extend).  Measured on log text:
+//                           34 bytes per step, 3 % of the steps cut with producers <= 7 windows ahead.
 //
 // The walker never waits for global memory on its common path (ring and table are shared memory), the producers never wait
 // for the walker except for ring space.  Sparse stretches (searchMatchCount > kPwRingSmc: incompressible data) and the last
@@ -48,7 +50,6 @@ constexpr uint32_t kPwCap = DLZ4_PW_CAP;              // producers pre-extend a 
 struct PwCtl {                                // one per chain, in shared memory
     volatile uint32_t w_pos;                  // walker's position (block-relative) | kPwSparse | kPwDone
     volatile uint32_t block;                  // block index of the team, 0xFFFFFFFF: no more work
-    volatile uint32_t nrec_pub;               // records the walker has written so far | kPwDone once the block is parsed (encoder warp)
 };
 
 __device__ __forceinline__ void pw_bar(uint32_t id, uint32_t nthreads) {
@@ -278,10 +279,8 @@ __device__ __forceinline__ void pw_producer(const uint8_t *__restrict__ base, co
 
 // ---- walker: the serial loop.  Returns the number of records written.
 __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, const int32_t len, const uint32_t nwin, uint16_t *tab,
-                                              const uint32_t *ring, PwCtl *ctl, uint64_t *__restrict__ rec, const uint32_t lane,
-                                              const bool publish_records) {
+                                              const uint32_t *ring, PwCtl *ctl, uint64_t *__restrict__ rec, const uint32_t lane) {
     const uint32_t lt = (1u << lane) - 1u;
-    uint32_t rpub = 0;                                                          // what ctl->nrec_pub holds
     const int32_t sEnd = len;
     const int32_t mflimit = sEnd - 12;                                          // blockCompress.js:34
     const int32_t matchLimit = sEnd - 5;                                        // :35
@@ -297,13 +296,6 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
     PT_DECL
 
     while (sIndex < mflimit) {                                                  // :48
-        if (publish_records && ((nrec ^ rpub) >> 5)) {
-            // another 32 records: hand them to the encoder warp (the records are plain global stores of several lanes)
-            __threadfence_block();
-            __syncwarp();
-            rpub = nrec;
-            if (lane == 0) ctl->nrec_pub = nrec;
-        }
         if (smc <= 96u && (sIndex | 31) < rlimit) {
             // ---- path step: while searchMatchCount stays below 128 the schedule steps by 1 (:66-67), so the parse inside an
             //      aligned window of 32 positions is a walk over the producers' match lengths: from a hit to the position
@@ -535,86 +527,17 @@ __device__ __forceinline__ uint32_t pw_walker(const uint8_t *__restrict__ base, 
     return nrec;
 }
 
-// ---- encoder warp: the block's bytes from the walker's records, 32 sequences per step, while the parse is still running
-//      (blockCompress.js:75-174 per match, :179-230 for the final literals; the loop body of k_encode_blocks)
-__device__ __forceinline__ uint32_t pw_encoder(const uint8_t *__restrict__ in, const uint32_t len, const uint64_t *rec, PwCtl *ctl,
-                                               uint8_t *__restrict__ out, const uint32_t lane) {
-    uint32_t D = 0, prev_end = 0, r0 = 0;                // output offset; end of the previous match (= mAnchor, :174); next record
-    for (;;) {
-        uint32_t pub = 0;
-        if (lane == 0) pub = ctl->nrec_pub;
-        pub = __shfl_sync(FULL, pub, 0);
-        uint32_t cnt = (pub & ~kPwDone) - r0;
-        if (cnt < 32u && !(pub & kPwDone)) { __nanosleep(512); continue; }
-        if (cnt == 0u) break;
-        cnt = cnt < 32u ? cnt : 32u;
-        const bool have = lane < cnt;
-        const uint2 rc = have ? __ldcg(reinterpret_cast<const uint2 *>(rec) + r0 + lane) : make_uint2(0u, 0u);
-        const uint32_t pos = rc.x & 0xFFFFu, ml = rc.y, offset = rc.x >> 16;
-        const uint32_t end = pos + ml;
-        uint32_t pe = __shfl_up_sync(FULL, end, 1);
-        if (lane == 0) pe = prev_end;
-        const uint32_t lit = have ? pos - pe : 0u;                                   // :74 litLen
-        const uint32_t code = ml - 4u;                                               // :160
-        const uint32_t litx = lit >= 15u ? 1u + (lit - 15u) / 255u : 0u;
-        const uint32_t mlx = have && code >= 15u ? 1u + (code - 15u) / 255u : 0u;
-        const uint32_t size = have ? 3u + litx + lit + mlx : 0u;
-        uint32_t incl = size;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
-        uint32_t d = D + incl - size;                        // this sequence's token
-        if (have) {
-            out[d++] = (uint8_t)(((lit < 15u ? lit : 15u) << 4) | (code < 15u ? code : 15u));   // :78-90, :161-170
-            if (lit >= 15u) {
-                uint32_t rest = lit - 15u;
-                while (rest >= 255u) { out[d++] = 255; rest -= 255u; }
-                out[d++] = (uint8_t)rest;
-            }
-        }
-        // literals (:92-140): short runs by their own lane, long ones by the whole warp
-        const uint32_t lits_at = d;
-        const bool longrun = have && lit > 24u;
-        if (have && !longrun) {
-            const uint8_t *sp = in + pe;
-            for (uint32_t k = 0; k < lit; ++k) out[d + k] = sp[k];
-        }
-        for (uint32_t mm = __ballot_sync(FULL, longrun); mm; mm &= mm - 1u) {
-            const int l = __ffs(mm) - 1;
-            const uint32_t o_ = __shfl_sync(FULL, lits_at, l), p_ = __shfl_sync(FULL, pe, l), n_ = __shfl_sync(FULL, lit, l);
-            warp_copy(out + o_, in + p_, n_, lane);
-        }
-        if (have) {
-            d += lit;
-            out[d] = (uint8_t)offset;                        // :156-157
-            out[d + 1] = (uint8_t)(offset >> 8);
-            d += 2;
-            if (code >= 15u) {
-                uint32_t rest = code - 15u;
-                while (rest >= 255u) { out[d++] = 255; rest -= 255u; }
-                out[d] = (uint8_t)rest;
-            }
-        }
-        D += __shfl_sync(FULL, incl, 31);
-        prev_end = __shfl_sync(FULL, end, cnt - 1u);
-        r0 += cnt;
-    }
-    __syncwarp();
-    uint8_t *e = emit_literals(out + D, SrcFlat{in}, (int32_t)prev_end, len - prev_end, 0u, lane);       // :179-230
-    return (uint32_t)(e - out);
-}
-
 // Fresh independent blocks <= 64 KiB as producer/walker teams.  CTA = kPwChains teams; warp t of a team: 0 = walker,
-// 1..kNP = producers, and with kEncode one more, the encoder (then the kernel is the whole compressor and writes dst / comp_len;
-// without it only the match records and their number, for k_encode_blocks).
-template <int kNP, bool kEncode>
-__global__ void __launch_bounds__(kPwChains * (1 + kNP + (kEncode ? 1 : 0)) * 32, 1)
+// 1..kNP = producers.  Output: the match records of every block and their number, for k_encode_blocks.  (An encoder warp
+// inside the team was measured: it delays the team's next block; the encoder stays a kernel of its own.)
+template <int kNP>
+__global__ void __launch_bounds__(kPwChains * (1 + kNP) * 32, 1)
 k_parse_pw(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ src_len,
            uint32_t nblocks, uint64_t *__restrict__ rec_base, uint64_t rec_stride /* records per block */,
            uint32_t *__restrict__ nrec_out, uint32_t *counter, uint32_t lead,
-           uint32_t full_ns /* a producer with a full ring sleeps this long: the ring buffers several windows */,
-           uint8_t *__restrict__ dst, const uint64_t *__restrict__ dst_off, uint32_t *__restrict__ comp_len) {
+           uint32_t full_ns /* a producer with a full ring sleeps this long: the ring buffers several windows */) {
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr uint32_t kRoles = 1 + kNP + (kEncode ? 1 : 0);
+    constexpr uint32_t kRoles = 1 + kNP;
     constexpr uint32_t kTeam = kRoles * 32;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t chain = warp / kRoles, role = warp % kRoles;
@@ -635,7 +558,6 @@ k_parse_pw(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off
             if (have_first) b = first; else b = qbase + atomicAdd(counter, 1u);
             ctl->block = b < nblocks ? b : 0xFFFFFFFFu;
             ctl->w_pos = 0u;
-            ctl->nrec_pub = 0u;
         }
         have_first = false;
         pw_bar(bar, kTeam);
@@ -643,7 +565,7 @@ k_parse_pw(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off
         if (b == 0xFFFFFFFFu) return;
         const uint32_t len = src_len[b];
         if (len > 65536u) {
-            if (role == 0 && lane == 0) { if (kEncode) comp_len[b] = 0xFFFFFFFFu; else nrec_out[b] = 0xFFFFFFFFu; }
+            if (role == 0 && lane == 0) nrec_out[b] = 0xFFFFFFFFu;
             continue;
         }
         {   // empty table (bufferCompress.js:182 / :235), invalid ring
@@ -657,17 +579,13 @@ k_parse_pw(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off
         // below it, 16-byte granules up to +79
         const uint32_t nwin = len >= 112u ? (len - 111u) / 32u + 1u : 0u;
         if (role == 0) {
-            const uint32_t n = pw_walker(base, (int32_t)len, nwin, tab, ring, ctl, rec, lane, kEncode);
-            if (kEncode) { __threadfence_block(); __syncwarp(); }
+            const uint32_t n = pw_walker(base, (int32_t)len, nwin, tab, ring, ctl, rec, lane);
             if (lane == 0) {
-                if (kEncode) ctl->nrec_pub = n | kPwDone; else nrec_out[b] = n;
+                nrec_out[b] = n;
                 ctl->w_pos = kPwDone;
             }
-        } else if (role <= (uint32_t)kNP) {
-            pw_producer<kNP>(base, nwin, lead, role - 1u, tab, ring, ctl, lane, full_ns);
         } else {
-            const uint32_t c = pw_encoder(base, len, rec, ctl, dst + dst_off[b], lane);
-            if (lane == 0) comp_len[b] = c;
+            pw_producer<kNP>(base, nwin, lead, role - 1u, tab, ring, ctl, lane, full_ns);
         }
     }
 }

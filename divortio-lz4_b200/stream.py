@@ -50,17 +50,11 @@ def _jenkins_slots(buf):
 
 
 def create_frame_header(block_independence, content_checksum, bd_id, dict_id, ctx=None):
-    """lz4Encode.js:61-94 (no content size in stream frames; a dictId of 0 counts as absent, `if (dictId)`)."""
-    flg = 1 << 6
-    if block_independence:
-        flg |= 0x20
-    if content_checksum:
-        flg |= 0x04
-    if dict_id:
-        flg |= 0x01
-    body = bytes([flg, (bd_id & 7) << 4]) + (_u32(dict_id) if dict_id else b"")
-    hc = (api.xxHash32(body, 0, ctx=ctx) >> 8) & 0xFF
-    return _u32(0x184D2204) + body + bytes([hc])
+    """lz4Encode.js:61-94 (no content size in stream frames; a dictId of 0 counts as absent, `if (dictId)`), written by the
+    library's one header writer (dlz4_frame_header)."""
+    from .sharded import frame_header
+    return frame_header(0, BLOCK_MAX_SIZES.get(bd_id & 7, 4194304), block_independence, content_checksum, False, False,
+                        dict_id if dict_id else None)
 
 
 class LZ4Encoder(object):
@@ -304,9 +298,9 @@ class LZ4Decoder(object):
         """The `nblocks` complete blocks in buffer[:body_end] as a synthetic frame (size words, data and block checksums as
         they came, copied once into page-locked memory): linked blocks see window ++ earlier output (:215-222,:240).  Block
         checksums are skipped like in the reference's stream decoder."""
-        flg = (1 << 6) | (0x20 if self.blockIndependence else 0) | (0x10 if self.hasBlockChecksum else 0)
-        body = bytes([flg, self._bd])
-        hdr = _u32(0x184D2204) + body + bytes([(api.xxHash32(body, 0, ctx=self._ctx) >> 8) & 0xFF])
+        from .sharded import frame_header
+        bmax = BLOCK_MAX_SIZES.get((self._bd >> 4) & 7, 4194304)
+        hdr = frame_header(0, bmax, self.blockIndependence, False, False, self.hasBlockChecksum)
         total = len(hdr) + body_end + 4
         f = self._pin_frame.get(total + 16)
         f[:len(hdr)] = np.frombuffer(hdr, dtype=np.uint8)
@@ -314,7 +308,6 @@ class LZ4Decoder(object):
         f[len(hdr):len(hdr) + body_end] = src
         del src                                                                  # (the bytearray is resized by the caller)
         f[len(hdr) + body_end:total] = 0                                         # EndMark
-        bmax = BLOCK_MAX_SIZES.get((self._bd >> 4) & 7, 4194304)
         out = self._pin_out.get(nblocks * bmax + 16)
         n = C.c_uint64(0)
         olen = np.zeros(nblocks, dtype=np.uint32)
