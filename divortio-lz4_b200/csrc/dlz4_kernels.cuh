@@ -710,38 +710,7 @@ __device__ __forceinline__ uint32_t next_block(uint32_t *counter, uint32_t lane)
 #include "dlz4_pw.cuh"
 namespace dlz4 {
 
-// Independent blocks <= 64 KiB, fresh table, no history: 16-bit table, 32 KiB of shared memory per warp.
-template <int WARPS, bool kWide>
-__global__ void __launch_bounds__(WARPS * 32, 1)
-k_compress_fresh16(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
-                   const uint32_t *__restrict__ src_len, uint32_t nblocks, uint8_t *__restrict__ dst,
-                   const uint64_t *__restrict__ dst_off, uint32_t *__restrict__ comp_len, uint32_t *counter) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    uint16_t *tab = reinterpret_cast<uint16_t *>(smem) + warp * kHashEntries;
-    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + WARPS * kHashEntries * 2 + warp * kRingBytes);
-    for (;;) {
-        const uint32_t b = next_block(counter, lane);
-        if (b >= nblocks) break;
-        const uint32_t len = src_len[b];
-        if (len > 65536u) { if (lane == 0) comp_len[b] = 0xFFFFFFFFu; continue; }
-        uint4 *t4 = reinterpret_cast<uint4 *>(tab);
-        for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
-        __syncwarp();
-        Tab16 T{tab, 0};
-        uint32_t c;
-        if (kWide) {
-            SpanState st{0, 0, 67u, 0u, 0u, -1};
-            c = compress_span64_warp<Tab16, true>(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], st, INT_MAX);
-        } else {
-            c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], ring);
-        }
-        if (lane == 0) comp_len[b] = c;
-        __syncwarp();
-    }
-}
-
-// Hybrid occupancy variant of k_compress_fresh16.  The parse is latency-bound (one dependent chain per block) and
+// Round-1 kernel for fresh blocks <= 64 KiB (kept as the A/B baseline, DLZ4_SPLIT=0).  The parse is latency-bound (one dependent chain per block) and
 // shared memory holds only 7 tables per SM, so most chains keep their table in L2-resident global scratch instead
 // (TabG16): a CTA is 7 warps = 1 chain on a shared-memory table + 6 chains on L2 tables, and 4 such CTAs share an SM
 // (28 chains, 64 registers each).  Small CTAs let the chunks of the host pipeline -- launched on different streams --
