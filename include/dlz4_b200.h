@@ -102,7 +102,8 @@ void dlz4_shard_range(uint64_t nblocks, uint32_t world, uint32_t rank, uint64_t 
  *   pipeline (H2D of chunk c+1, kernels of chunk c, D2H of chunk c-1 overlap), moving only real bytes over PCIe.
  *   dlz4_decompress_blocks accepts that layout with src_off == NULL.
  *   max_block_len: an upper bound of src_len[] known to the caller (0xFFFFFFFF if unknown); blocks of at most
- *   64 KiB with no prefix and DLZ4_WARM_NONE run on the 16-bit-table kernel (7 blocks in flight per SM instead of 3).
+ *   64 KiB with no prefix and DLZ4_WARM_NONE take the match finder + encoder pair (k_parse_pw, k_encode_blocks); batches of
+ *   uniform blocks > 64 KiB are cut into segments (the call then reads the descriptors back and synchronises the stream).
  */
 int dlz4_compress_blocks_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len,
                              uint32_t nblocks, uint32_t max_block_len, const uint8_t *prefix, uint32_t prefix_len, int warm,
@@ -117,6 +118,9 @@ int dlz4_compress_blocks(dlz4_ctx *ctx, const uint8_t *src, uint64_t src_bytes, 
  *   block i = src[src_off[i] .. +src_len[i]) decodes to dst[dst_off[i] ..) with capacity dst_cap[i];
  *   out_len[i] = bytes written, status[i] = 0 or DLZ4_E_* (1..4).  Returns the first non-zero status (host
  *   variant) or DLZ4_OK/CUDA error (_dev variant: read status[] yourself).
+ *   Batches of fewer than 1024 blocks without dictionary are inspected (descriptors read back, the stream synchronised): uniform
+ *   blocks > 64 KiB tiling one output range go to the jump decoder (parallel inside every block); everything else is one
+ *   warp per block, asynchronous on `stream`.
  */
 int dlz4_decompress_blocks_dev(dlz4_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_len,
                                uint32_t nblocks, uint8_t *dst, const uint64_t *dst_off, const uint32_t *dst_cap,
