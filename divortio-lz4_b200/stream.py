@@ -308,12 +308,17 @@ class LZ4Decoder(object):
         f[len(hdr):len(hdr) + body_end] = src
         del src                                                                  # (the bytearray is resized by the caller)
         f[len(hdr) + body_end:total] = 0                                         # EndMark
-        out = self._pin_out.get(nblocks * bmax + 16)
+        # output room: the library's own bound for this frame (sum of min(len * 255, blockMaxSize) over the blocks), not
+        # nblocks * blockMaxSize -- thousands of small blocks under a 4 MiB descriptor would ask for tens of GiB of pinned memory
+        info = api.FrameInfo()
+        self._ctx.check(api.lib().dlz4_frame_info(api._ptr(f), total, C.byref(info)))
+        cap = int(info.max_decoded)
+        out = self._pin_out.get(cap + 16)
         n = C.c_uint64(0)
         olen = np.zeros(nblocks, dtype=np.uint32)
         hist = self.window if (not self.blockIndependence and self.window.size) else None
         st = api.lib().dlz4_frame_decompress_ex(self._ctx.handle, api._ptr(f), total, api._ptr(hist), hist.size if hist is not None else 0, 0,
-                                                api._ptr(out), nblocks * bmax, C.byref(n), api._ptr(olen))
+                                                api._ptr(out), cap, C.byref(n), api._ptr(olen))
         self._ctx.check(st)
         chunks, p = [], 0
         for k in range(nblocks):
