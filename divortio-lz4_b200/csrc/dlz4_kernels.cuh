@@ -761,43 +761,6 @@ k_compress_fresh16h(const uint8_t *__restrict__ src, const uint64_t *__restrict_
     }
 }
 
-// Helper chains beside k_parse_pw.  The match finder's CTA fills an SM's shared memory with six tables, but it leaves a sixth
-// of the register file and half of the issue slots unused; this kernel's CTA (no table in shared memory: TabG16, L2-resident
-// global scratch, as the L2 warps of k_compress_fresh16h) fits into that rest and runs beside it, one CTA per SM.  Its warps
-// take whole blocks from the SAME work queue and compress them start to end (compress_block_warp_v2: match finder and
-// encoder in one), then mark the block as done for k_encode_blocks (kRecDone).  A helper chain is three to four times
-// slower than a team, so it stops taking blocks when fewer than `guard` are left in the queue: the teams finish the tail.
-constexpr int kHelpMaxWarps = 8;
-constexpr uint32_t kRecDone = 0xFFFFFFFEu;         // nrec value: the block's bytes are already written
-__global__ void __launch_bounds__(kHelpMaxWarps * 32, 4)
-k_compress_help(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ src_len,
-                uint32_t nblocks, uint8_t *__restrict__ dst, const uint64_t *__restrict__ dst_off, uint32_t *__restrict__ comp_len,
-                uint32_t *__restrict__ nrec_out, uint32_t *counter, uint32_t qbase /* queue index 0 is this block */,
-                uint32_t guard, uint16_t *gtabs /* gridDim.x * warps tables */) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    uint32_t *ring = reinterpret_cast<uint32_t *>(smem + warp * kRingBytes);
-    uint16_t *tab = gtabs + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * kHashEntries;
-    for (;;) {
-        uint32_t b = 0xFFFFFFFFu;
-        if (lane == 0) {
-            const uint32_t taken = *reinterpret_cast<volatile uint32_t *>(counter);
-            if ((uint64_t)qbase + taken + guard < (uint64_t)nblocks) b = qbase + atomicAdd(counter, 1u);
-        }
-        b = __shfl_sync(FULL, b, 0);
-        if (b >= nblocks) break;
-        const uint32_t len = src_len[b];
-        if (len > 65536u) { if (lane == 0) { comp_len[b] = 0xFFFFFFFFu; nrec_out[b] = kRecDone; } continue; }
-        uint4 *t4 = reinterpret_cast<uint4 *>(tab);
-        for (uint32_t i = lane; i < kHashEntries * 2 / 16; i += 32) __stcg(t4 + i, make_uint4(0, 0, 0, 0));
-        __syncwarp();
-        TabG16 T{tab, 0};
-        const uint32_t c = compress_block_warp_v2(src + src_off[b], 0, (int32_t)len, T, dst + dst_off[b], ring);
-        if (lane == 0) { comp_len[b] = c; nrec_out[b] = kRecDone; }
-        __syncwarp();
-    }
-}
-
 // Blocks of <= 4096 bytes behind a shared prefix, all starting from the same initial table (TabOv).  Same CTA shape as
 // k_compress_fresh16h: warp 0 keeps its overlay in shared memory, warps 1..6 in L2-resident global scratch.
 __global__ void __launch_bounds__(kHyWarps * 32, kHyCtasPerSm)

@@ -318,7 +318,6 @@ k_encode_blocks(const uint8_t *__restrict__ src, const uint64_t *__restrict__ sr
         if (b >= nblocks) break;
         const uint32_t n = nrec_in[b];
         if (n == 0xFFFFFFFFu) { if (lane == 0) comp_len[b] = 0xFFFFFFFFu; continue; }
-        if (n == 0xFFFFFFFEu) continue;                          // kRecDone: a helper chain wrote the block (k_compress_help)
         const uint8_t *in = src + src_off[b];
         const uint32_t len = src_len[b];
         const uint64_t *rec = rec_base + (uint64_t)b * rec_stride;

@@ -360,42 +360,3 @@ def test_compress_fuzz_random_structured_blocks_bit_exact(dl, seed):
     assert not status.any() and np.array_equal(olen, ln)
     for i in range(0, len(items), 37):
         assert out[int(off[i]):int(off[i]) + int(ln[i])].tobytes() == items[i], i
-
-
-@pytest.mark.parametrize("warps,guard", [(8, 0), (5, 64), (0, 0)])
-def test_helper_chains_beside_the_match_finder_bit_exact(dl, warps, guard):
-    """k_compress_help: whole blocks compressed by L2-table warps next to the k_parse_pw teams, from the same work queue.
-    With the tail guard at 0 the helpers keep taking blocks to the very end; every block must still be the oracle's."""
-    import os
-    from divortio_lz4_b200 import corpus
-    n = 80 * 1024 * 1024 + 4321
-    data = np.concatenate([corpus.mixed(21, n // 2), corpus.log(22, n - n // 2)])
-    off = np.arange(0, n, 65536, dtype=np.uint64)
-    ln = np.minimum(65536, n - off).astype(np.uint32)
-    old = {k: os.environ.get(k) for k in ("DLZ4_HELP", "DLZ4_HELP_GUARD", "DLZ4_CHUNK_MIB")}
-    os.environ.update({"DLZ4_HELP": str(warps), "DLZ4_HELP_GUARD": str(guard), "DLZ4_CHUNK_MIB": "128"})
-    try:
-        ctx = dl.Context(0)
-        l0 = ctx.launch_count
-        dst, doff, clen = dl.compress_blocks(data, off, ln, ctx=ctx)
-        launches = ctx.launch_count - l0
-    finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
-    odst, odoff, oclen = oracle.compress_blocks(data, off, ln)
-    assert np.array_equal(clen, oclen)
-    for i in range(len(off)):
-        a = dst[int(doff[i]):int(doff[i]) + int(clen[i])]
-        b = odst[int(odoff[i]):int(odoff[i]) + int(oclen[i])]
-        assert np.array_equal(a, b), i
-    out, olen, status = dl.decompress_blocks(dst, doff, clen, off, ln, ctx=ctx)
-    assert not status.any() and np.array_equal(out[:n], data)
-    test_helper_chains_beside_the_match_finder_bit_exact.launches[warps] = launches
-    if warps == 0 and 8 in test_helper_chains_beside_the_match_finder_bit_exact.launches:
-        assert test_helper_chains_beside_the_match_finder_bit_exact.launches[8] > launches      # the helper kernel did launch
-
-
-test_helper_chains_beside_the_match_finder_bit_exact.launches = {}
