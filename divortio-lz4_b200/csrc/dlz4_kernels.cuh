@@ -42,6 +42,9 @@ __device__ unsigned long long g_phase[16];
 #ifndef DLZ4_DEC_MINB
 #define DLZ4_DEC_MINB 6                 // resident CTAs of the block decoder per SM the register allocation is held to
 #endif
+#ifndef DLZ4_DEC_PREFETCH
+#define DLZ4_DEC_PREFETCH 1             // every real token of a window prefetches the line of its match source into L1
+#endif
 #ifndef DLZ4_DEC_Q
 #define DLZ4_DEC_Q 2                    // sequences per step of the decoder's quick copy form
 #endif
@@ -1343,6 +1346,11 @@ __device__ uint32_t decompress_block_warp_v2(const uint8_t *__restrict__ in, con
                 if (kDict && di >= 0 && srel + hist + (int64_t)ml <= 0) dsrc = (uint32_t)di + 1u;
                 else fine = false;
             }
+#if DLZ4_DEC_PREFETCH
+            // the match source is output this warp wrote a while ago: it sits in L2, one round trip per sequence.  Start all
+            // round trips of the window now; the copies below then find the lines on their way (or in L1).
+            else asm volatile("prefetch.global.L1 [%0];" ::"l"(ob + srel));
+#endif
         }
         const uint32_t notfine = real & ~__ballot_sync(FULL, fine);
         const uint32_t good = notfine ? (real & ((notfine & (0u - notfine)) - 1u)) : real;
@@ -1453,9 +1461,21 @@ k_decompress_blocks(const uint8_t *__restrict__ src, const uint64_t *__restrict_
                     const uint8_t *__restrict__ stored /* nullable: 1 = raw copy (frame stored block) */,
                     uint32_t *__restrict__ out_len, uint8_t *__restrict__ status, uint32_t *counter) {
     const uint32_t lane = lane_id();
+    // Queue order: a block of text keeps its warp busy for milliseconds -- about as long as the whole kernel runs on a mixed
+    // batch -- while runs and incompressible blocks take microseconds, so the queue is walked twice: first the blocks that
+    // look like work (compressed size between 1/16 and 15/16 of the room for the decoded bytes), then the rest, which fill the
+    // tail.  Only the order changes; with frame history one warp takes the blocks in their own order.
+    const bool twice = !hist_frame && nblocks <= 0x7FFFFFFFu;
+    const uint32_t qlen = twice ? 2u * nblocks : nblocks;
     for (;;) {
-        const uint32_t b = next_block(counter, lane);
-        if (b >= nblocks) break;
+        const uint32_t qi = next_block(counter, lane);
+        if (qi >= qlen) break;
+        const uint32_t b = qi < nblocks ? qi : qi - nblocks;
+        if (twice) {
+            const uint32_t cl = src_len[b], room = dst_cap[b];
+            const bool work = !(stored && stored[b]) && cl > (room >> 4) && cl + (room >> 4) < room;
+            if (work != (qi < nblocks)) continue;
+        }
         uint32_t st;
         uint32_t w;
         if (stored && stored[b]) {                               // bufferDecompress.js:147-149
