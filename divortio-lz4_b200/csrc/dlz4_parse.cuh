@@ -313,10 +313,16 @@ k_encode_blocks(const uint8_t *__restrict__ src, const uint64_t *__restrict__ sr
                 uint32_t nblocks, const uint64_t *__restrict__ rec_base, uint64_t rec_stride, const uint32_t *__restrict__ nrec_in,
                 uint8_t *__restrict__ dst, const uint64_t *__restrict__ dst_off, uint32_t *__restrict__ comp_len, uint32_t *counter) {
     const uint32_t lane = lane_id();
+    // the queue is walked twice: blocks with many sequences first (a text block takes a warp about as long as the whole kernel
+    // runs), the light ones fill the tail
+    const bool twice = nblocks <= 0x7FFFFFFFu;
+    const uint32_t qlen = twice ? 2u * nblocks : nblocks;
     for (;;) {
-        const uint32_t b = next_block(counter, lane);
-        if (b >= nblocks) break;
+        const uint32_t qi = next_block(counter, lane);
+        if (qi >= qlen) break;
+        const uint32_t b = qi < nblocks ? qi : qi - nblocks;
         const uint32_t n = nrec_in[b];
+        if (twice && (n != 0xFFFFFFFFu && n >= 256u) != (qi < nblocks)) continue;
         if (n == 0xFFFFFFFFu) { if (lane == 0) comp_len[b] = 0xFFFFFFFFu; continue; }
         const uint8_t *in = src + src_off[b];
         const uint32_t len = src_len[b];

@@ -1,6 +1,6 @@
 """End-to-end round trips of configs[1] through the host-pointer C ABI on page-locked buffers: the two calls of a step back to
 back on one context, and consecutive steps overlapped on two contexts (compress(k+1) beside decompress(k)).
-Usage: [CUDA_DEVICE_MAX_CONNECTIONS=32] python divortio-lz4_b200/tools/e2e_pipe.py [MiB] [steps] [priority-of-the-decode-context]"""
+Usage: [CUDA_DEVICE_MAX_CONNECTIONS=32] python divortio-lz4_b200/tools/e2e_pipe.py [MiB] [steps]"""
 import ctypes as C
 import os
 import sys
@@ -22,14 +22,10 @@ def pinned(L, n):
 def main():
     mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-    prio = sys.argv[3] if len(sys.argv) > 3 else ""
     n, B = mib << 20, 65536
     L = dl.lib()
     ctx = dl.Context(0)
-    if prio:
-        os.environ["DLZ4_PRIORITY"] = prio
     ctx2 = dl.Context(0)
-    os.environ.pop("DLZ4_PRIORITY", None)
     pin_in, host = pinned(L, n)
     corpus.mixed(2, n, out=host)
     nblk = (n + B - 1) // B
@@ -80,8 +76,8 @@ def main():
     t0 = time.perf_counter(); pipelined(steps); tp = (time.perf_counter() - t0) / steps
     for s in slots:
         assert np.array_equal(s[3][:n], host[:n])
-    print("%d MiB x %d steps, max_connections=%s, decode-context priority=%s: serial %.2f ms/step (compress %.2f + decompress %.2f) = %.2f GB/s | "
-          "overlapped %.2f ms/step = %.2f GB/s" % (mib, steps, os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "default"), prio or "default",
+    print("%d MiB x %d steps, max_connections=%s: serial %.2f ms/step (compress %.2f + decompress %.2f) = %.2f GB/s | "
+          "overlapped %.2f ms/step = %.2f GB/s" % (mib, steps, os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "default"),
                                                   ts * 1e3, tc * 1e3, td * 1e3, n / ts / 1e9, tp * 1e3, n / tp / 1e9), flush=True)
 
 
