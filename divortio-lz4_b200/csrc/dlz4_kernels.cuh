@@ -2137,26 +2137,43 @@ __device__ __forceinline__ uint32_t xxh32_quad(const uint8_t *p, uint32_t len, u
         uint32_t v = a == 0 ? seed + P32_1 + P32_2 : a == 1 ? seed + P32_2 : a == 2 ? seed : seed - P32_1;   // :29-32
         const uint8_t *q = p + 4 * a;
         uint32_t s = 0;
-        if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0) {
+        // eight stripes per step, their loads issued together; two dependent operations per stripe (see k_xxh32_stream):
+        // a' = (a >> 19)*P1 + (a*(P1 << 13) + x'*P2)
+        auto eight = [&](const uint32_t (&x)[8]) {
+            constexpr uint32_t K1 = P32_1 << 13;
+            uint32_t acc = v + x[0] * P32_2;
+#pragma unroll
+            for (int u = 1; u < 8; ++u) {
+                const uint32_t y = x[u] * P32_2;
+                uint32_t c;
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(c) : "r"(acc), "r"(K1), "r"(y));
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(acc >> 19), "r"(P32_1), "r"(c));
+            }
+            v = rotl32(acc, 13) * P32_1;
+        };
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+        if (mis == 0) {
             const uint32_t *w = reinterpret_cast<const uint32_t *>(q);
             for (; s + 8 <= nstripes; s += 8) {
                 uint32_t x[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) x[u] = w[(s + u) * 4];
-                // eight stripes with two dependent operations each (see k_xxh32_stream): a' = (a >> 19)*P1 + (a*(P1 << 13) + x'*P2)
-                constexpr uint32_t K1 = P32_1 << 13;
-                uint32_t acc = v + x[0] * P32_2;
-#pragma unroll
-                for (int u = 1; u < 8; ++u) {
-                    const uint32_t y = x[u] * P32_2;
-                    uint32_t c;
-                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(c) : "r"(acc), "r"(K1), "r"(y));
-                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(acc >> 19), "r"(P32_1), "r"(c));
-                }
-                v = rotl32(acc, 13) * P32_1;
+                eight(x);
             }
             for (; s < nstripes; ++s) v = xxh_round(v, w[s * 4]);
         } else {
+            // any alignment (the packed payloads of a frame body): the word from the two aligned words around it; the step that
+            // would read behind the last stripe is left to the loop below
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(q - mis);
+            const uint32_t sh = mis * 8u;
+            for (; s + 8 < nstripes; s += 8) {
+                uint32_t lo[8], hi[8], x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { lo[u] = w[(s + u) * 4]; hi[u] = w[(s + u) * 4 + 1]; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = __funnelshift_r(lo[u], hi[u], sh);
+                eight(x);
+            }
             for (; s < nstripes; ++s) v = xxh_round(v, ld32u(q + 16 * s));
         }
         const uint32_t base = lane_id() & ~3u;
@@ -2339,14 +2356,33 @@ k_frame_gather(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src
             }
             d += 4;
         }
-        const uint32_t head = static_cast<uint32_t>(-reinterpret_cast<intptr_t>(d)) & 3u;
+        // bytes up to the destination's next 16-byte boundary, then 16-byte stores whose source bytes come from aligned
+        // 16-byte loads realigned in registers, then the last bytes (all loads stay inside [s, s + sz))
+        const uint32_t head = static_cast<uint32_t>(-reinterpret_cast<intptr_t>(d)) & 15u;
         const uint32_t h = head < sz ? head : sz;
         if (threadIdx.x < h) d[threadIdx.x] = s[threadIdx.x];
-        const uint32_t nw = (sz - h) >> 2;
-        uint32_t *dw = reinterpret_cast<uint32_t *>(d + h);
         const uint8_t *sb = s + h;
-        for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) dw[i] = ld32u(sb + 4 * i);
-        const uint32_t done = h + (nw << 2);
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(sb) & 15u);
+        uint32_t nv = (sz - h) >> 4;
+        if (mis && nv) --nv;                                     // (the realigned form reads the granule behind each vector)
+        uint4 *dv = reinterpret_cast<uint4 *>(d + h);
+        if (mis == 0u) {
+            const uint4 *sv = reinterpret_cast<const uint4 *>(sb);
+            for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) dv[i] = __ldg(sv + i);
+        } else {
+            const uint4 *sv = reinterpret_cast<const uint4 *>(sb - mis);
+            const uint32_t wsel = mis >> 2, sh = (mis & 3u) * 8u;
+            for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) {
+                const uint4 a = __ldg(sv + i), c4 = __ldg(sv + i + 1);
+                const uint32_t v[8] = {a.x, a.y, a.z, a.w, c4.x, c4.y, c4.z, c4.w};
+                uint32_t t[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) t[k] = wsel == 0 ? v[k] : wsel == 1 ? v[k + 1] : wsel == 2 ? v[k + 2] : v[k + 3];
+                dv[i] = make_uint4(__funnelshift_r(t[0], t[1], sh), __funnelshift_r(t[1], t[2], sh),
+                                   __funnelshift_r(t[2], t[3], sh), __funnelshift_r(t[3], t[4], sh));
+            }
+        }
+        const uint32_t done = h + (nv << 4);                     // at most 31 bytes left
         if (threadIdx.x < sz - done) d[done + threadIdx.x] = s[done + threadIdx.x];
     }
 }

@@ -264,9 +264,10 @@ __device__ __forceinline__ void pw_producer(const uint8_t *__restrict__ base, co
     for (;;) {
         const uint32_t wpos = ctl->w_pos;
         if (wpos & kPwDone) break;
-        if (wpos & kPwSparse) { __nanosleep(256); PT_MARK(8) continue; }
+        if (wpos & kPwSparse) { __nanosleep(1024); PT_MARK(8) continue; }
         const uint32_t wk = wpos >> 5;
-        while (k + 1u < wk) k += 2u * (uint32_t)kNP;
+        // skip the window pairs the walker has left behind (a long match moves it by hundreds of windows at once)
+        if (k + 1u < wk) k += (wk - k - 2u + 2u * (uint32_t)kNP) / (2u * (uint32_t)kNP) * (2u * (uint32_t)kNP);
         if (k >= nwin) { __nanosleep(1024); PT_MARK(8) continue; }
         if (k + 1u >= wk + lead) { __nanosleep(full_ns); PT_MARK(7) continue; }
         if (kPwPrefetch && lane < 2u && k + 2u * (uint32_t)kNP < nwin) pw_prefetch(base + 32u * (k + 2u * (uint32_t)kNP) + 128u * lane);

@@ -2,8 +2,8 @@
 
 One process per GPU, one `dlz4_ctx` each.  Independent blocks shard with no data-path collective:
 
-  compress    the input is cut into frames of at most FRAME_MAX bytes (one frame call takes < 2 GiB like the reference,
-              bufferCompress.js:127 `len|0`; an 8 GiB input is 5 frames, which every LZ4 frame reader decodes as one stream of
+  compress    an input above FRAME_MAX bytes is cut into frames of FRAME_SPLIT bytes (one frame call takes < 2 GiB like the reference,
+              bufferCompress.js:127 `len|0`; an 8 GiB input is 8 frames, which every LZ4 frame reader decodes as one stream of
               concatenated frames).  Inside a frame, rank r owns the contiguous block range dlz4_shard_range(nblocks, world, r),
               compresses it on its GPU into the frame-body bytes of that range ([u32 size|stored][data][u32 xxh32]*, exactly
               what the single-GPU path writes for those blocks), the ranks exchange the LENGTHS of their bodies (one integer
@@ -41,6 +41,10 @@ from . import api
 MAGIC = b"\x04\x22\x4D\x18"
 BLOCK_SIZES = {4: 65536, 5: 262144, 6: 1048576, 7: 4194304}
 FRAME_MAX = (2 << 30) - (4 << 20)      # content bytes per frame: < 2 GiB (bufferCompress.js:127), whole blocks of every size
+FRAME_SPLIT = 1 << 30                  # an input above FRAME_MAX is written as frames of this many bytes: the content checksum is
+                                       # one serial chain per frame (2.4 GB/s), so more frames = more chains side by side, while
+                                       # the large-block compressor loses efficiency on short calls (8 GiB, one GPU, compress /
+                                       # decompress GB/s: 2 GiB frames 7.8 / 6.5, 1 GiB 9.4 / 8.8, 512 MiB 5.5 / 7.0)
 STATE_BYTES = C.sizeof(api.Xxh32State)
 
 
@@ -56,10 +60,15 @@ def block_id_for(max_block_size):
 
 
 def frame_spans(total_len, frame_max=FRAME_MAX):
-    """Byte ranges of the frames an input of total_len bytes is written as (an empty input is one empty frame)."""
+    """Byte ranges of the frames an input of total_len bytes is written as (an empty input is one empty frame).  Up to
+    frame_max bytes: one frame, the reference's own output.  More (the reference cannot take such an input at all): frames of
+    FRAME_SPLIT bytes -- of frame_max bytes when the caller sets a limit of its own."""
     if total_len == 0:
         return [(0, 0)]
-    return [(lo, min(lo + frame_max, total_len)) for lo in range(0, total_len, frame_max)]
+    if total_len <= frame_max:
+        return [(0, total_len)]
+    step = FRAME_SPLIT if frame_max == FRAME_MAX else frame_max
+    return [(lo, min(lo + step, total_len)) for lo in range(0, total_len, step)]
 
 
 shard_range = api.shard_range          # dlz4_shard_range: block i -> rank floor(i * world / nblocks), contiguous ranges

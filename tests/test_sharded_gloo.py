@@ -230,11 +230,13 @@ def test_plan_covers_every_block_once():
 
 
 def test_frame_spans_for_inputs_of_2_gib_and_more():
-    """DESIGN: an input of >= 2 GiB is written as ceil(n / (2 GiB - 4 MiB)) frames (each frame call takes len|0 < 2 GiB like
-    bufferCompress.js:127); the content size field of every frame is that frame's own length."""
+    """DESIGN: an input above 2 GiB - 4 MiB is written as ceil(n / 1 GiB) frames (each frame call takes len|0 < 2 GiB like
+    bufferCompress.js:127; more frames = more content-checksum chains side by side); the content size field of every frame is
+    that frame's own length."""
     from divortio_lz4_b200 import sharded
     spans = sharded.frame_spans(8 << 30)
-    assert len(spans) == 5 and spans[0] == (0, sharded.FRAME_MAX) and spans[-1][1] == 8 << 30
+    assert len(spans) == 8 and spans[0] == (0, sharded.FRAME_SPLIT) and spans[-1][1] == 8 << 30
+    assert sharded.frame_spans(sharded.FRAME_MAX) == [(0, sharded.FRAME_MAX)]            # up to the limit: the reference's one frame
     assert all((hi - lo) % (4 << 20) == 0 for lo, hi in spans[:-1]) and all(hi - lo < (2 << 30) for lo, hi in spans)
     assert sharded.frame_spans(0) == [(0, 0)] and sharded.frame_spans(5) == [(0, 5)]
     # a content size above 32 bits would be written in full (the header writer takes u64)
