@@ -188,6 +188,33 @@ def test_overlay_tables_ragged_messages_odd_prefixes(dl):
             assert not bad, (plen, mode, bad[:5])
 
 
+def test_overlay_caller_table_with_entries_beyond_16_bits(dl):
+    """A caller-supplied initial table may hold anything (Int32): positions beyond the prefix, -1, huge values must give the
+    oracle's bytes all the same (k_compress_overlay reads the table as it is)."""
+    from divortio_lz4_b200 import corpus
+    rng = np.random.RandomState(5)
+    nmsg = 3000
+    raw = corpus.jsonmsgs(11, 0, nmsg)
+    off = np.arange(nmsg, dtype=np.uint64) * 4096
+    ln = np.full(nmsg, 4096, dtype=np.uint32)
+    dic = corpus.json_dictionary(44)
+    primed = oracle.new_table()
+    oracle.compress_block(dic, 0, dic.size, primed)
+    weird = primed.copy()
+    idx = rng.choice(weird.size, size=4000, replace=False)
+    weird[idx[:1000]] = -1
+    weird[idx[1000:2000]] = rng.randint(65536, 70000, size=1000)          # inside the first message's virtual range
+    weird[idx[2000:3000]] = rng.randint(70000, 1 << 30, size=1000)
+    weird[idx[3000:]] = 65536                                            # position 65535 + 1: the last that fits is 65535
+    for tab in (weird, primed):
+        dst, doff, clen = dl.compress_blocks(raw, off, ln, prefix=dic, warm=dl.WARM_TABLE, init_table=tab)
+        odst, odoff, oclen = oracle.compress_blocks_prefix(dic, tab, raw, off, ln)
+        assert np.array_equal(clen, oclen)
+        bad = [i for i in range(nmsg) if not np.array_equal(dst[int(doff[i]):int(doff[i]) + int(clen[i])],
+                                                             odst[int(odoff[i]):int(odoff[i]) + int(oclen[i])])]
+        assert not bad, bad[:5]
+
+
 def test_decompress_edge_corpora(dl):
     corp = edge_corpora()
     names = list(corp)
