@@ -306,8 +306,10 @@ def compress_blocks(src, off, length, prefix=None, warm=WARM_NONE, init_table=No
     if packed:
         dst = np.empty(int((length.astype(np.uint64) + length.astype(np.uint64) // 255 + 16).sum()), dtype=np.uint8)
         comp = np.zeros(n, dtype=np.uint32)
-        st = lib().dlz4_compress_blocks(ctx.handle, _ptr(src), src.size, _ptr(off), _ptr(length), n, None, 0, WARM_NONE, None,
-                                        _ptr(dst), dst.size, None, _ptr(comp))
+        p = ensureBuffer(prefix) if prefix is not None else None
+        t = np.ascontiguousarray(init_table, dtype=np.int32) if init_table is not None else None
+        st = lib().dlz4_compress_blocks(ctx.handle, _ptr(src), src.size, _ptr(off), _ptr(length), n, _ptr(p),
+                                        p.size if p is not None else 0, int(warm), _ptr(t), _ptr(dst), dst.size, None, _ptr(comp))
         ctx.check(st)
         dst_off = np.zeros(n, dtype=np.uint64)
         if n:

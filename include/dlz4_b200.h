@@ -99,7 +99,8 @@ void dlz4_shard_range(uint64_t nblocks, uint32_t world, uint32_t rank, uint64_t 
  * Pointers of the _dev variants are device pointers (off/len arrays too).
  *   Host variant only: dst_off == NULL selects PACKED output -- block i is written directly behind block i-1 (its offset
  *   is the running sum of comp_len[]); blocks must then be ascending and disjoint in src, and the call runs as a chunked
- *   pipeline (H2D of chunk c+1, kernels of chunk c, D2H of chunk c-1 overlap), moving only real bytes over PCIe.
+ *   pipeline (H2D of chunk c+1, kernels of chunk c, D2H of chunk c-1 overlap), moving only real bytes over PCIe; prefix,
+ *   warm and init_table apply as in the strided form (uploaded once, before the first chunk).
  *   dlz4_decompress_blocks accepts that layout with src_off == NULL.
  *   max_block_len: an upper bound of src_len[] known to the caller (0xFFFFFFFF if unknown); blocks of at most
  *   64 KiB with no prefix and DLZ4_WARM_NONE take the match finder + encoder pair (k_parse_pw, k_encode_blocks); batches of

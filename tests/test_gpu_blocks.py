@@ -155,6 +155,13 @@ def test_compress_with_shared_prefix_three_table_modes(dl):
             assert np.array_equal(dst[int(doff[i]):int(doff[i]) + int(clen[i])],
                                   odst[int(odoff[i]):int(odoff[i]) + int(oclen[i])]), (mode, i)
         sizes[mode] = int(clen.sum())
+        # packed output through the chunked pipeline: the same blocks back to back
+        pdst, pdoff, pclen = dl.compress_blocks(msgs, off, ln, prefix=dic, warm=warm, init_table=init, packed=True)
+        assert np.array_equal(pclen, oclen), mode
+        want = np.concatenate([odst[int(odoff[i]):int(odoff[i]) + int(oclen[i])] for i in range(nmsg)])
+        assert np.array_equal(pdst, want), mode
+        pout, polen, pstatus = dl.decompress_blocks(pdst, None, pclen, off, ln, dictionary=dic, hist_mode=dl.HIST_RAW)
+        assert not pstatus.any() and np.array_equal(pout[:nmsg * 4096], msgs)
         # decode side: every message has its own output base whose index 0 is the dictionary boundary
         out, olen, status = dl.decompress_blocks(dst, doff, clen, off, ln, dictionary=dic, hist_mode=dl.HIST_RAW)
         assert not status.any() and np.array_equal(olen, ln)
