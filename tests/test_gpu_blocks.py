@@ -330,6 +330,32 @@ def test_xxh32_single_and_batch(dl):
     assert dl.xxHash32(b"") == 0x02CC5D05 and dl.xxHash32("Hello World") == 0xB1FD16EE   # reference KATs
 
 
+def test_xxh32_batch_every_alignment_and_stripe_boundary(dl):
+    """k_xxh32_batch hashes items at any byte alignment (the packed payloads of a frame body) eight stripes per step; lengths
+    around the 128-byte steps and the 16-byte stripes, every alignment 0..15, two seeds."""
+    rng = np.random.RandomState(123)
+    lens = [0, 1, 3, 4, 15, 16, 17, 31, 32, 127, 128, 129, 143, 144, 145, 159, 160, 255, 256, 257, 271, 272, 273, 1000, 4097, 65541]
+    items, off, pos = [], [], 0
+    parts = []
+    for a in range(16):
+        for n in lens:
+            pad = (a - pos) % 16
+            parts.append(bytes(pad))
+            pos += pad
+            d = rng.randint(0, 256, size=n, dtype=np.uint8).tobytes()
+            off.append(pos)
+            items.append(d)
+            parts.append(d)
+            pos += n
+    buf = np.frombuffer(b"".join(parts) + bytes(8), dtype=np.uint8)
+    off = np.array(off, dtype=np.uint64)
+    ln = np.array([len(d) for d in items], dtype=np.uint32)
+    assert sorted(set(int(o) % 16 for o in off)) == list(range(16))
+    for seed in (0, 0x9E3779B1):
+        got = dl.xxh32_batch(buf, off, ln, seed) if seed else dl.xxh32_batch(buf, off, ln)
+        assert got.tolist() == [oracle.xxh32(d, seed) for d in items], seed
+
+
 def test_packed_pipelined_host_path(dl):
     """dst_off == NULL: packed output through the chunked H2D/compute/D2H pipeline; bytes identical to the strided call."""
     from divortio_lz4_b200 import corpus
